@@ -1,0 +1,307 @@
+"""CPU restatement of the DiffUS B-mode renderer hot path.  TEST INFRASTRUCTURE ONLY.
+
+Every function cites the reference file:line (relative to the reference repo root) whose
+arithmetic it restates.  Written against torch so it runs in fp32 or fp64 and gives
+gradients through autograd; nothing here is imported by the product package.
+
+Pinned by: ``tests/golden/*.npz`` (outputs of the real reference, made by
+``oracle/make_golden.py``) and, when ``/root/reference`` is importable, live comparison in
+``tests/test_oracle_vs_reference.py``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+# ----------------------------------------------------------------------------------------
+# geometry  (src/cone.py:242-259)
+# ----------------------------------------------------------------------------------------
+
+
+def generate_cone_directions(direction_mri_world, opening_angle, n_rays) -> torch.Tensor:
+    """Fan of unit directions in the z=0 plane around a median direction.
+
+    Follows ``src/cone.py:242-259``: normalise the first two components ``d``;
+    ``ortho = (-d_y, d_x)``; ``a = linspace(-theta/2, theta/2, n)`` in float64;
+    ``v = cos(a) d + sin(a) ortho``; rows ``[v_x, v_y, 0]`` cast to float32.
+    """
+    d = np.asarray(direction_mri_world, dtype=np.float64)[:2]
+    d = d / np.linalg.norm(d)
+    ortho = np.array([-d[1], d[0]])
+    a = np.linspace(-opening_angle / 2, opening_angle / 2, n_rays)
+    v = np.cos(a)[:, None] * d[None, :] + np.sin(a)[:, None] * ortho[None, :]
+    out = np.zeros((n_rays, 3), dtype=np.float64)
+    out[:, :2] = v
+    return torch.tensor(out, dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# ray points and samplers  (src/renderer.py:119-124, :741-759)
+# ----------------------------------------------------------------------------------------
+
+
+def ray_points(source: torch.Tensor, directions: torch.Tensor, num_samples: int) -> torch.Tensor:
+    """``points[r, k] = source + k * directions[r]`` (``src/renderer.py:119-124``).
+
+    ``steps`` is a float32 arange; the product and the sum are separate roundings and the
+    result dtype follows torch promotion (fp64 directions/source give fp64 points).
+    """
+    if directions.ndim == 1:
+        directions = directions.unsqueeze(0)
+    steps = torch.arange(0, num_samples, dtype=torch.float32).view(1, -1, 1)
+    return source + steps * directions.unsqueeze(1)
+
+
+def nearest_indices(shape, points: torch.Tensor):
+    """Round-half-even, clamp to the volume (``src/renderer.py:751-756``)."""
+    D, H, W = shape
+    p = points.float()
+    x = torch.clamp(p[..., 0].round().long(), 0, D - 1)
+    y = torch.clamp(p[..., 1].round().long(), 0, H - 1)
+    z = torch.clamp(p[..., 2].round().long(), 0, W - 1)
+    return x, y, z
+
+
+def sample_nearest(volume: torch.Tensor, points: torch.Tensor):
+    """``Z[x, y, z]`` at the nearest voxel with border clamp (``src/renderer.py:754-759``)."""
+    x, y, z = nearest_indices(volume.shape, points)
+    return x, y, z, volume[x, y, z]
+
+
+def sample_trilinear(volume: torch.Tensor, points: torch.Tensor):
+    """Border-clamped trilinear interpolation at continuous index coordinates.
+
+    Restates what ``F.grid_sample(mode='bilinear', padding_mode='border',
+    align_corners=True)`` computes for the reference's notebook-era sampler
+    (``notebooks/[DEPR] fxiafixing_voxel_plot.ipynb`` cell 29; the same grid construction
+    survives at ``src/renderer.py:802-815``): each coordinate is clamped to
+    ``[0, size-1]`` first, ``i0 = floor``, weights ``(1-f, f)``, the ``+1`` corner clamped.
+    The derivative w.r.t. a coordinate is exactly zero when ``p <= 0`` or ``p >= size-1``
+    (ATen's ``clip_coordinates_set_grad``), which the ``where`` below reproduces.
+    """
+    D, H, W = volume.shape
+    pts = points.to(volume.dtype)
+    x, y, z = nearest_indices(volume.shape, points)
+    idx0, idx1, frac = [], [], []
+    for a, n in enumerate((D, H, W)):
+        p = pts[..., a]
+        inside = (p > 0) & (p < n - 1)
+        pc = torch.where(inside, p, p.detach().clamp(0, n - 1))
+        i0 = pc.detach().floor()
+        f = pc - i0
+        i0 = i0.long().clamp(0, n - 1)
+        i1 = (i0 + 1).clamp(max=n - 1)
+        idx0.append(i0)
+        idx1.append(i1)
+        frac.append(f)
+    val = 0
+    for cx in (0, 1):
+        wx = frac[0] if cx else 1 - frac[0]
+        ix = idx1[0] if cx else idx0[0]
+        for cy in (0, 1):
+            wy = frac[1] if cy else 1 - frac[1]
+            iy = idx1[1] if cy else idx0[1]
+            for cz in (0, 1):
+                wz = frac[2] if cz else 1 - frac[2]
+                iz = idx1[2] if cz else idx0[2]
+                val = val + volume[ix, iy, iz] * (wx * wy * wz)
+    return x, y, z, val
+
+
+# ----------------------------------------------------------------------------------------
+# reflection and propagation  (src/renderer.py:27-33, :367-457)
+# ----------------------------------------------------------------------------------------
+
+
+def reflection_coeff(Z1: torch.Tensor, Z2: torch.Tensor) -> torch.Tensor:
+    """Signed amplitude coefficient ``(Z2 - Z1) / (Z1 + Z2)`` (``src/renderer.py:33``)."""
+    return (Z2 - Z1) / (Z1 + Z2)
+
+
+def _layered_system(r: torch.Tensor):
+    """The ``2(n+1) x 2(n+1)`` system of ``src/renderer.py:384-405`` for ``n`` interfaces.
+
+    Unknowns ``[g0, d0, g1, d1, ..., gn, dn]`` (right- and left-going amplitudes);
+    ``g0 = 1``; ``dn = 0``; per interface i:
+    ``g_{i+1} = (1 + r_i) g_i + r_i d_{i+1}`` and ``d_i = r_i g_i + (1 - r_i) d_{i+1}``.
+    """
+    B, n = r.shape
+    size = 2 * (n + 1)
+    A = torch.zeros((B, size, size), dtype=r.dtype)
+    b = torch.zeros((B, size), dtype=r.dtype)
+    b[:, 0] = 1
+    A[:, 0, 0] = 1
+    A[:, -1, -1] = 1
+    if n:
+        i = torch.arange(n)
+        g, d, gn, dn = 2 * i, 2 * i + 1, 2 * i + 2, 2 * i + 3
+        A[:, gn, g] = -(1 + r)
+        A[:, gn, dn] = -r
+        A[:, gn, gn] = 1
+        A[:, d, g] = -r
+        A[:, d, dn] = -(1 - r)
+        A[:, d, d] = 1
+    return A, b
+
+
+def surface_return_dense(r: torch.Tensor) -> torch.Tensor:
+    """``d0`` of the truncated stacks, literally as the reference computes it.
+
+    For every truncation depth ``k = 0..N`` solve the dense system of the first ``k``
+    interfaces and keep ``d0`` (``src/renderer.py:407-408, :428-431``); NaNs become 0.
+    O(N^4) flops per ray -- this IS the reference's cost.
+    """
+    B, N = r.shape
+    cols = []
+    for k in range(N + 1):
+        A, b = _layered_system(r[:, :k])
+        w = torch.nan_to_num(torch.linalg.solve(A, b), nan=0.0)
+        cols.append(w[:, 1])
+    return torch.stack(cols, dim=1)
+
+
+def echo_dense_solve(r: torch.Tensor) -> torch.Tensor:
+    """Echo line of ``compute_echo_traces`` (``src/renderer.py:434-435, :453-454``).
+
+    The reference cumulative-sums ``d0`` over depth, then takes the first difference and
+    left-pads a zero, i.e. ``echo = [0, d0^(1), ..., d0^(N)]`` up to the rounding of the
+    cumsum round trip (kept here so fp32 runs reproduce the reference's own noise).
+    """
+    d0 = torch.cumsum(surface_return_dense(r), dim=1)
+    return torch.nn.functional.pad(d0[:, 1:] - d0[:, :-1], (1, 0))
+
+
+def echo_closed_form(r: torch.Tensor) -> torch.Tensor:
+    """Same echo line as :func:`echo_dense_solve` in O(N) per ray.
+
+    ``echo[k] = P_k[0,1] / P_k[1,1]`` with ``P_k = prod_{i<k} [[1-2 r_i^2, r_i], [-r_i, 1]]``
+    and ``echo[0] = 0`` -- eliminating the interior unknowns of the system at
+    ``src/renderer.py:393-405`` gives exactly this 2x2 transfer-matrix product.  NaN rule
+    of ``src/renderer.py:408``: once a NaN coefficient is included every later entry is 0.
+    Verified against the dense form and the live reference in the tests.
+    """
+    B, N = r.shape
+    one = torch.ones(B, dtype=r.dtype)
+    zero = torch.zeros(B, dtype=r.dtype)
+    p00, p01, p10, p11 = one, zero, zero, one
+    out = [zero]
+    for k in range(N):
+        rk = r[:, k]
+        a = 1 - 2 * rk * rk
+        p00, p01, p10, p11 = p00 * a - p01 * rk, p00 * rk + p01, p10 * a - p11 * rk, p10 * rk + p11
+        out.append(torch.nan_to_num(p01 / p11, nan=0.0))
+    return torch.stack(out, dim=1)
+
+
+def delays_us(n: int, spacing: float = 1.0, c: float = 1.54e3) -> torch.Tensor:
+    """Second return value of ``compute_echo_traces`` (``src/renderer.py:455``)."""
+    return 2 * spacing * torch.arange(n) / c
+
+
+# ----------------------------------------------------------------------------------------
+# the path itself  (src/renderer.py:35-71, :201-275)
+# ----------------------------------------------------------------------------------------
+
+
+def resolve_start(start, num_samples: int) -> int:
+    """``src/renderer.py:237-240``: a float start is a fraction of ``num_samples``."""
+    if type(start) is float:
+        start = int(start * num_samples)
+    if type(start) is int:
+        start = max(0, start)
+    return start
+
+
+def plot_beam_frame(volume, source, directions, num_samples, attenuation_coeff=0.5, start=0,
+                    sampler="nearest", propagation="closed_form"):
+    """``UltrasoundRenderer.plot_beam_frame`` with ``artifacts=False`` (``src/renderer.py:201-275``).
+
+    sample (``:228`` -> ``:57`` -> ``:178``) -> reflection (``:65-68``) -> start crop and
+    the median-over-rays replacement of column 0 (``:241-244``, restated out of place so
+    autograd works) -> echo line (``:251``) -> ``* exp(-alpha k)`` with k restarting at 0
+    after the crop (``:256-259``) -> ``(x[:, start:], y[:, start:], z[:, start:], frame)``.
+    """
+    pts = ray_points(source, directions, num_samples)
+    if sampler == "nearest":
+        x, y, z, imp = sample_nearest(volume, pts)
+    elif sampler == "trilinear":
+        x, y, z, imp = sample_trilinear(volume, pts)
+    else:
+        raise ValueError(sampler)
+    r = reflection_coeff(imp[:, :-1], imp[:, 1:])
+    start = resolve_start(start, num_samples)
+    if start > 0:
+        r = r[:, start:]
+        med = r[:, 0].median()
+        r = torch.cat([med.expand(r.shape[0], 1), r[:, 1:]], dim=1)
+    if propagation == "closed_form":
+        echo = echo_closed_form(r)
+    elif propagation == "dense":
+        echo = echo_dense_solve(r)
+    else:
+        raise ValueError(propagation)
+    depths = torch.arange(echo.shape[1]).float()
+    att = torch.exp(-attenuation_coeff * depths)
+    frame = echo * att[None, :]          # fp32 attenuation, promoted if the echo is fp64
+    return x[:, start:], y[:, start:], z[:, start:], frame
+
+
+# ----------------------------------------------------------------------------------------
+# MRI -> impedance MLP  (src/impedance.py:6-17)
+# ----------------------------------------------------------------------------------------
+
+
+def mlp_forward(x, w1, b1, w2, b2, w3, b3):
+    """``Linear(1,32)-ReLU-Linear(32,32)-ReLU-Linear(32,1)`` (``src/impedance.py:10-17``).
+
+    ``x`` (M, 1); weights in ``nn.Linear`` layout (out, in).
+    """
+    h1 = torch.relu(x @ w1.t() + b1)
+    h2 = torch.relu(h1 @ w2.t() + b2)
+    return h2 @ w3.t() + b3
+
+
+# ----------------------------------------------------------------------------------------
+# scan conversion  (src/renderer.py:694-737)  -- SURVEY row f1
+# ----------------------------------------------------------------------------------------
+
+
+def splat(x, y, z, intensities, H=256, W=256, sigma=2.0):
+    """``differentiable_splat`` (``src/renderer.py:694-737``).
+
+    Pick the two axes of largest coordinate variance (descending); round+clamp to pixels;
+    NON-accumulating indexed write of intensities and ones (duplicates: one write wins);
+    blur both with a normalised separable Gaussian of size ``int(6 sigma) | 1``; divide;
+    return transposed.
+    """
+    import torch.nn.functional as F
+    coords = [x, y, z]
+    variances = [c.float().var().item() for c in coords]
+    a0, a1 = sorted(range(3), key=lambda i: -variances[i])[:2]
+    c0 = coords[a0].to(torch.float32)
+    c1 = coords[a1].to(torch.float32)
+    val = intensities.to(torch.float32)
+    img = torch.zeros((1, 1, H, W))
+    wgt = torch.zeros_like(img)
+    i0 = torch.clamp(c0.round().long(), 0, W - 1)
+    i1 = torch.clamp(c1.round().long(), 0, H - 1)
+    img[0, 0, i1, i0] += val
+    wgt[0, 0, i1, i0] += 1
+    size = int(6 * sigma) | 1
+    t = torch.arange(size) - size // 2
+    k1 = torch.exp(-0.5 * (t / sigma) ** 2)
+    k1 = k1 / k1.sum()
+    k2 = (k1[:, None] @ k1[None, :])[None, None]
+    bi = F.conv2d(img, k2, padding=size // 2)
+    bw = F.conv2d(wgt, k2, padding=size // 2)
+    return (bi / (bw + 1e-8))[0, 0].T
+
+
+def flops_dense_per_ray(n_interfaces: int) -> float:
+    """Rough LU flop count of the reference's per-depth solves, for reporting only."""
+    return sum(2.0 / 3.0 * (2 * (k + 1)) ** 3 for k in range(n_interfaces + 1))
+
+
+__all__ = [n for n in dir() if not n.startswith("_") and n not in ("math", "np", "torch", "annotations")]
