@@ -1,0 +1,15 @@
+"""diffus_b200 -- B200-native DiffUS B-mode renderer hot path.
+
+Drop-in for ``UltrasoundRenderer.plot_beam_frame`` (+ ``generate_cone_directions`` and
+``ImpedanceEstimator``) of gduguey/DiffUS over hand-written sm_100a kernels behind a C ABI
+(``include/diffus_b200.h``).  Importing the package is cheap and works without a GPU; the
+first op call loads ``libdiffus_b200.so`` and fails loudly if it has not been built.
+"""
+from .cone import generate_cone_directions
+from .impedance import ImpedanceEstimator
+from .renderer import (PreparedVolume, UltrasoundRenderer, compute_echo_traces, custom_nearest_sampler,
+                       propagate_full_rays_batched, render_frames)
+
+__all__ = ["UltrasoundRenderer", "render_frames", "PreparedVolume", "compute_echo_traces",
+           "propagate_full_rays_batched", "custom_nearest_sampler", "generate_cone_directions",
+           "ImpedanceEstimator"]

@@ -1,0 +1,272 @@
+// extern "C" entry points of libdiffus_b200.so (see include/diffus_b200.h).
+// Argument validation and parameter packing only; kernels live in the other translation units.
+#include "common.cuh"
+#include "launch.h"
+
+using namespace diffus;
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int32_t check_volume(const DiffusVolume& v) {
+    if (!v.data) return DIFFUS_E_NULL;
+    if (v.dim[0] < 1 || v.dim[1] < 1 || v.dim[2] < 1) return DIFFUS_E_SHAPE;
+    if ((int64_t)v.dim[0] * v.dim[1] * v.dim[2] >= ((int64_t)1 << 40)) return DIFFUS_E_SHAPE;
+    if (v.layout != DIFFUS_LAYOUT_LINEAR && v.layout != DIFFUS_LAYOUT_BRICK) return DIFFUS_E_ENUM;
+    return DIFFUS_OK;
+}
+
+int32_t check_render(const DiffusRenderArgs* a, bool need_frame) {
+    if (!a) return DIFFUS_E_NULL;
+    int32_t e = check_volume(a->volume);
+    if (e) return e;
+    if (!a->sources || !a->directions) return DIFFUS_E_NULL;
+    if (need_frame && !a->frame) return DIFFUS_E_NULL;
+    if (a->pose_dtype != DIFFUS_POSE_F32 && a->pose_dtype != DIFFUS_POSE_F64) return DIFFUS_E_ENUM;
+    if (a->sampler != DIFFUS_SAMPLER_NEAREST && a->sampler != DIFFUS_SAMPLER_TRILINEAR) return DIFFUS_E_ENUM;
+    if (a->n_poses < 1 || a->n_rays < 1 || a->n_samples < 2) return DIFFUS_E_SHAPE;
+    if (a->n_samples > (1 << 24)) return DIFFUS_E_SHAPE;             // k must be exact in float32
+    if (a->start < 0 || a->start > a->n_samples - 2) return DIFFUS_E_SHAPE;
+    if (a->dir_pose_stride != 0 && a->dir_pose_stride != a->n_rays * 3) return DIFFUS_E_SHAPE;
+    if (a->n_poses * a->n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
+    if (a->start > 0 && a->n_rays > 12288) return DIFFUS_E_UNSUPPORTED; // median kernel keeps a pose's rays in smem
+    return DIFFUS_OK;
+}
+
+RenderParams pack(const DiffusRenderArgs* a) {
+    RenderParams p{};
+    p.vol.data = a->volume.data;
+    p.vol.D = a->volume.dim[0];
+    p.vol.H = a->volume.dim[1];
+    p.vol.W = a->volume.dim[2];
+    p.vol.nbj = (p.vol.H + BRICK_J - 1) / BRICK_J;
+    p.vol.nbk = (p.vol.W + BRICK_K - 1) / BRICK_K;
+    p.sources = a->sources;
+    p.directions = a->directions;
+    p.dir_pose_stride = a->dir_pose_stride;
+    p.product_f32 = a->product_f32;
+    p.n_poses = a->n_poses;
+    p.n_rays = a->n_rays;
+    p.total_rays = a->n_poses * a->n_rays;
+    p.S = a->n_samples;
+    p.start = a->start;
+    p.Sout = a->n_samples - a->start;
+    p.nseg = (p.Sout + SEG - 1) / SEG;
+    p.alpha = a->attenuation;
+    p.frame = a->frame;
+    p.seg_prefix = a->seg_prefix;
+    return p;
+}
+
+// forward workspace (start > 0): [median float P | argmedian int32 P]
+struct FwdWorkspace {
+    float* median;
+    int32_t* argmedian;
+    int64_t bytes;
+};
+FwdWorkspace fwd_workspace(const DiffusRenderArgs* a, void* base) {
+    FwdWorkspace w{};
+    int64_t off = 0;
+    if (a->start > 0) {
+        w.median = (float*)((char*)base + off);
+        off += align_up(a->n_poses * 4, 256);
+        w.argmedian = (int32_t*)((char*)base + off);
+        off += align_up(a->n_poses * 4, 256);
+    }
+    w.bytes = off;
+    return w;
+}
+
+// backward workspace: [fwd workspace | source partials (P*R*3) | direction scratch (P*R*3) | first_rbar (P*R)]
+struct BwdWorkspace {
+    FwdWorkspace fwd;
+    float* src_partial;
+    float* dir_scratch;
+    float* first_rbar;
+    int64_t bytes;
+};
+BwdWorkspace bwd_workspace(const DiffusRenderBwdArgs* b, void* base) {
+    BwdWorkspace w{};
+    const DiffusRenderArgs* a = &b->fwd;
+    w.fwd = fwd_workspace(a, base);
+    int64_t off = w.fwd.bytes;
+    int64_t rays = a->n_poses * a->n_rays;
+    bool pose_grad = a->sampler == DIFFUS_SAMPLER_TRILINEAR && (b->grad_sources || b->grad_directions);
+    if (pose_grad) {
+        w.src_partial = (float*)((char*)base + off);
+        off += align_up(rays * 12, 256);
+        if (!b->grad_directions) {
+            w.dir_scratch = (float*)((char*)base + off);
+            off += align_up(rays * 12, 256);
+        }
+    }
+    if (a->start > 0) {
+        w.first_rbar = (float*)((char*)base + off);
+        off += align_up(rays * 4, 256);
+    }
+    w.bytes = off;
+    return w;
+}
+
+int32_t cuda_rc(cudaError_t e) { return e == cudaSuccess ? DIFFUS_OK : (int32_t)e; }
+
+}  // namespace
+
+extern "C" {
+
+int32_t diffus_abi_version(void) { return DIFFUS_ABI_VERSION; }
+
+const char* diffus_error_string(int32_t code) {
+    switch (code) {
+        case DIFFUS_OK: return "ok";
+        case DIFFUS_E_NULL: return "a required pointer is NULL";
+        case DIFFUS_E_SHAPE: return "non-positive or inconsistent sizes";
+        case DIFFUS_E_ENUM: return "unknown sampler / layout / dtype tag";
+        case DIFFUS_E_WORKSPACE: return "workspace missing or too small";
+        case DIFFUS_E_UNSUPPORTED: return "unsupported configuration";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int64_t diffus_render_workspace_bytes(const DiffusRenderArgs* a) {
+    if (!a) return 0;
+    return fwd_workspace(a, nullptr).bytes;
+}
+
+int32_t diffus_render_forward(const DiffusRenderArgs* a, void* stream) {
+    int32_t e = check_render(a, true);
+    if (e) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    RenderParams p = pack(a);
+    const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;
+    if (a->start > 0) {
+        FwdWorkspace w = fwd_workspace(a, a->workspace);
+        if (!a->workspace || a->workspace_bytes < w.bytes) return DIFFUS_E_WORKSPACE;
+        cudaError_t ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.median, w.argmedian, st);
+        if (ce != cudaSuccess) return (int32_t)ce;
+        p.median = w.median;
+    }
+    return cuda_rc(launch_render_fwd(p, a->sampler, a->volume.layout, pose64, st));
+}
+
+int64_t diffus_render_bwd_workspace_bytes(const DiffusRenderBwdArgs* b) {
+    if (!b) return 0;
+    return bwd_workspace(b, nullptr).bytes;
+}
+
+int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
+    if (!b) return DIFFUS_E_NULL;
+    const DiffusRenderArgs* a = &b->fwd;
+    int32_t e = check_render(a, false);
+    if (e) return e;
+    if (!b->grad_frame) return DIFFUS_E_NULL;
+    const bool trilinear = a->sampler == DIFFUS_SAMPLER_TRILINEAR;
+    const bool pose_grad = trilinear && (b->grad_sources || b->grad_directions);
+    const bool vol_grad = b->grad_volume != nullptr;
+    if (!pose_grad && !vol_grad) return DIFFUS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    RenderParams p = pack(a);
+    if (p.nseg > 1 && !a->seg_prefix) return DIFFUS_E_NULL;
+    BwdWorkspace w = bwd_workspace(b, b->workspace);
+    if (w.bytes > 0 && (!b->workspace || b->workspace_bytes < w.bytes)) return DIFFUS_E_WORKSPACE;
+    const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;
+    cudaError_t ce;
+    if (a->start > 0) {
+        ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.fwd.median, w.fwd.argmedian, st);
+        if (ce != cudaSuccess) return (int32_t)ce;
+        p.median = w.fwd.median;
+        p.first_rbar = w.first_rbar;
+    }
+    p.grad_frame = b->grad_frame;
+    p.grad_volume = b->grad_volume;
+    p.grad_src_partial = w.src_partial;
+    p.grad_dir = b->grad_directions ? b->grad_directions : w.dir_scratch;
+    ce = launch_render_bwd(p, a->sampler, a->volume.layout, pose64, pose_grad, vol_grad, st);
+    if (ce != cudaSuccess) return (int32_t)ce;
+    if (a->start > 0) {
+        ce = launch_median_backward(p, a->sampler, a->volume.layout, pose64, w.fwd.argmedian, pose_grad, vol_grad, st);
+        if (ce != cudaSuccess) return (int32_t)ce;
+    }
+    if (pose_grad && b->grad_sources) {
+        ce = launch_reduce_rays(w.src_partial, a->n_poses, a->n_rays, b->grad_sources, st);
+        if (ce != cudaSuccess) return (int32_t)ce;
+    }
+    return DIFFUS_OK;
+}
+
+int32_t diffus_ray_indices(const DiffusRenderArgs* a, int64_t* x, int64_t* y, int64_t* z, void* stream) {
+    int32_t e = check_render(a, false);
+    if (e) return e;
+    if (!x || !y || !z) return DIFFUS_E_NULL;
+    RenderParams p = pack(a);
+    return cuda_rc(launch_ray_indices(p, a->pose_dtype == DIFFUS_POSE_F64, x, y, z, (cudaStream_t)stream));
+}
+
+int32_t diffus_trace_values(const DiffusRenderArgs* a, float* out, void* stream) {
+    int32_t e = check_render(a, false);
+    if (e) return e;
+    if (!out) return DIFFUS_E_NULL;
+    RenderParams p = pack(a);
+    return cuda_rc(launch_trace_values(p, a->sampler, a->volume.layout, a->pose_dtype == DIFFUS_POSE_F64, out,
+                                       (cudaStream_t)stream));
+}
+
+int32_t diffus_echo_forward(const float* refl, int64_t n_rays, int32_t n_interfaces, float* echo, void* stream) {
+    if (!refl || !echo) return DIFFUS_E_NULL;
+    if (n_rays < 1 || n_interfaces < 1 || n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_echo_fwd(refl, n_rays, n_interfaces, echo, (cudaStream_t)stream));
+}
+
+int32_t diffus_echo_backward(const float* refl, const float* grad_echo, int64_t n_rays, int32_t n_interfaces,
+                             float* grad_refl, void* stream) {
+    if (!refl || !grad_echo || !grad_refl) return DIFFUS_E_NULL;
+    if (n_rays < 1 || n_interfaces < 1 || n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_echo_bwd(refl, grad_echo, n_rays, n_interfaces, grad_refl, (cudaStream_t)stream));
+}
+
+int32_t diffus_cone_directions(const double* median, int64_t n_poses, int64_t n_rays, double opening_angle, float* out,
+                               void* stream) {
+    if (!median || !out) return DIFFUS_E_NULL;
+    if (n_poses < 1 || n_rays < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_cone_directions(median, n_poses, n_rays, opening_angle, out, (cudaStream_t)stream));
+}
+
+int32_t diffus_mlp_forward(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
+                           float fill, float* out, void* stream) {
+    if (!params || !x || !out) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_mlp_fwd(params, x, mask, n, out_scale, fill, out, (cudaStream_t)stream));
+}
+
+int64_t diffus_mlp_bwd_workspace_bytes(int64_t n) { return n < 1 ? 0 : mlp_bwd_workspace_bytes(n); }
+
+int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                            float out_scale, float* grad_params, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+    if (!params || !x || !grad_out || !grad_params) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    if (!workspace || workspace_bytes < mlp_bwd_workspace_bytes(n)) return DIFFUS_E_WORKSPACE;
+    return cuda_rc(launch_mlp_bwd(params, x, mask, grad_out, n, out_scale, grad_params, workspace, (cudaStream_t)stream));
+}
+
+int64_t diffus_brick_elems(const int32_t dim[3]) {
+    if (!dim) return 0;
+    int64_t nbi = (dim[0] + BRICK_I - 1) / BRICK_I, nbj = (dim[1] + BRICK_J - 1) / BRICK_J,
+            nbk = (dim[2] + BRICK_K - 1) / BRICK_K;
+    return nbi * nbj * nbk * 32;
+}
+
+int32_t diffus_volume_to_bricks(const float* linear, const int32_t dim[3], float* bricks, void* stream) {
+    if (!linear || !dim || !bricks) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_to_bricks(linear, dim, bricks, (cudaStream_t)stream));
+}
+
+int32_t diffus_bricks_to_volume(const float* bricks, const int32_t dim[3], float* linear, void* stream) {
+    if (!linear || !dim || !bricks) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_from_bricks(bricks, dim, linear, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+// Small kernels around the march: start>0 median, index/value outputs, reductions, fans, bricks.
+#include "common.cuh"
+#include "launch.h"
+
+namespace diffus {
+
+// ---------------------------------------------------------------------------------------
+// start > 0: the first kept reflection coefficient of every ray of a pose is replaced by
+// the LOWER median over the pose's rays (torch.median), reference src/renderer.py:241-244.
+// One CTA per pose; rank by counting (R is a few hundred at most).
+// ---------------------------------------------------------------------------------------
+template <int SAMPLER, int LAYOUT, bool POSE64>
+__global__ void first_refl_median_kernel(const RenderParams p, float* __restrict__ median, int32_t* __restrict__ argmedian) {
+    extern __shared__ float vals[];
+    const int64_t pose = blockIdx.x;
+    const int R = (int)p.n_rays;
+    for (int ray = threadIdx.x; ray < R; ray += blockDim.x) {
+        RaySetup<POSE64> rs;
+        rs.load(p.sources, p.directions, pose, ray, p.n_rays, p.dir_pose_stride, p.product_f32);
+        float g[3];
+        int k = p.start;
+        float z0 = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
+        float z1 = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k + 1), rs.coord(1, k + 1), rs.coord(2, k + 1), g);
+        vals[ray] = (z1 - z0) / (z0 + z1);
+    }
+    __syncthreads();
+    const int target = (R - 1) / 2;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        float v = vals[i];
+        if (v != v) {                     // torch.median propagates NaN
+            median[pose] = v;
+            argmedian[pose] = i;
+            continue;
+        }
+        int rank = 0, nan_seen = 0;
+        for (int j = 0; j < R; ++j) {
+            float w = vals[j];
+            nan_seen |= (w != w);
+            rank += (w < v) || (w == v && j < i);
+        }
+        if (!nan_seen && rank == target) {
+            median[pose] = v;
+            argmedian[pose] = i;
+        }
+    }
+}
+
+cudaError_t launch_first_refl_median(const RenderParams& p, int sampler, int layout, int pose64, float* median,
+                                     int32_t* argmedian, cudaStream_t st) {
+    int threads = (int)min((int64_t)256, ((p.n_rays + 31) / 32) * 32);
+    size_t smem = (size_t)p.n_rays * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    DIFFUS_DISPATCH(first_refl_median_kernel<S_, L_, P64_><<<(unsigned)p.n_poses, threads, smem, st>>>(p, median, argmedian);
+                    return cudaGetLastError())
+    return cudaErrorInvalidValue;
+}
+
+// Gradient of the median replacement: the summed d loss / d r_1 of a pose flows into the
+// two impedances of the median ray's first interface.  One warp per pose; runs after the
+// main backward kernel and before the ray reduction.
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD>
+__global__ void median_backward_kernel(const RenderParams p, const int32_t* __restrict__ argmedian) {
+    const int64_t pose = blockIdx.x;
+    const int lane = threadIdx.x;
+    float acc = 0.f;
+    for (int64_t ray = lane; ray < p.n_rays; ray += 32) acc += p.first_rbar[pose * p.n_rays + ray];
+    acc = warp_sum(acc);
+    if (lane != 0) return;
+    const int m = argmedian[pose];
+    const int64_t ray = pose * p.n_rays + m;
+    RaySetup<POSE64> rs;
+    rs.load(p.sources, p.directions, pose, m, p.n_rays, p.dir_pose_stride, p.product_f32);
+    float g0[3], g1[3];
+    int k = p.start;
+    float z0 = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g0);
+    float z1 = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k + 1), rs.coord(1, k + 1), rs.coord(2, k + 1), g1);
+    float sum = z0 + z1;
+    float zb0 = -acc * 2.f * z1 / (sum * sum), zb1 = acc * 2.f * z0 / (sum * sum);
+    if (!(zb0 == zb0)) zb0 = 0.f;
+    if (!(zb1 == zb1)) zb1 = 0.f;
+    if (POSE_GRAD) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            p.grad_src_partial[ray * 3 + a] += zb0 * g0[a] + zb1 * g1[a];
+            p.grad_dir[ray * 3 + a] += (float)k * zb0 * g0[a] + (float)(k + 1) * zb1 * g1[a];
+        }
+    }
+    if (VOL_GRAD) {
+        for (int which = 0; which < 2; ++which) {
+            int kk = k + which;
+            float zb = which ? zb1 : zb0;
+            float p0 = rs.coord(0, kk), p1 = rs.coord(1, kk), p2 = rs.coord(2, kk);
+            if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+                int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
+                atomicAdd(p.grad_volume + ((int64_t)i * p.vol.H + j) * p.vol.W + l, zb);
+            } else {
+                TriCell c;
+                tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
+                tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
+                tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+                for (int q = 0; q < 8; ++q) {
+                    int i = (q & 4) ? c.i1[0] : c.i0[0];
+                    int j = (q & 2) ? c.i1[1] : c.i0[1];
+                    int l = (q & 1) ? c.i1[2] : c.i0[2];
+                    float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
+                    if (w != 0.f) atomicAdd(p.grad_volume + ((int64_t)i * p.vol.H + j) * p.vol.W + l, w * zb);
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_median_backward(const RenderParams& p, int sampler, int layout, int pose64,
+                                   const int32_t* argmedian, bool pose_grad, bool vol_grad, cudaStream_t st) {
+    if (sampler == DIFFUS_SAMPLER_NEAREST) pose_grad = false;
+#define DIFFUS_MB(PG, VG) median_backward_kernel<S_, L_, P64_, PG, VG><<<(unsigned)p.n_poses, 32, 0, st>>>(p, argmedian)
+    DIFFUS_DISPATCH(if (pose_grad && vol_grad) DIFFUS_MB(true, true); else if (pose_grad) DIFFUS_MB(true, false);
+                    else DIFFUS_MB(false, true); return cudaGetLastError())
+#undef DIFFUS_MB
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------
+// x, y, z index outputs (src/renderer.py:754-756) and raw sampled values (trace_ray)
+// ---------------------------------------------------------------------------------------
+template <bool POSE64>
+__global__ void ray_indices_kernel(const RenderParams p, int64_t* __restrict__ x, int64_t* __restrict__ y, int64_t* __restrict__ z) {
+    const int64_t n = p.total_rays * p.Sout;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t ray = t / p.Sout;
+        int c = (int)(t - ray * p.Sout);
+        int64_t pose = ray / p.n_rays;
+        RaySetup<POSE64> rs;
+        rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
+        int k = p.start + c;
+        x[t] = nearest_index(rs.coord(0, k), p.vol.D);
+        y[t] = nearest_index(rs.coord(1, k), p.vol.H);
+        z[t] = nearest_index(rs.coord(2, k), p.vol.W);
+    }
+}
+
+cudaError_t launch_ray_indices(const RenderParams& p, int pose64, int64_t* x, int64_t* y, int64_t* z, cudaStream_t st) {
+    int64_t n = p.total_rays * p.Sout;
+    unsigned grid = (unsigned)min((int64_t)148 * 16, (n + 255) / 256);
+    if (pose64) ray_indices_kernel<true><<<grid, 256, 0, st>>>(p, x, y, z);
+    else ray_indices_kernel<false><<<grid, 256, 0, st>>>(p, x, y, z);
+    return cudaGetLastError();
+}
+
+template <int SAMPLER, int LAYOUT, bool POSE64>
+__global__ void trace_values_kernel(const RenderParams p, float* __restrict__ out) {
+    const int64_t n = p.total_rays * p.S;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t ray = t / p.S;
+        int k = (int)(t - ray * p.S);
+        int64_t pose = ray / p.n_rays;
+        RaySetup<POSE64> rs;
+        rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
+        float g[3];
+        out[t] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
+    }
+}
+
+cudaError_t launch_trace_values(const RenderParams& p, int sampler, int layout, int pose64, float* out, cudaStream_t st) {
+    int64_t n = p.total_rays * p.S;
+    unsigned grid = (unsigned)min((int64_t)148 * 16, (n + 255) / 256);
+    DIFFUS_DISPATCH(trace_values_kernel<S_, L_, P64_><<<grid, 256, 0, st>>>(p, out); return cudaGetLastError())
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------
+// per-ray source partials -> per-pose gradient (atomic-free, fixed order)
+// ---------------------------------------------------------------------------------------
+__global__ void reduce_rays_kernel(const float* __restrict__ partial, int64_t n_poses, int64_t n_rays, float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pose = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (pose >= n_poses) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const float* src = partial + pose * n_rays * 3;
+    for (int64_t r = lane; r < n_rays; r += 32) { a0 += src[r * 3]; a1 += src[r * 3 + 1]; a2 += src[r * 3 + 2]; }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { out[pose * 3] = a0; out[pose * 3 + 1] = a1; out[pose * 3 + 2] = a2; }
+}
+
+cudaError_t launch_reduce_rays(const float* partial, int64_t n_poses, int64_t n_rays, float* out, cudaStream_t st) {
+    unsigned grid = (unsigned)((n_poses + 3) / 4);
+    reduce_rays_kernel<<<grid, 128, 0, st>>>(partial, n_poses, n_rays, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// fans for a batch of poses (src/cone.py:242-259 per pose)
+// ---------------------------------------------------------------------------------------
+__global__ void cone_directions_kernel(const double* __restrict__ median, int64_t n_poses, int64_t n_rays, double angle,
+                                       float* __restrict__ out) {
+    const int64_t n = n_poses * n_rays;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t pose = t / n_rays, i = t - pose * n_rays;
+        double dx = median[pose * 2], dy = median[pose * 2 + 1];
+        double nrm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        dx /= nrm; dy /= nrm;
+        double lo = -angle / 2, hi = angle / 2;
+        double a = lo;                                   // numpy.linspace: start + i*step, endpoint pinned
+        if (n_rays > 1) {
+            double step = (hi - lo) / (double)(n_rays - 1);
+            a = (i == n_rays - 1) ? hi : __dadd_rn(__dmul_rn((double)i, step), lo);
+        }
+        double ca = cos(a), sa = sin(a);
+        out[t * 3 + 0] = (float)__dadd_rn(__dmul_rn(ca, dx), __dmul_rn(sa, -dy));
+        out[t * 3 + 1] = (float)__dadd_rn(__dmul_rn(ca, dy), __dmul_rn(sa, dx));
+        out[t * 3 + 2] = 0.f;
+    }
+}
+
+cudaError_t launch_cone_directions(const double* median, int64_t n_poses, int64_t n_rays, double opening_angle,
+                                   float* out, cudaStream_t st) {
+    int64_t n = n_poses * n_rays;
+    unsigned grid = (unsigned)min((int64_t)148 * 8, (n + 127) / 128);
+    cone_directions_kernel<<<grid, 128, 0, st>>>(median, n_poses, n_rays, opening_angle, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// LINEAR <-> BRICK (4x4x2 voxels = one 128-byte line)
+// ---------------------------------------------------------------------------------------
+template <bool TO_BRICKS>
+__global__ void brick_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int D, int H, int W, int nbi,
+                                  int nbj, int nbk) {
+    const int64_t n = (int64_t)nbi * nbj * nbk * 32;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int e = (int)(t & 31);
+        int64_t b = t >> 5;
+        int bk = (int)(b % nbk);
+        int bj = (int)((b / nbk) % nbj);
+        int bi = (int)(b / ((int64_t)nbk * nbj));
+        int i = bi * BRICK_I + (e >> 3), j = bj * BRICK_J + ((e >> 1) & 3), k = bk * BRICK_K + (e & 1);
+        bool ok = i < D && j < H && k < W;
+        int64_t lin = ((int64_t)i * H + j) * W + k;
+        if (TO_BRICKS) dst[t] = ok ? src[lin] : 0.f;
+        else if (ok) dst[lin] = src[t];
+    }
+}
+
+static void brick_counts(const int32_t dim[3], int& nbi, int& nbj, int& nbk) {
+    nbi = (dim[0] + BRICK_I - 1) / BRICK_I;
+    nbj = (dim[1] + BRICK_J - 1) / BRICK_J;
+    nbk = (dim[2] + BRICK_K - 1) / BRICK_K;
+}
+
+cudaError_t launch_to_bricks(const float* linear, const int32_t dim[3], float* bricks, cudaStream_t st) {
+    int nbi, nbj, nbk;
+    brick_counts(dim, nbi, nbj, nbk);
+    int64_t n = (int64_t)nbi * nbj * nbk * 32;
+    unsigned grid = (unsigned)min((int64_t)148 * 32, (n + 255) / 256);
+    brick_copy_kernel<true><<<grid, 256, 0, st>>>(linear, bricks, dim[0], dim[1], dim[2], nbi, nbj, nbk);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_from_bricks(const float* bricks, const int32_t dim[3], float* linear, cudaStream_t st) {
+    int nbi, nbj, nbk;
+    brick_counts(dim, nbi, nbj, nbk);
+    int64_t n = (int64_t)nbi * nbj * nbk * 32;
+    unsigned grid = (unsigned)min((int64_t)148 * 32, (n + 255) / 256);
+    brick_copy_kernel<false><<<grid, 256, 0, st>>>(bricks, linear, dim[0], dim[1], dim[2], nbi, nbj, nbk);
+    return cudaGetLastError();
+}
+
+}  // namespace diffus

@@ -1,0 +1,236 @@
+// Shared device helpers for the DiffUS B-mode renderer kernels (sm_100a).
+//
+// Column convention used by every kernel in this directory
+// --------------------------------------------------------
+// A ray has S samples; after the `start` crop there are Sout = S - start output columns
+// c = 0..Sout-1, column c belonging to sample k = start + c.  Column c >= 1 owns the
+// interface between samples c-1 and c with reflection coefficient
+//     r_c = (Z_c - Z_{c-1}) / (Z_{c-1} + Z_c)                (reference src/renderer.py:33,65-68)
+// and transfer matrix M_c = [[1 - 2 r_c^2, r_c], [-r_c, 1]]; M_0 = I.  With
+//     P_c = M_0 M_1 ... M_c,     echo[c] = P_c[0][1] / P_c[1][1]
+// the echo line equals what the reference obtains from one dense linear solve per
+// truncation depth (src/renderer.py:367-457); see oracle/port.py::echo_closed_form.
+//
+// A warp owns a ray and walks it in segments of SEG = 512 columns: a gather phase with
+// lane = consecutive sample (coalesced stores, few cache lines per load instruction)
+// parks impedances in shared memory, a chunk phase with lane = 16 consecutive columns does
+// the sequential 2x2 products plus ONE warp-shuffle scan per segment, and a tile phase
+// writes the result back with lane = consecutive column.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+#include "../../include/diffus_b200.h"
+
+namespace diffus {
+
+constexpr int SEG = 512;    // columns per segment (= 32 lanes x CHUNK)
+constexpr int CHUNK = 16;   // columns per lane in the chunk phase
+constexpr unsigned FULL = 0xffffffffu;
+
+// padded shared-memory slot: stride-17 rows make the lane*16+i pattern conflict free
+__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
+constexpr int ZBUF = SEG + 1 + (SEG + 1) / 16 + 3;   // slots 0..SEG (slot 0 = sample c0-1)
+constexpr int OBUF = SEG + SEG / 16 + 3;             // slots 0..SEG-1
+
+struct M2 {          // [[a, b], [c, d]]
+    float a, b, c, d;
+};
+__device__ __forceinline__ M2 m2_identity() { return M2{1.f, 0.f, 0.f, 1.f}; }
+__device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) {
+    return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+// P * M(r),  M(r) = [[1 - 2 r^2, r], [-r, 1]]
+__device__ __forceinline__ M2 m2_mul_interface(const M2& p, float r) {
+    float q = 1.f - 2.f * r * r;
+    return M2{p.a * q - p.b * r, p.a * r + p.b, p.c * q - p.d * r, p.c * r + p.d};
+}
+// X * M(r)^T
+__device__ __forceinline__ M2 m2_mul_interface_t(const M2& x, float r) {
+    float q = 1.f - 2.f * r * r;
+    return M2{x.a * q + x.b * r, x.b - x.a * r, x.c * q + x.d * r, x.d - x.c * r};
+}
+__device__ __forceinline__ M2 m2_transpose(const M2& x) { return M2{x.a, x.c, x.b, x.d}; }
+__device__ __forceinline__ M2 m2_add(const M2& x, const M2& y) { return M2{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
+__device__ __forceinline__ M2 m2_shfl_up(const M2& x, int d) {
+    return M2{__shfl_up_sync(FULL, x.a, d), __shfl_up_sync(FULL, x.b, d), __shfl_up_sync(FULL, x.c, d), __shfl_up_sync(FULL, x.d, d)};
+}
+__device__ __forceinline__ M2 m2_shfl_down(const M2& x, int d) {
+    return M2{__shfl_down_sync(FULL, x.a, d), __shfl_down_sync(FULL, x.b, d), __shfl_down_sync(FULL, x.c, d), __shfl_down_sync(FULL, x.d, d)};
+}
+__device__ __forceinline__ M2 m2_shfl(const M2& x, int src) {
+    return M2{__shfl_sync(FULL, x.a, src), __shfl_sync(FULL, x.b, src), __shfl_sync(FULL, x.c, src), __shfl_sync(FULL, x.d, src)};
+}
+
+// nan_to_num(nan=0) of src/renderer.py:408 (+-inf -> +-FLT_MAX like torch's default)
+__device__ __forceinline__ float nan_to_num(float e) {
+    if (e != e) return 0.f;
+    return fminf(fmaxf(e, -FLT_MAX), FLT_MAX);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// volume addressing
+// ---------------------------------------------------------------------------------------
+struct VolumeView {
+    const float* data;
+    int D, H, W;      // extents along point components 0, 1, 2
+    int nbj, nbk;     // BRICK layout: bricks along components 1 and 2
+};
+
+constexpr int BRICK_I = 4, BRICK_J = 4, BRICK_K = 2;   // 32 floats = one 128-byte line
+
+template <int LAYOUT>
+__device__ __forceinline__ int64_t voxel_offset(const VolumeView& v, int i, int j, int k) {
+    if (LAYOUT == DIFFUS_LAYOUT_LINEAR) {
+        return ((int64_t)i * v.H + j) * v.W + k;
+    } else {
+        int64_t brick = ((int64_t)(i >> 2) * v.nbj + (j >> 2)) * v.nbk + (k >> 1);
+        return brick * 32 + ((i & 3) << 3) + ((j & 3) << 1) + (k & 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// ray points:  p = source + k * direction   (src/renderer.py:119-124), cast to float32 (:751)
+// The reference multiplies and adds in separate roundings; no FMA contraction here so the
+// nearest-voxel indices are bit-identical.
+// ---------------------------------------------------------------------------------------
+template <bool POSE64>
+struct RaySetup;
+
+template <>
+struct RaySetup<false> {
+    float s[3], d[3];
+    __device__ __forceinline__ void load(const void* src, const void* dir, int64_t pose, int64_t ray,
+                                         int64_t n_rays, int64_t dir_pose_stride, int) {
+        const float* sp = (const float*)src + pose * 3;
+        const float* dp = (const float*)dir + pose * dir_pose_stride + ray * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s[a] = __ldg(sp + a); d[a] = __ldg(dp + a); }
+    }
+    __device__ __forceinline__ float coord(int a, int k) const {
+        return __fadd_rn(s[a], __fmul_rn((float)k, d[a]));
+    }
+};
+
+template <>
+struct RaySetup<true> {
+    double s[3], d[3];
+    int product_f32;
+    __device__ __forceinline__ void load(const void* src, const void* dir, int64_t pose, int64_t ray,
+                                         int64_t n_rays, int64_t dir_pose_stride, int prod_f32) {
+        const double* sp = (const double*)src + pose * 3;
+        const double* dp = (const double*)dir + pose * dir_pose_stride + ray * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s[a] = __ldg(sp + a); d[a] = __ldg(dp + a); }
+        product_f32 = prod_f32;
+    }
+    __device__ __forceinline__ float coord(int a, int k) const {
+        double prod = product_f32 ? (double)__fmul_rn((float)k, (float)d[a]) : __dmul_rn((double)k, d[a]);
+        return (float)__dadd_rn(s[a], prod);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// samplers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_index(float p, int n) {
+    int i = __float2int_rn(p);                 // round half to even == torch.round; saturating
+    return min(max(i, 0), n - 1);
+}
+
+struct TriCell {       // clamp-then-floor cell of a trilinear sample, grid_sample border semantics
+    int i0[3], i1[3];
+    float f[3];
+    bool inside[3];    // derivative w.r.t. the coordinate is non-zero only strictly inside
+};
+
+__device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float& f, bool& inside) {
+    float hi = (float)(n - 1);
+    inside = (p > 0.f) && (p < hi);
+    float pc = fminf(fmaxf(p, 0.f), hi);
+    float fl = floorf(pc);
+    f = pc - fl;
+    i0 = (int)fl;
+    i1 = min(i0 + 1, n - 1);
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void tri_offsets(const VolumeView& v, const TriCell& c, int64_t off[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int i = (q & 4) ? c.i1[0] : c.i0[0];
+        int j = (q & 2) ? c.i1[1] : c.i0[1];
+        int k = (q & 1) ? c.i1[2] : c.i0[2];
+        off[q] = voxel_offset<LAYOUT>(v, i, j, k);
+    }
+}
+
+// value (and optionally the spatial gradient) of the border-clamped trilinear interpolant
+template <bool GRAD>
+__device__ __forceinline__ float tri_combine(const float z[8], const TriCell& c, float g[3]) {
+    float fx = c.f[0], fy = c.f[1], fz = c.f[2];
+    float gx = 1.f - fx, gy = 1.f - fy, gz = 1.f - fz;
+    float c00 = z[0] * gz + z[1] * fz;   // (i0, j0)
+    float c01 = z[2] * gz + z[3] * fz;   // (i0, j1)
+    float c10 = z[4] * gz + z[5] * fz;   // (i1, j0)
+    float c11 = z[6] * gz + z[7] * fz;   // (i1, j1)
+    float c0 = c00 * gy + c01 * fy;
+    float c1 = c10 * gy + c11 * fy;
+    if (GRAD) {
+        g[0] = c.inside[0] ? (c1 - c0) : 0.f;
+        g[1] = c.inside[1] ? ((c01 - c00) * gx + (c11 - c10) * fx) : 0.f;
+        float d00 = z[1] - z[0], d01 = z[3] - z[2], d10 = z[5] - z[4], d11 = z[7] - z[6];
+        g[2] = c.inside[2] ? ((d00 * gy + d01 * fy) * gx + (d10 * gy + d11 * fy) * fx) : 0.f;
+    }
+    return c0 * gx + c1 * fx;
+}
+
+template <int SAMPLER, int LAYOUT, bool GRAD>
+__device__ __forceinline__ float sample_volume(const VolumeView& v, float p0, float p1, float p2, float g[3]) {
+    if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+        int i = nearest_index(p0, v.D), j = nearest_index(p1, v.H), k = nearest_index(p2, v.W);
+        if (GRAD) { g[0] = g[1] = g[2] = 0.f; }
+        return __ldg(v.data + voxel_offset<LAYOUT>(v, i, j, k));
+    } else {
+        TriCell c;
+        tri_axis(p0, v.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
+        tri_axis(p1, v.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
+        tri_axis(p2, v.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+        int64_t off[8];
+        tri_offsets<LAYOUT>(v, c, off);
+        float z[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z[q] = __ldg(v.data + off[q]);
+        return tri_combine<GRAD>(z, c, g);
+    }
+}
+
+// kernel parameter block (host fills it from the C-ABI structs)
+struct RenderParams {
+    VolumeView vol;
+    const void* sources;
+    const void* directions;
+    int64_t dir_pose_stride;
+    int product_f32;
+    int64_t n_poses, n_rays, total_rays;
+    int S, start, Sout, nseg;
+    float alpha;
+    float* frame;
+    float* seg_prefix;          // (total_rays, nseg-1, 4) or null
+    const float* median;        // (P) replacement for r_1 when start > 0, else null
+    // backward
+    const float* grad_frame;
+    float* grad_volume;
+    float* grad_src_partial;    // (total_rays, 3)
+    float* grad_dir;            // (total_rays, 3)
+    float* first_rbar;          // (total_rays) d loss / d (median-replaced r_1), start > 0
+};
+
+}  // namespace diffus

@@ -1,0 +1,56 @@
+// Host-side launcher declarations (internal to the shared library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace diffus {
+
+// 8-way template dispatch on (sampler, layout, pose dtype); the body sees S_, L_, P64_.
+#define DIFFUS_DISPATCH_CASE(Sv, Lv, Pv, ...)                              \
+    if (sampler == (Sv) && layout == (Lv) && pose64 == ((Pv) ? 1 : 0)) {   \
+        constexpr int S_ = (Sv);                                           \
+        constexpr int L_ = (Lv);                                           \
+        constexpr bool P64_ = (Pv);                                        \
+        __VA_ARGS__;                                                       \
+    }
+#define DIFFUS_DISPATCH(...)                                                                   \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, false, __VA_ARGS__)     \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, true, __VA_ARGS__)      \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, false, __VA_ARGS__)   \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, true, __VA_ARGS__)    \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)      \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)       \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)    \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)
+
+// render_kernels.cu
+cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st);
+cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad,
+                              bool vol_grad, cudaStream_t st);
+cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* echo, cudaStream_t st);
+cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n_rays, int N, float* grad_refl,
+                            cudaStream_t st);
+
+// aux_kernels.cu
+cudaError_t launch_first_refl_median(const RenderParams& p, int sampler, int layout, int pose64, float* median,
+                                     int32_t* argmedian, cudaStream_t st);
+cudaError_t launch_median_backward(const RenderParams& p, int sampler, int layout, int pose64,
+                                   const int32_t* argmedian, bool pose_grad, bool vol_grad, cudaStream_t st);
+cudaError_t launch_ray_indices(const RenderParams& p, int pose64, int64_t* x, int64_t* y, int64_t* z, cudaStream_t st);
+cudaError_t launch_trace_values(const RenderParams& p, int sampler, int layout, int pose64, float* out, cudaStream_t st);
+cudaError_t launch_reduce_rays(const float* partial, int64_t n_poses, int64_t n_rays, float* out, cudaStream_t st);
+cudaError_t launch_cone_directions(const double* median, int64_t n_poses, int64_t n_rays, double opening_angle,
+                                   float* out, cudaStream_t st);
+cudaError_t launch_to_bricks(const float* linear, const int32_t dim[3], float* bricks, cudaStream_t st);
+cudaError_t launch_from_bricks(const float* bricks, const int32_t dim[3], float* linear, cudaStream_t st);
+
+// mlp_kernels.cu
+cudaError_t launch_mlp_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
+                           float fill, float* out, cudaStream_t st);
+int64_t mlp_bwd_workspace_bytes(int64_t n);
+cudaError_t launch_mlp_bwd(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                           float out_scale, float* grad_params, void* workspace, cudaStream_t st);
+
+}  // namespace diffus

@@ -1,0 +1,404 @@
+"""torch.library custom ops over the C ABI (``libdiffus_b200.so``), with autograd.
+
+PyTorch is plumbing here: it owns device memory and streams and carries autograd; every
+number is produced by the hand-written kernels behind ``include/diffus_b200.h``.  All ops
+require CUDA tensors and raise otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (LAYOUT_BRICK, LAYOUT_LINEAR, MLP_NPARAMS, POSE_F32, POSE_F64, SAMPLER_NEAREST,
+                   SAMPLER_TRILINEAR, DiffusRenderArgs, DiffusRenderBwdArgs)
+
+SEG = 512  # columns per scan segment (csrc/common.cuh)
+
+_LAUNCHES = 0  # kernels enqueued through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.DiffusError(
+                "diffus_b200 ops run only on CUDA tensors (sm_100a kernels); there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.DiffusError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _stream(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _nseg(sout: int) -> int:
+    return (sout + SEG - 1) // SEG
+
+
+def _fill_render_args(a: DiffusRenderArgs, volume, bricks, dims, sources, directions, n_samples, start, alpha,
+                      sampler, product_f32):
+    use_bricks = bricks is not None and bricks.numel() > 0
+    data = bricks if use_bricks else volume
+    a.volume.data = data.data_ptr()
+    a.volume.dim[0], a.volume.dim[1], a.volume.dim[2] = dims
+    a.volume.layout = LAYOUT_BRICK if use_bricks else LAYOUT_LINEAR
+    a.sources = sources.data_ptr()
+    a.directions = directions.data_ptr()
+    a.pose_dtype = POSE_F64 if sources.dtype == torch.float64 else POSE_F32
+    a.product_f32 = int(product_f32)
+    P = sources.shape[0]
+    R = directions.shape[-2]
+    a.n_poses, a.n_rays = P, R
+    a.dir_pose_stride = R * 3 if directions.dim() == 3 else 0     # (R,3): one fan shared by all poses
+    a.n_samples, a.start, a.sampler, a.attenuation = n_samples, start, sampler, alpha
+    return P, R
+
+
+def _check_inputs(volume, bricks, dims, sources, directions):
+    if volume.dtype != torch.float32 or not volume.is_contiguous():
+        raise _lib.DiffusError("volume must be a contiguous float32 tensor")
+    if sources.dtype not in (torch.float32, torch.float64) or sources.dtype != directions.dtype:
+        raise _lib.DiffusError("sources/directions must both be float32 or both float64")
+    if sources.dim() != 2 or sources.shape[1] != 3 or not sources.is_contiguous():
+        raise _lib.DiffusError("sources must be contiguous (P,3)")
+    if directions.shape[-1] != 3 or directions.dim() not in (2, 3) or not directions.is_contiguous():
+        raise _lib.DiffusError("directions must be contiguous (R,3) or (P,R,3)")
+    if directions.dim() == 3 and directions.shape[0] != sources.shape[0]:
+        raise _lib.DiffusError("directions (P,R,3) must have one fan per source")
+    if len(dims) != 3:
+        raise _lib.DiffusError("dims must have three entries")
+
+
+# ---------------------------------------------------------------------------------------
+# render
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("diffus::render_fwd", mutates_args=())
+def render_fwd(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
+               directions: torch.Tensor, n_samples: int, start: int, alpha: float, sampler: int,
+               product_f32: bool, save_prefix: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    dev = _require_cuda(volume, bricks, sources, directions)
+    _check_inputs(volume, bricks, dims, sources, directions)
+    lib = _lib.load()
+    a = DiffusRenderArgs()
+    with torch.cuda.device(dev):
+        P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
+                                 product_f32)
+        sout = n_samples - start
+        frame = torch.empty((P, R, max(sout, 0)), dtype=torch.float32, device=dev)
+        nseg = _nseg(sout)
+        prefix = torch.empty((P, R, nseg - 1, 4) if (save_prefix and nseg > 1) else (0,), dtype=torch.float32,
+                             device=dev)
+        a.frame = frame.data_ptr() if frame.numel() else None
+        a.seg_prefix = _ptr(prefix)
+        wbytes = lib.diffus_render_workspace_bytes(C.byref(a))
+        ws = torch.empty((max(wbytes, 1),), dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), wbytes
+        _lib.check(lib.diffus_render_forward(C.byref(a), _stream(dev)), "diffus_render_forward")
+        _count(2 if start > 0 else 1)
+    return frame, prefix
+
+
+@render_fwd.register_fake
+def _(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler, product_f32, save_prefix):
+    P, R = sources.shape[0], directions.shape[-2]
+    sout = n_samples - start
+    nseg = _nseg(sout)
+    frame = volume.new_empty((P, R, sout), dtype=torch.float32)
+    prefix = volume.new_empty((P, R, nseg - 1, 4) if (save_prefix and nseg > 1) else (0,), dtype=torch.float32)
+    return frame, prefix
+
+
+@torch.library.custom_op("diffus::render_bwd", mutates_args=())
+def render_bwd(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int],
+               sources: torch.Tensor, directions: torch.Tensor, prefix: torch.Tensor, n_samples: int, start: int,
+               alpha: float, sampler: int, product_f32: bool, need_volume: bool,
+               need_pose: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    dev = _require_cuda(grad_frame, volume, bricks, sources, directions)
+    _check_inputs(volume, bricks, dims, sources, directions)
+    lib = _lib.load()
+    b = DiffusRenderBwdArgs()
+    with torch.cuda.device(dev):
+        P, R = _fill_render_args(b.fwd, volume, bricks, dims, sources, directions, n_samples, start, alpha,
+                                 sampler, product_f32)
+        grad_frame = grad_frame.contiguous().float()
+        need_pose = need_pose and sampler == SAMPLER_TRILINEAR
+        gvol = torch.zeros(tuple(dims), dtype=torch.float32, device=dev) if need_volume else \
+            torch.empty((0,), dtype=torch.float32, device=dev)
+        gsrc = torch.empty((P, 3) if need_pose else (0,), dtype=torch.float32, device=dev)
+        gdir = torch.empty((P, R, 3) if need_pose else (0,), dtype=torch.float32, device=dev)
+        b.fwd.seg_prefix = _ptr(prefix)
+        b.grad_frame = grad_frame.data_ptr()
+        b.grad_volume, b.grad_sources, b.grad_directions = _ptr(gvol), _ptr(gsrc), _ptr(gdir)
+        wbytes = lib.diffus_render_bwd_workspace_bytes(C.byref(b))
+        ws = torch.empty((max(wbytes, 1),), dtype=torch.uint8, device=dev)
+        b.workspace, b.workspace_bytes = ws.data_ptr(), wbytes
+        b.fwd.workspace, b.fwd.workspace_bytes = None, 0
+        _lib.check(lib.diffus_render_backward(C.byref(b), _stream(dev)), "diffus_render_backward")
+        _count((1 if (need_volume or need_pose) else 0) + (2 if start > 0 else 0) + (1 if need_pose else 0))
+    return gvol, gsrc, gdir
+
+
+@render_bwd.register_fake
+def _(grad_frame, volume, bricks, dims, sources, directions, prefix, n_samples, start, alpha, sampler, product_f32,
+      need_volume, need_pose):
+    P, R = sources.shape[0], directions.shape[-2]
+    need_pose = need_pose and sampler == SAMPLER_TRILINEAR
+    gvol = volume.new_empty(tuple(dims) if need_volume else (0,), dtype=torch.float32)
+    gsrc = volume.new_empty((P, 3) if need_pose else (0,), dtype=torch.float32)
+    gdir = volume.new_empty((P, R, 3) if need_pose else (0,), dtype=torch.float32)
+    return gvol, gsrc, gdir
+
+
+def _render_setup(ctx, inputs, output):
+    (volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler, product_f32, save_prefix) = inputs
+    ctx.save_for_backward(volume, bricks if bricks is not None else volume.new_empty(0), sources, directions,
+                          output[1])
+    ctx.has_bricks = bricks is not None
+    ctx.meta = (list(dims), n_samples, start, alpha, sampler, product_f32, save_prefix)
+
+
+def _render_backward(ctx, grad_frame, grad_prefix):
+    volume, bricks, sources, directions, prefix = ctx.saved_tensors
+    dims, n_samples, start, alpha, sampler, product_f32, save_prefix = ctx.meta
+    need_volume = ctx.needs_input_grad[0]
+    need_pose = (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) and sampler == SAMPLER_TRILINEAR
+    sout = n_samples - start
+    if _nseg(sout) > 1 and not save_prefix:
+        raise _lib.DiffusError("render_fwd was called with save_prefix=False but a gradient was requested")
+    gvol = gsrc = gdir = None
+    if need_volume or need_pose:
+        gv, gs, gd = render_bwd(grad_frame, volume, bricks if ctx.has_bricks else None, dims, sources, directions,
+                                prefix, n_samples, start, alpha, sampler, product_f32, need_volume, need_pose)
+        if need_volume:
+            gvol = gv
+        if need_pose and ctx.needs_input_grad[3]:
+            gsrc = gs.to(sources.dtype)
+        if need_pose and ctx.needs_input_grad[4]:
+            gdir = gd if directions.dim() == 3 else gd.sum(0)
+            gdir = gdir.to(directions.dtype)
+    return gvol, None, None, gsrc, gdir, None, None, None, None, None, None
+
+
+torch.library.register_autograd("diffus::render_fwd", _render_backward, setup_context=_render_setup)
+
+
+# ---------------------------------------------------------------------------------------
+# indices / raw values
+# ---------------------------------------------------------------------------------------
+def ray_indices(dims, sources, directions, n_samples, start, product_f32=False):
+    """int64 (P,R,S-start) nearest-voxel indices x, y, z (reference ``src/renderer.py:754-756``)."""
+    dev = _require_cuda(sources, directions)
+    lib = _lib.load()
+    a = DiffusRenderArgs()
+    with torch.cuda.device(dev):
+        dummy = torch.empty((1,), dtype=torch.float32, device=dev)
+        P, R = _fill_render_args(a, dummy, None, dims, sources, directions, n_samples, start, 0.0, SAMPLER_NEAREST,
+                                 product_f32)
+        out = torch.empty((3, P, R, n_samples - start), dtype=torch.int64, device=dev)
+        _lib.check(lib.diffus_ray_indices(C.byref(a), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                          _stream(dev)), "diffus_ray_indices")
+        _count(1)
+    return out[0], out[1], out[2]
+
+
+def trace_values(volume, bricks, dims, sources, directions, n_samples, sampler, product_f32=False):
+    """float32 (P,R,S) impedances along the rays (reference ``trace_ray``'s values)."""
+    dev = _require_cuda(volume, bricks, sources, directions)
+    _check_inputs(volume, bricks, dims, sources, directions)
+    lib = _lib.load()
+    a = DiffusRenderArgs()
+    with torch.cuda.device(dev):
+        P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, 0, 0.0, sampler, product_f32)
+        out = torch.empty((P, R, n_samples), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_trace_values(C.byref(a), out.data_ptr(), _stream(dev)), "diffus_trace_values")
+        _count(1)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# echo traces on explicit reflection coefficients
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("diffus::echo_fwd", mutates_args=())
+def echo_fwd(refl: torch.Tensor) -> torch.Tensor:
+    dev = _require_cuda(refl)
+    lib = _lib.load()
+    r = refl.contiguous().float()
+    B, N = r.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((B, N + 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_echo_forward(r.data_ptr(), B, N, out.data_ptr(), _stream(dev)), "diffus_echo_forward")
+        _count(1)
+    return out
+
+
+@echo_fwd.register_fake
+def _(refl):
+    return refl.new_empty((refl.shape[0], refl.shape[1] + 1), dtype=torch.float32)
+
+
+@torch.library.custom_op("diffus::echo_bwd", mutates_args=())
+def echo_bwd(refl: torch.Tensor, grad_echo: torch.Tensor) -> torch.Tensor:
+    dev = _require_cuda(refl, grad_echo)
+    lib = _lib.load()
+    r = refl.contiguous().float()
+    g = grad_echo.contiguous().float()
+    B, N = r.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((B, N), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_echo_backward(r.data_ptr(), g.data_ptr(), B, N, out.data_ptr(), _stream(dev)),
+                   "diffus_echo_backward")
+        _count(1)
+    return out
+
+
+@echo_bwd.register_fake
+def _(refl, grad_echo):
+    return refl.new_empty(refl.shape, dtype=torch.float32)
+
+
+def _echo_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _echo_backward(ctx, grad):
+    (refl,) = ctx.saved_tensors
+    return echo_bwd(refl, grad).to(refl.dtype)
+
+
+torch.library.register_autograd("diffus::echo_fwd", _echo_backward, setup_context=_echo_setup)
+
+
+# ---------------------------------------------------------------------------------------
+# fans, bricks
+# ---------------------------------------------------------------------------------------
+def cone_directions(median: torch.Tensor, opening_angle: float, n_rays: int) -> torch.Tensor:
+    """(P,2+) median directions -> (P,R,3) float32 fans in the z=0 plane, on the device."""
+    dev = _require_cuda(median)
+    lib = _lib.load()
+    m = median[..., :2].to(torch.float64).contiguous()
+    P = m.shape[0]
+    with torch.cuda.device(dev):
+        out = torch.empty((P, n_rays, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_cone_directions(m.data_ptr(), P, n_rays, float(opening_angle), out.data_ptr(),
+                                              _stream(dev)), "diffus_cone_directions")
+        _count(1)
+    return out
+
+
+def to_bricks(volume: torch.Tensor) -> torch.Tensor:
+    """LINEAR (D,H,W) float32 -> 1-D brick buffer (4x4x2 voxels per 128-byte line)."""
+    dev = _require_cuda(volume)
+    lib = _lib.load()
+    v = volume.detach().contiguous().float()
+    dim = (C.c_int32 * 3)(*v.shape)
+    with torch.cuda.device(dev):
+        out = torch.empty((lib.diffus_brick_elems(C.byref(dim)),), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_volume_to_bricks(v.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
+                   "diffus_volume_to_bricks")
+        _count(1)
+    return out
+
+
+def from_bricks(bricks: torch.Tensor, dims) -> torch.Tensor:
+    dev = _require_cuda(bricks)
+    lib = _lib.load()
+    dim = (C.c_int32 * 3)(*dims)
+    with torch.cuda.device(dev):
+        out = torch.empty(tuple(dims), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_bricks_to_volume(bricks.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
+                   "diffus_bricks_to_volume")
+        _count(1)
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# MLP
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("diffus::mlp_fwd", mutates_args=())
+def mlp_fwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], out_scale: float,
+            fill: float) -> torch.Tensor:
+    dev = _require_cuda(params, x, mask)
+    lib = _lib.load()
+    if params.numel() != MLP_NPARAMS:
+        raise _lib.DiffusError(f"params must hold {MLP_NPARAMS} floats")
+    p = params.contiguous().float()
+    xc = x.contiguous().float()
+    m = None if mask is None else mask.contiguous().to(torch.uint8)
+    with torch.cuda.device(dev):
+        out = torch.empty(x.shape, dtype=torch.float32, device=dev)
+        if xc.numel():
+            _lib.check(lib.diffus_mlp_forward(p.data_ptr(), xc.data_ptr(), _ptr(m), xc.numel(), out_scale, fill,
+                                              out.data_ptr(), _stream(dev)), "diffus_mlp_forward")
+            _count(1)
+    return out
+
+
+@mlp_fwd.register_fake
+def _(params, x, mask, out_scale, fill):
+    return x.new_empty(x.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("diffus::mlp_bwd", mutates_args=())
+def mlp_bwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
+            out_scale: float) -> torch.Tensor:
+    dev = _require_cuda(params, x, mask, grad_out)
+    lib = _lib.load()
+    p = params.contiguous().float()
+    xc = x.contiguous().float()
+    g = grad_out.contiguous().float()
+    m = None if mask is None else mask.contiguous().to(torch.uint8)
+    with torch.cuda.device(dev):
+        gp = torch.zeros((MLP_NPARAMS,), dtype=torch.float32, device=dev)
+        n = xc.numel()
+        if n:
+            wbytes = lib.diffus_mlp_bwd_workspace_bytes(n)
+            ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+            _lib.check(lib.diffus_mlp_backward(p.data_ptr(), xc.data_ptr(), _ptr(m), g.data_ptr(), n, out_scale,
+                                               gp.data_ptr(), ws.data_ptr(), wbytes, _stream(dev)),
+                       "diffus_mlp_backward")
+            _count(2)
+    return gp
+
+
+@mlp_bwd.register_fake
+def _(params, x, mask, grad_out, out_scale):
+    return params.new_empty((MLP_NPARAMS,), dtype=torch.float32)
+
+
+def _mlp_setup(ctx, inputs, output):
+    params, x, mask, out_scale, fill = inputs
+    ctx.save_for_backward(params, x, mask if mask is not None else x.new_empty(0))
+    ctx.has_mask = mask is not None
+    ctx.out_scale = out_scale
+
+
+def _mlp_backward(ctx, grad):
+    params, x, mask = ctx.saved_tensors
+    gp = None
+    if ctx.needs_input_grad[0]:
+        gp = mlp_bwd(params, x, mask if ctx.has_mask else None, grad, ctx.out_scale).to(params.dtype)
+    return gp, None, None, None, None
+
+
+torch.library.register_autograd("diffus::mlp_fwd", _mlp_backward, setup_context=_mlp_setup)

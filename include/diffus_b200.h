@@ -1,0 +1,166 @@
+/*
+ * diffus_b200.h -- C ABI of the B200-native DiffUS B-mode renderer hot path.
+ *
+ * The reference (gduguey/DiffUS) is pure Python and has no FFI of its own; its boundary
+ * is the Python call surface of src/renderer.py, src/cone.py and src/impedance.py.  Each
+ * entry point below names the reference interface it replaces (file:line relative to
+ * the reference root).  The Python host package (diffus_b200/) binds these symbols with
+ * ctypes and wraps them in torch.library custom ops + autograd; INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; all tensors are
+ *     dense, row-major, caller-owned; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - functions only enqueue work: they never allocate device memory, never synchronise
+ *     and keep no global state (re-entrant across streams and devices);
+ *   - return 0 on success, a negative DIFFUS_E_* for rejected arguments, or a positive
+ *     cudaError_t if a launch failed;
+ *   - there is no CPU implementation behind this ABI.
+ */
+#ifndef DIFFUS_B200_H
+#define DIFFUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIFFUS_ABI_VERSION 1
+
+/* error codes (negative = bad argument) */
+#define DIFFUS_OK 0
+#define DIFFUS_E_NULL (-1)       /* a required pointer is NULL            */
+#define DIFFUS_E_SHAPE (-2)      /* non-positive or inconsistent sizes    */
+#define DIFFUS_E_ENUM (-3)       /* unknown sampler / layout / dtype tag  */
+#define DIFFUS_E_WORKSPACE (-4)  /* workspace missing or too small        */
+#define DIFFUS_E_UNSUPPORTED (-5)
+
+/* sampler: how impedance is read at a ray point */
+#define DIFFUS_SAMPLER_NEAREST 0   /* src/renderer.py:751-759 (HEAD)                          */
+#define DIFFUS_SAMPLER_TRILINEAR 1 /* grid_sample(bilinear, border, align_corners=True): the
+                                      reference's notebook-era sampler, src/renderer.py:802-815
+                                      grid construction; the only pose-differentiable form    */
+
+/* volume layout in HBM */
+#define DIFFUS_LAYOUT_LINEAR 0 /* C-contiguous [p0][p1][p2], exactly the torch tensor        */
+#define DIFFUS_LAYOUT_BRICK 1  /* 4x4x2-voxel bricks of 128 B made by diffus_volume_to_bricks */
+
+/* dtype tags for the probe pose (the reference's `points` dtype follows torch promotion,
+   src/renderer.py:124, and is cast to float32 at :751) */
+#define DIFFUS_POSE_F32 0 /* sources/directions are float32 arrays                            */
+#define DIFFUS_POSE_F64 1 /* both are float64 arrays; see `product_f32`                        */
+
+typedef struct DiffusVolume {
+    const float* data; /* impedance volume, float32                                          */
+    int32_t dim[3];    /* extent along point component 0,1,2  (volume[p0][p1][p2])           */
+    int32_t layout;    /* DIFFUS_LAYOUT_*                                                    */
+} DiffusVolume;
+
+/* One batched render: P poses x R rays x S samples.  Replaces
+ * UltrasoundRenderer.plot_beam_frame (src/renderer.py:201-275) with artifacts=False, i.e.
+ * trace_ray (:89-180) + custom_nearest_sampler (:741-819) + compute_reflection_coeff
+ * (:27-33) + the start crop / median (:237-245) + compute_echo_traces (:439-457, whose
+ * per-depth dense solves are evaluated as a 2x2 transfer-matrix prefix product) + the
+ * exp(-alpha k) attenuation (:256-259), for a leading batch of probe poses. */
+typedef struct DiffusRenderArgs {
+    DiffusVolume volume;
+    const void* sources;        /* (P,3) float32 or float64 per pose_dtype                   */
+    const void* directions;     /* (P,R,3) or, if dir_pose_stride == 0, (R,3) shared by poses */
+    int32_t pose_dtype;         /* DIFFUS_POSE_*                                             */
+    int32_t product_f32;        /* POSE_F64 only: directions were float32, so k*dir rounds to
+                                   float32 before the float64 add (torch promotion)          */
+    int64_t n_poses;            /* P >= 1                                                    */
+    int64_t n_rays;             /* R >= 1                                                    */
+    int64_t dir_pose_stride;    /* elements between poses in `directions`: R*3 or 0          */
+    int32_t n_samples;          /* S >= 2 samples per ray (1-voxel steps)                    */
+    int32_t start;              /* columns cropped from the front, 0 <= start <= S-2; when > 0
+                                   the first kept reflection coefficient of every ray of a pose
+                                   is replaced by the lower median over that pose's rays     */
+    int32_t sampler;            /* DIFFUS_SAMPLER_*                                          */
+    float attenuation;          /* alpha: frame[k] = echo[k] * exp(-alpha k), k from 0 after crop */
+    float* frame;               /* out (P,R,S-start)                                         */
+    float* seg_prefix;          /* out, optional: (P,R,nseg-1,4) transfer-matrix prefixes at
+                                   512-column segment boundaries, consumed by the backward;
+                                   may be NULL (always unused when S-start <= 512)           */
+    void* workspace;            /* diffus_render_workspace_bytes() bytes, needed iff start>0 */
+    int64_t workspace_bytes;
+} DiffusRenderArgs;
+
+/* Backward of the render above (what torch autograd computes through the reference,
+ * SURVEY.md 3.2): given d loss / d frame, accumulate d loss / d volume (index_put_
+ * accumulate semantics of src/renderer.py:758's backward) and, for the trilinear sampler,
+ * d loss / d source and d loss / d directions.  Any of the three outputs may be NULL. */
+typedef struct DiffusRenderBwdArgs {
+    DiffusRenderArgs fwd;       /* same inputs as the forward; fwd.frame may be NULL;
+                                   fwd.seg_prefix = the buffer the forward filled (required
+                                   when S-start > 512)                                        */
+    const float* grad_frame;    /* (P,R,S-start)                                             */
+    float* grad_volume;         /* (D,H,W) LINEAR layout, ACCUMULATED into (caller zero-fills) */
+    float* grad_sources;        /* (P,3) overwritten; trilinear only                         */
+    float* grad_directions;     /* (P,R,3) overwritten; trilinear only (per pose, also when
+                                   the directions were shared)                                */
+    void* workspace;            /* diffus_render_bwd_workspace_bytes() bytes                 */
+    int64_t workspace_bytes;
+} DiffusRenderBwdArgs;
+
+int32_t diffus_abi_version(void);
+const char* diffus_error_string(int32_t code);
+
+int64_t diffus_render_workspace_bytes(const DiffusRenderArgs* args);
+int32_t diffus_render_forward(const DiffusRenderArgs* args, void* stream);
+int64_t diffus_render_bwd_workspace_bytes(const DiffusRenderBwdArgs* args);
+int32_t diffus_render_backward(const DiffusRenderBwdArgs* args, void* stream);
+
+/* Clamped nearest-voxel indices of every ray point: the x, y, z int64 outputs of
+ * custom_nearest_sampler (src/renderer.py:754-756, :816-819), cropped like
+ * plot_beam_frame's return (:275).  Outputs are (P,R,S-start) int64. */
+int32_t diffus_ray_indices(const DiffusRenderArgs* args, int64_t* x, int64_t* y, int64_t* z,
+                           void* stream);
+
+/* Sampled impedances along the rays, no propagation: the `values` output of
+ * UltrasoundRenderer.trace_ray (src/renderer.py:89-180).  out is (P,R,S) (start ignored). */
+int32_t diffus_trace_values(const DiffusRenderArgs* args, float* out, void* stream);
+
+/* compute_echo_traces (src/renderer.py:439-457, through propagate_full_rays_batched :412-436
+ * and prop_single_ray :367-410) on explicit reflection coefficients refl (B,N):
+ * echo (B,N+1) = [0, d0^(1), ..., d0^(N)], NaN -> 0.  Backward: grad_refl (B,N) overwritten. */
+int32_t diffus_echo_forward(const float* refl, int64_t n_rays, int32_t n_interfaces, float* echo,
+                            void* stream);
+int32_t diffus_echo_backward(const float* refl, const float* grad_echo, int64_t n_rays,
+                             int32_t n_interfaces, float* grad_refl, void* stream);
+
+/* Fans for a batch of poses: generate_cone_directions (src/cone.py:242-259) generalised to
+ * a leading pose dimension.  median (P,2) float64 (first two components of the median
+ * direction), out (P,R,3) float32; float64 trigonometry then a float32 cast, like the
+ * reference. */
+int32_t diffus_cone_directions(const double* median, int64_t n_poses, int64_t n_rays,
+                               double opening_angle, float* out, void* stream);
+
+/* ImpedanceEstimator (src/impedance.py:6-17): Linear(1,32)-ReLU-Linear(32,32)-ReLU-Linear(32,1).
+ * params is the 1153-float concatenation [W1(32x1) b1(32) W2(32x32 row-major out,in) b2(32)
+ * W3(1x32) b3(1)] in nn.Linear layout.  out[i] = out_scale * mlp(x[i]); when mask != NULL
+ * voxels with mask[i] == 0 get `fill` instead (compute_impedance_volume, :46-54). */
+#define DIFFUS_MLP_NPARAMS 1153
+int32_t diffus_mlp_forward(const float* params, const float* x, const uint8_t* mask,
+                           int64_t n, float out_scale, float fill, float* out, void* stream);
+/* grad_params (1153) is ACCUMULATED into (caller zero-fills): d/dparams of
+ * sum_i grad_out[i] * out_scale * mlp(x[i]) over unmasked i.  workspace:
+ * diffus_mlp_bwd_workspace_bytes(n) bytes. */
+int64_t diffus_mlp_bwd_workspace_bytes(int64_t n);
+int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* mask,
+                            const float* grad_out, int64_t n, float out_scale,
+                            float* grad_params, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+
+/* LINEAR (D,H,W) -> BRICK copy of a volume (and back, for gradients). dst holds
+ * diffus_brick_elems(dim) floats. */
+int64_t diffus_brick_elems(const int32_t dim[3]);
+int32_t diffus_volume_to_bricks(const float* linear, const int32_t dim[3], float* bricks, void* stream);
+int32_t diffus_bricks_to_volume(const float* bricks, const int32_t dim[3], float* linear, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFUS_B200_H */
