@@ -50,6 +50,10 @@ class DiffusRenderBwdArgs(C.Structure):
         ("grad_volume", C.c_void_p),
         ("grad_sources", C.c_void_p),
         ("grad_directions", C.c_void_p),
+        ("target", C.c_void_p),
+        ("grad_scale", C.c_float),
+        ("loss_scale", C.c_float),
+        ("loss", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
     ]

@@ -12,7 +12,8 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 int32_t check_volume(const DiffusVolume& v) {
     if (!v.data) return DIFFUS_E_NULL;
     if (v.dim[0] < 1 || v.dim[1] < 1 || v.dim[2] < 1) return DIFFUS_E_SHAPE;
-    if ((int64_t)v.dim[0] * v.dim[1] * v.dim[2] >= ((int64_t)1 << 40)) return DIFFUS_E_SHAPE;
+    // 32-bit element offsets (also in the padded brick layout)
+    if (((int64_t)v.dim[0] + 3) * ((int64_t)v.dim[1] + 3) * ((int64_t)v.dim[2] + 1) >= ((int64_t)1 << 31)) return DIFFUS_E_UNSUPPORTED;
     if (v.layout != DIFFUS_LAYOUT_LINEAR && v.layout != DIFFUS_LAYOUT_BRICK) return DIFFUS_E_ENUM;
     return DIFFUS_OK;
 }
@@ -26,7 +27,7 @@ int32_t check_render(const DiffusRenderArgs* a, bool need_frame) {
     if (a->pose_dtype != DIFFUS_POSE_F32 && a->pose_dtype != DIFFUS_POSE_F64) return DIFFUS_E_ENUM;
     if (a->sampler != DIFFUS_SAMPLER_NEAREST && a->sampler != DIFFUS_SAMPLER_TRILINEAR) return DIFFUS_E_ENUM;
     if (a->n_poses < 1 || a->n_rays < 1 || a->n_samples < 2) return DIFFUS_E_SHAPE;
-    if (a->n_samples > (1 << 24)) return DIFFUS_E_SHAPE;             // k must be exact in float32
+    if (a->n_samples > 32768) return DIFFUS_E_UNSUPPORTED;           // attenuation table lives in shared memory
     if (a->start < 0 || a->start > a->n_samples - 2) return DIFFUS_E_SHAPE;
     if (a->dir_pose_stride != 0 && a->dir_pose_stride != a->n_rays * 3) return DIFFUS_E_SHAPE;
     if (a->n_poses * a->n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
@@ -40,8 +41,14 @@ RenderParams pack(const DiffusRenderArgs* a) {
     p.vol.D = a->volume.dim[0];
     p.vol.H = a->volume.dim[1];
     p.vol.W = a->volume.dim[2];
-    p.vol.nbj = (p.vol.H + BRICK_J - 1) / BRICK_J;
-    p.vol.nbk = (p.vol.W + BRICK_K - 1) / BRICK_K;
+    if (a->volume.layout == DIFFUS_LAYOUT_BRICK) {
+        uint32_t nbj = (p.vol.H + BRICK_J - 1) / BRICK_J, nbk = (p.vol.W + BRICK_K - 1) / BRICK_K;
+        p.vol.sy = nbk * 32;
+        p.vol.sx = nbj * nbk * 32;
+    } else {
+        p.vol.sy = (uint32_t)p.vol.W;
+        p.vol.sx = (uint32_t)p.vol.H * (uint32_t)p.vol.W;
+    }
     p.sources = a->sources;
     p.directions = a->directions;
     p.dir_pose_stride = a->dir_pose_stride;
@@ -53,6 +60,7 @@ RenderParams pack(const DiffusRenderArgs* a) {
     p.start = a->start;
     p.Sout = a->n_samples - a->start;
     p.nseg = (p.Sout + SEG - 1) / SEG;
+    p.att_slots = (p.Sout + 3) / 4 * 4;
     p.alpha = a->attenuation;
     p.frame = a->frame;
     p.seg_prefix = a->seg_prefix;
@@ -84,6 +92,7 @@ struct BwdWorkspace {
     float* src_partial;
     float* dir_scratch;
     float* first_rbar;
+    float* loss_partial;
     int64_t bytes;
 };
 BwdWorkspace bwd_workspace(const DiffusRenderBwdArgs* b, void* base) {
@@ -103,6 +112,10 @@ BwdWorkspace bwd_workspace(const DiffusRenderBwdArgs* b, void* base) {
     }
     if (a->start > 0) {
         w.first_rbar = (float*)((char*)base + off);
+        off += align_up(rays * 4, 256);
+    }
+    if (b->target && b->loss) {
+        w.loss_partial = (float*)((char*)base + off);
         off += align_up(rays * 4, 256);
     }
     w.bytes = off;
@@ -160,11 +173,12 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     const DiffusRenderArgs* a = &b->fwd;
     int32_t e = check_render(a, false);
     if (e) return e;
-    if (!b->grad_frame) return DIFFUS_E_NULL;
+    const bool mse = b->target != nullptr;
+    if (!mse && !b->grad_frame) return DIFFUS_E_NULL;
     const bool trilinear = a->sampler == DIFFUS_SAMPLER_TRILINEAR;
     const bool pose_grad = trilinear && (b->grad_sources || b->grad_directions);
     const bool vol_grad = b->grad_volume != nullptr;
-    if (!pose_grad && !vol_grad) return DIFFUS_OK;
+    if (!pose_grad && !vol_grad && !(mse && (b->loss || a->frame))) return DIFFUS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     RenderParams p = pack(a);
     if (p.nseg > 1 && !a->seg_prefix) return DIFFUS_E_NULL;
@@ -179,6 +193,10 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
         p.first_rbar = w.first_rbar;
     }
     p.grad_frame = b->grad_frame;
+    p.target = b->target;
+    p.grad_scale = b->grad_scale;
+    p.loss_partial = w.loss_partial;
+    if (!mse) p.frame = nullptr;
     p.grad_volume = b->grad_volume;
     p.grad_src_partial = w.src_partial;
     p.grad_dir = b->grad_directions ? b->grad_directions : w.dir_scratch;
@@ -190,6 +208,10 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     }
     if (pose_grad && b->grad_sources) {
         ce = launch_reduce_rays(w.src_partial, a->n_poses, a->n_rays, b->grad_sources, st);
+        if (ce != cudaSuccess) return (int32_t)ce;
+    }
+    if (w.loss_partial) {
+        ce = launch_reduce_sum(w.loss_partial, a->n_poses * a->n_rays, b->loss_scale, b->loss, st);
         if (ce != cudaSuccess) return (int32_t)ce;
     }
     return DIFFUS_OK;

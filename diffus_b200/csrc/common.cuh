@@ -38,18 +38,24 @@ struct M2 {          // [[a, b], [c, d]]
     float a, b, c, d;
 };
 __device__ __forceinline__ M2 m2_identity() { return M2{1.f, 0.f, 0.f, 1.f}; }
+// The products below spell out their roundings (one multiply + one fused multiply-add per
+// entry) so that every kernel that walks the same ray produces bit-identical prefixes,
+// whatever the compiler would have contracted on its own.
+__device__ __forceinline__ float mul_add2(float a, float b, float c, float d) {   // a*b + c*d
+    return __fmaf_rn(a, b, __fmul_rn(c, d));
+}
 __device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) {
-    return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+    return M2{mul_add2(x.a, y.a, x.b, y.c), mul_add2(x.a, y.b, x.b, y.d), mul_add2(x.c, y.a, x.d, y.c), mul_add2(x.c, y.b, x.d, y.d)};
 }
 // P * M(r),  M(r) = [[1 - 2 r^2, r], [-r, 1]]
 __device__ __forceinline__ M2 m2_mul_interface(const M2& p, float r) {
-    float q = 1.f - 2.f * r * r;
-    return M2{p.a * q - p.b * r, p.a * r + p.b, p.c * q - p.d * r, p.c * r + p.d};
+    float q = __fmaf_rn(-2.f * r, r, 1.f);
+    return M2{__fmaf_rn(p.a, q, -__fmul_rn(p.b, r)), __fmaf_rn(p.a, r, p.b), __fmaf_rn(p.c, q, -__fmul_rn(p.d, r)), __fmaf_rn(p.c, r, p.d)};
 }
 // X * M(r)^T
 __device__ __forceinline__ M2 m2_mul_interface_t(const M2& x, float r) {
-    float q = 1.f - 2.f * r * r;
-    return M2{x.a * q + x.b * r, x.b - x.a * r, x.c * q + x.d * r, x.d - x.c * r};
+    float q = __fmaf_rn(-2.f * r, r, 1.f);
+    return M2{mul_add2(x.a, q, x.b, r), __fmaf_rn(-x.a, r, x.b), mul_add2(x.c, q, x.d, r), __fmaf_rn(-x.c, r, x.d)};
 }
 __device__ __forceinline__ M2 m2_transpose(const M2& x) { return M2{x.a, x.c, x.b, x.d}; }
 __device__ __forceinline__ M2 m2_add(const M2& x, const M2& y) { return M2{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
@@ -76,25 +82,42 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// volume addressing
+// volume addressing: offset(i, j, k) = ox(i) + oy(j) + oz(k) in 32-bit element units, so the
+// eight corners of a trilinear cell cost six per-axis terms and a handful of adds instead
+// of eight full index computations (integer address math was 47 % of the forward's
+// instructions in the first profile, profiles/r1_first_ncu.md).
 // ---------------------------------------------------------------------------------------
 struct VolumeView {
     const float* data;
-    int D, H, W;      // extents along point components 0, 1, 2
-    int nbj, nbk;     // BRICK layout: bricks along components 1 and 2
+    int D, H, W;          // extents along point components 0, 1, 2
+    uint32_t sx, sy;      // LINEAR: H*W, W     BRICK: bricks-per-slab*32, bricks-per-row*32
 };
 
 constexpr int BRICK_I = 4, BRICK_J = 4, BRICK_K = 2;   // 32 floats = one 128-byte line
 
 template <int LAYOUT>
-__device__ __forceinline__ int64_t voxel_offset(const VolumeView& v, int i, int j, int k) {
-    if (LAYOUT == DIFFUS_LAYOUT_LINEAR) {
-        return ((int64_t)i * v.H + j) * v.W + k;
-    } else {
-        int64_t brick = ((int64_t)(i >> 2) * v.nbj + (j >> 2)) * v.nbk + (k >> 1);
-        return brick * 32 + ((i & 3) << 3) + ((j & 3) << 1) + (k & 1);
-    }
+__device__ __forceinline__ uint32_t axis_x(const VolumeView& v, int i) {
+    return LAYOUT == DIFFUS_LAYOUT_LINEAR ? (uint32_t)i * v.sx : (uint32_t)(i >> 2) * v.sx + ((uint32_t)(i & 3) << 3);
 }
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t axis_y(const VolumeView& v, int j) {
+    return LAYOUT == DIFFUS_LAYOUT_LINEAR ? (uint32_t)j * v.sy : (uint32_t)(j >> 2) * v.sy + ((uint32_t)(j & 3) << 1);
+}
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t axis_z(const VolumeView& v, int k) {
+    return LAYOUT == DIFFUS_LAYOUT_LINEAR ? (uint32_t)k : ((uint32_t)(k >> 1) << 5) + (uint32_t)(k & 1);
+}
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t voxel_offset(const VolumeView& v, int i, int j, int k) {
+    return axis_x<LAYOUT>(v, i) + axis_y<LAYOUT>(v, j) + axis_z<LAYOUT>(v, k);
+}
+
+// a / b without the IEEE slow path (<= 2 ulp): the reference's own float32 run is ~1e-5 of
+// peak away from its float64 run, so correctly-rounded division buys nothing here
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_rcp(float b) { return __fdividef(1.f, b); }
+// echo of a prefix: P[0][1] / P[1][1] (same rounding in the forward and in the fused backward)
+__device__ __forceinline__ float echo_of(float pb, float inv_pd) { return __fmul_rn(pb, inv_pd); }
 
 // ---------------------------------------------------------------------------------------
 // ray points:  p = source + k * direction   (src/renderer.py:119-124), cast to float32 (:751)
@@ -162,14 +185,13 @@ __device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float
 }
 
 template <int LAYOUT>
-__device__ __forceinline__ void tri_offsets(const VolumeView& v, const TriCell& c, int64_t off[8]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        int i = (q & 4) ? c.i1[0] : c.i0[0];
-        int j = (q & 2) ? c.i1[1] : c.i0[1];
-        int k = (q & 1) ? c.i1[2] : c.i0[2];
-        off[q] = voxel_offset<LAYOUT>(v, i, j, k);
-    }
+__device__ __forceinline__ void tri_offsets(const VolumeView& v, const TriCell& c, uint32_t off[8]) {
+    uint32_t x0 = axis_x<LAYOUT>(v, c.i0[0]), x1 = axis_x<LAYOUT>(v, c.i1[0]);
+    uint32_t y0 = axis_y<LAYOUT>(v, c.i0[1]), y1 = axis_y<LAYOUT>(v, c.i1[1]);
+    uint32_t z0 = axis_z<LAYOUT>(v, c.i0[2]), z1 = axis_z<LAYOUT>(v, c.i1[2]);
+    uint32_t a00 = x0 + y0, a01 = x0 + y1, a10 = x1 + y0, a11 = x1 + y1;
+    off[0] = a00 + z0; off[1] = a00 + z1; off[2] = a01 + z0; off[3] = a01 + z1;
+    off[4] = a10 + z0; off[5] = a10 + z1; off[6] = a11 + z0; off[7] = a11 + z1;
 }
 
 // value (and optionally the spatial gradient) of the border-clamped trilinear interpolant
@@ -203,7 +225,7 @@ __device__ __forceinline__ float sample_volume(const VolumeView& v, float p0, fl
         tri_axis(p0, v.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
         tri_axis(p1, v.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
         tri_axis(p2, v.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
-        int64_t off[8];
+        uint32_t off[8];
         tri_offsets<LAYOUT>(v, c, off);
         float z[8];
 #pragma unroll
@@ -221,6 +243,7 @@ struct RenderParams {
     int product_f32;
     int64_t n_poses, n_rays, total_rays;
     int S, start, Sout, nseg;
+    int att_slots;              // floats reserved at the start of dynamic smem for the attenuation table
     float alpha;
     float* frame;
     float* seg_prefix;          // (total_rays, nseg-1, 4) or null
@@ -231,6 +254,10 @@ struct RenderParams {
     float* grad_src_partial;    // (total_rays, 3)
     float* grad_dir;            // (total_rays, 3)
     float* first_rbar;          // (total_rays) d loss / d (median-replaced r_1), start > 0
+    // fused MSE loss (target != null): d loss / d frame = grad_scale * (frame - target)
+    const float* target;        // (total_rays, Sout)
+    float grad_scale;
+    float* loss_partial;        // (total_rays) sum over the ray of (frame - target)^2, or null
 };
 
 }  // namespace diffus

@@ -4,7 +4,9 @@
 // backward : what torch autograd derives from it, written as a reverse
 //            affine scan of 2x2 matrices; per-ray gradient partials are written once
 //            (no atomics) and only the volume gradient uses red.global.add.f32, mirroring
-//            index_put_(accumulate=True).
+//            index_put_(accumulate=True).  With a target frame the backward kernel also
+//            evaluates the forward and the MSE loss itself, so one launch is a whole
+//            pose-recovery step (fused forward + loss + backward, one gather pass).
 #include "common.cuh"
 #include "launch.h"
 
@@ -38,42 +40,62 @@ __device__ __forceinline__ M2 forward_chunk(const float r[CHUNK], M2 carry, floa
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
         P = m2_mul_interface(P, r[i]);
-        obuf[pad(lane * CHUNK + i)] = nan_to_num(P.b / P.d);
+        obuf[lane * (CHUNK + 1) + i] = nan_to_num(echo_of(P.b, fast_rcp(P.d)));
     }
     return m2_shfl(P, 31);
 }
 
+// What the upstream gradient of a column is made of.
+//   LOSS_GRAD : gbuf holds d loss / d frame, abuf the attenuation         -> ebar = g * att
+//   LOSS_MSE  : gbuf holds the target frame, abuf the attenuation; the kernel forms
+//               frame = echo * att, diff = frame - target, ebar = grad_scale * diff * att,
+//               accumulates diff^2 and leaves the frame in abuf
+constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
+
 // Backward chunk phase for one segment.
 //   r[i]        coefficient of column c0 + lane*16 + i (0 where the column does not exist)
-//   gbuf        in: d loss / d echo per column (0 where none); out: d loss / d r per column
+//   gbuf/abuf   see above; on return gbuf holds d loss / d r per column
 //   carry       forward prefix P through the column before the segment
 //   vin         adjoint flowing into the segment's last column from later segments
+//   ncol_lane   number of existing columns in this lane's chunk (for the loss sum)
 // returns the adjoint flowing out of the segment's first column (into the previous segment)
-__device__ __forceinline__ M2 backward_chunk(const float r[CHUNK], const M2& carry, const M2& vin,
-                                             float* gbuf, int lane) {
-    // local chunk product and true prefixes
+template <int LOSS>
+__device__ __forceinline__ M2 backward_chunk(const float r[CHUNK], const M2& carry, const M2& vin, float* gbuf,
+                                             float* abuf, float grad_scale, int ncol_lane, float& loss_acc, int lane) {
+    const int base = lane * (CHUNK + 1);
     M2 T = m2_identity();
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) T = m2_mul_interface(T, r[i]);
     M2 P = warp_exclusive_prefix(T, carry, lane);
-    M2 Pst[CHUNK];                 // true prefix BEFORE column i of the chunk
+    M2 Pck[CHUNK / 2];             // true prefix BEFORE column 2j of the chunk (checkpoint every 2 columns)
     M2 G = m2_identity();          // local inclusive prefix
     M2 B = M2{0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
-        Pst[i] = P;
+        if ((i & 1) == 0) Pck[i >> 1] = P;
         P = m2_mul_interface(P, r[i]);
         G = m2_mul_interface(G, r[i]);
-        float e = P.b / P.d;
-        float ge = gbuf[pad(lane * CHUNK + i)];
-        if (!(fabsf(e) <= FLT_MAX)) ge = 0.f;          // nan_to_num passes no gradient at NaN/inf
-        float inv = 1.f / P.d;
+        float inv = fast_rcp(P.d);
+        float e = echo_of(P.b, inv);
+        bool finite = fabsf(e) <= FLT_MAX;             // nan_to_num passes no gradient at NaN/inf
+        float ge;
+        if (LOSS == LOSS_MSE) {
+            float att = abuf[base + i];
+            float fr = __fmul_rn(nan_to_num(e), att);
+            float diff = fr - gbuf[base + i];
+            if (i < ncol_lane) loss_acc += diff * diff;
+            abuf[base + i] = fr;
+            ge = grad_scale * diff * att;
+        } else {
+            ge = gbuf[base + i] * abuf[base + i];
+        }
+        if (!finite) ge = 0.f;
+        gbuf[base + i] = ge;
         float da = ge * inv, db = -ge * e * inv;       // D = [[0, da], [0, db]]
         B.a += da * G.b; B.b += da * G.d; B.c += db * G.b; B.d += db * G.d;
     }
     // suffix scan of the affine maps X -> X * A + B, A = T^T
-    M2 A = m2_transpose(T);
-    M2 As = A, Bs = B;
+    M2 As = m2_transpose(T), Bs = B;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         M2 An = m2_shfl_down(As, d), Bn = m2_shfl_down(Bs, d);
@@ -88,44 +110,73 @@ __device__ __forceinline__ M2 backward_chunk(const float r[CHUNK], const M2& car
     M2 vout = m2_add(m2_mul(vin, As), Bs);             // valid on lane 0
 #pragma unroll
     for (int i = CHUNK - 1; i >= 0; --i) {
-        M2 Pc = m2_mul_interface(Pst[i], r[i]);
-        float e = Pc.b / Pc.d;
-        float ge = gbuf[pad(lane * CHUNK + i)];
-        if (!(fabsf(e) <= FLT_MAX)) ge = 0.f;
-        float inv = 1.f / Pc.d;
+        M2 Q = Pck[i >> 1];                            // prefix before column i
+        if (i & 1) Q = m2_mul_interface(Q, r[i - 1]);
+        M2 Pc = m2_mul_interface(Q, r[i]);
+        float inv = fast_rcp(Pc.d);
+        float e = echo_of(Pc.b, inv);
+        float ge = gbuf[base + i];
         M2 Pbar = V;
         Pbar.b += ge * inv;
-        Pbar.d += -ge * e * inv;
-        const M2& Q = Pst[i];
+        Pbar.d -= ge * e * inv;
         float ma = Q.a * Pbar.a + Q.c * Pbar.c;
         float mb = Q.a * Pbar.b + Q.c * Pbar.d;
         float mc = Q.b * Pbar.a + Q.d * Pbar.c;
         float rbar = -4.f * r[i] * ma + mb - mc;
-        gbuf[pad(lane * CHUNK + i)] = (rbar == rbar) ? rbar : 0.f;
+        gbuf[base + i] = (rbar == rbar) ? rbar : 0.f;
         V = m2_mul_interface_t(Pbar, r[i]);
     }
     return m2_shfl(vout, 0);
 }
 
 // coefficient of the interface owned by column c from the two impedances around it
-__device__ __forceinline__ float reflection(float z_prev, float z_cur) { return (z_cur - z_prev) / (z_prev + z_cur); }
+__device__ __forceinline__ float reflection(float z_prev, float z_cur) {
+    return __fmul_rn(__fsub_rn(z_cur, z_prev), fast_rcp(__fadd_rn(z_prev, z_cur)));
+}
+
+// attenuation table exp(-alpha c), c = 0..Sout-1, shared by the rays of a CTA
+__device__ __forceinline__ void fill_attenuation(float* att, int Sout, float alpha) {
+    for (int c = threadIdx.x; c < Sout; c += blockDim.x) att[c] = expf(-alpha * (float)c);
+    __syncthreads();
+}
+
+// lane's 16 reflection coefficients from the padded impedance buffer (slot s holds sample c0 + s - 1)
+__device__ __forceinline__ void chunk_reflections(const float* zbuf, int c0, int ncol, const float* median, float med,
+                                                  int lane, float r[CHUNK]) {
+    const int cl = lane * CHUNK;
+    float zp = zbuf[pad(cl)];
+#pragma unroll
+    for (int i = 0; i < CHUNK; ++i) {
+        float zc = zbuf[pad(cl + i + 1)];
+        int c = c0 + cl + i;
+        float ri = reflection(zp, zc);
+        if (c == 1 && median) ri = med;
+        r[i] = (c >= 1 && cl + i < ncol) ? ri : 0.f;
+        zp = zc;
+    }
+}
 
 // ---------------------------------------------------------------------------------------
 // forward render
 // ---------------------------------------------------------------------------------------
+constexpr int FWD_SMEM_PER_WARP = ZBUF + OBUF;
+
 template <int SAMPLER, int LAYOUT, bool POSE64>
 __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
     extern __shared__ float smem[];
+    float* att = smem;
+    fill_attenuation(att, p.Sout, p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
-    float* zbuf = smem + warp * (ZBUF + OBUF);
+    float* zbuf = smem + p.att_slots + warp * FWD_SMEM_PER_WARP;
     float* obuf = zbuf + ZBUF;
     const int64_t pose = ray / p.n_rays;
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
     const float med = p.median ? __ldg(p.median + pose) : 0.f;
     float* out = p.frame + ray * (int64_t)p.Sout;
+    if (lane == 0) zbuf[0] = 0.f;
 
     M2 carry = m2_identity();
     for (int s = 0; s < p.nseg; ++s) {
@@ -146,19 +197,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
         __syncwarp();
         // chunk phase: lane = 16 consecutive columns
         float r[CHUNK];
-        {
-            int cl = lane * CHUNK;
-            float zp = zbuf[pad(cl)];
-#pragma unroll
-            for (int i = 0; i < CHUNK; ++i) {
-                float zc = zbuf[pad(cl + i + 1)];
-                int c = c0 + cl + i;
-                float ri = reflection(zp, zc);
-                if (c == 1 && p.median) ri = med;
-                r[i] = (c >= 1 && cl + i < ncol) ? ri : 0.f;
-                zp = zc;
-            }
-        }
+        chunk_reflections(zbuf, c0, ncol, p.median, med, lane, r);
         carry = forward_chunk(r, carry, obuf, lane);
         if (p.seg_prefix && s + 1 < p.nseg && lane == 0) {
             float4* sp = (float4*)(p.seg_prefix + (ray * (p.nseg - 1) + s) * 4);
@@ -169,10 +208,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
 #pragma unroll 4
         for (int t = 0; t < ntile; ++t) {
             int idx = t * 32 + lane;
-            if (idx < ncol) {
-                int c = c0 + idx;
-                out[c] = obuf[pad(idx)] * expf(-p.alpha * (float)c);
-            }
+            if (idx < ncol) out[c0 + idx] = __fmul_rn(obuf[pad(idx)], att[c0 + idx]);
         }
         if (lane == 0) zbuf[pad(0)] = zbuf[pad(SEG)];   // sample c0+SEG-1 becomes the next segment's left neighbour
         __syncwarp();
@@ -180,17 +216,18 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
-// backward render
+// backward render (optionally fused with the forward and an MSE loss)
 // ---------------------------------------------------------------------------------------
-constexpr int BWD_SMEM_PER_WARP = ZBUF + OBUF + 3 * SEG;
+constexpr int BWD_SMEM_PER_WARP = ZBUF + 2 * OBUF + 3 * SEG;
 
 template <int SAMPLER, bool POSE64>
 __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const RaySetup<POSE64>& rs, int k, float zbar) {
-    // gradient volume is always LINEAR (it is handed back to torch / the MLP backward)
+    // the gradient volume is always LINEAR (it goes back to torch / the MLP backward)
     float p0 = rs.coord(0, k), p1 = rs.coord(1, k), p2 = rs.coord(2, k);
+    const uint32_t HW = (uint32_t)p.vol.H * p.vol.W, W = p.vol.W;
     if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
         int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), kk = nearest_index(p2, p.vol.W);
-        atomicAdd(p.grad_volume + ((int64_t)i * p.vol.H + j) * p.vol.W + kk, zbar);
+        atomicAdd(p.grad_volume + ((uint32_t)i * HW + (uint32_t)j * W + kk), zbar);
     } else {
         TriCell c;
         tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
@@ -202,76 +239,72 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
             int j = (q & 2) ? c.i1[1] : c.i0[1];
             int kk = (q & 1) ? c.i1[2] : c.i0[2];
             float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
-            if (w != 0.f) atomicAdd(p.grad_volume + ((int64_t)i * p.vol.H + j) * p.vol.W + kk, w * zbar);
+            if (w != 0.f) atomicAdd(p.grad_volume + ((uint32_t)i * HW + (uint32_t)j * W + kk), w * zbar);
         }
     }
 }
 
-template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD>
-__global__ void __launch_bounds__(128) render_bwd_kernel(const RenderParams p) {
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS>
+__global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p) {
     extern __shared__ float smem[];
+    float* att = smem;
+    fill_attenuation(att, p.Sout, p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
-    float* zbuf = smem + warp * BWD_SMEM_PER_WARP;
-    float* gbuf = zbuf + ZBUF;
-    float* dz = gbuf + OBUF;                 // [3][SEG] spatial gradient of Z at each sample
+    float* zbuf = smem + p.att_slots + warp * BWD_SMEM_PER_WARP;
+    float* gbuf = zbuf + ZBUF;               // target / upstream gradient in, d loss / d r out
+    float* abuf = gbuf + OBUF;               // attenuation in, frame out (LOSS_MSE)
+    float* dz = abuf + OBUF;                 // [3][SEG] spatial gradient of Z at each sample
     const int64_t pose = ray / p.n_rays;
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
     const float med = p.median ? __ldg(p.median + pose) : 0.f;
-    const float* gout = p.grad_frame + ray * (int64_t)p.Sout;
+    const float* gin = (LOSS == LOSS_MSE ? p.target : p.grad_frame) + ray * (int64_t)p.Sout;
+    float* fout = (LOSS == LOSS_MSE && p.frame) ? p.frame + ray * (int64_t)p.Sout : nullptr;
+    if (lane == 0) zbuf[0] = 0.f;
 
     M2 vin = M2{0.f, 0.f, 0.f, 0.f};
     float carry_rbar = 0.f, carry_z = 0.f;   // column c0+SEG of the later segment: its d loss/d r and its impedance
     float acc_s[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
+    float loss_acc = 0.f;
 
     for (int s = p.nseg - 1; s >= 0; --s) {
         const int c0 = s * SEG;
         const int ncol = min(SEG, p.Sout - c0);
         const int ntile = (ncol + 31) >> 5;
-        // gather phase (re-gather: nothing but the segment prefixes is saved by the forward)
+        // gather phase (nothing but the segment prefixes is saved by the forward)
 #pragma unroll 2
-        for (int t = 0; t < ntile; ++t) {
+        for (int t = 0; t < SEG / 32; ++t) {
             int idx = t * 32 + lane;
+            float gval = 0.f, aval = 0.f;
             if (idx < ncol) {
                 int c = c0 + idx, k = p.start + c;
                 float g[3];
                 float z = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
                 zbuf[pad(idx + 1)] = z;
                 if (POSE_GRAD) { dz[idx] = g[0]; dz[SEG + idx] = g[1]; dz[2 * SEG + idx] = g[2]; }
-                gbuf[pad(idx)] = __ldg(gout + c) * expf(-p.alpha * (float)c);
+                gval = __ldg(gin + c);
+                aval = att[c];
             }
+            gbuf[pad(idx)] = gval;           // columns that do not exist carry no gradient
+            abuf[pad(idx)] = aval;
         }
         if (s > 0 && lane == 0) {            // left neighbour of the segment's first column
             int k = p.start + c0 - 1;
             float g[3];
             zbuf[pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
         }
-        // columns that do not exist carry no gradient
-        for (int idx = ncol + lane; idx < SEG; idx += 32) gbuf[pad(idx)] = 0.f;
         __syncwarp();
 
         float r[CHUNK];
-        {
-            int cl = lane * CHUNK;
-            float zp = zbuf[pad(cl)];
-#pragma unroll
-            for (int i = 0; i < CHUNK; ++i) {
-                float zc = zbuf[pad(cl + i + 1)];
-                int c = c0 + cl + i;
-                float ri = reflection(zp, zc);
-                if (c == 1 && p.median) ri = med;
-                r[i] = (c >= 1 && cl + i < ncol) ? ri : 0.f;
-                zp = zc;
-            }
-        }
+        chunk_reflections(zbuf, c0, ncol, p.median, med, lane, r);
         M2 carry = m2_identity();
         if (s > 0) {
             float4 c4 = __ldg((const float4*)(p.seg_prefix + (ray * (p.nseg - 1) + (s - 1)) * 4));
             carry = M2{c4.x, c4.y, c4.z, c4.w};
         }
-        vin = backward_chunk(r, carry, vin, gbuf, lane);
+        vin = backward_chunk<LOSS>(r, carry, vin, gbuf, abuf, p.grad_scale, ncol - lane * CHUNK, loss_acc, lane);
         __syncwarp();
 
         // tile phase: d loss / d Z per sample, then pose partials and the volume scatter
@@ -280,13 +313,14 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const RenderParams p) {
             int idx = t * 32 + lane;
             if (idx < ncol) {
                 int c = c0 + idx;
+                if (fout) fout[c] = abuf[pad(idx)];
                 float zc = zbuf[pad(idx + 1)];
                 float zbar = 0.f;
                 // as the right-hand impedance of its own column's interface
                 if (c >= 1 && !(c == 1 && p.median)) {
                     float zp = zbuf[pad(idx)];
                     float sum = zp + zc;
-                    zbar += gbuf[pad(idx)] * (2.f * zp / (sum * sum));
+                    zbar += gbuf[pad(idx)] * fast_div(2.f * zp, sum * sum);
                 }
                 // as the left-hand impedance of the next column's interface
                 if (c + 1 < p.Sout && !(c == 0 && p.median)) {
@@ -294,7 +328,7 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const RenderParams p) {
                     if (idx + 1 < ncol) { zn = zbuf[pad(idx + 2)]; rb = gbuf[pad(idx + 1)]; }
                     else { zn = carry_z; rb = carry_rbar; }
                     float sum = zc + zn;
-                    zbar -= rb * (2.f * zn / (sum * sum));
+                    zbar -= rb * fast_div(2.f * zn, sum * sum);
                 }
                 if (!(zbar == zbar)) zbar = 0.f;
                 int k = p.start + c;
@@ -324,6 +358,10 @@ __global__ void __launch_bounds__(128) render_bwd_kernel(const RenderParams p) {
                 p.grad_dir[ray * 3 + a] = dd;
             }
         }
+    }
+    if (LOSS == LOSS_MSE && p.loss_partial) {
+        float l = warp_sum(loss_acc);
+        if (lane == 0) p.loss_partial[ray] = l;
     }
 }
 
@@ -368,9 +406,10 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= n_rays) return;
     const int Sout = N + 1, nseg = (Sout + SEG - 1) / SEG;
-    float* rbuf = smem + warp * (2 * OBUF + 4 * nseg);
+    float* rbuf = smem + warp * (3 * OBUF + 4 * nseg);
     float* gbuf = rbuf + OBUF;
-    float* prefix = gbuf + OBUF;             // carry entering segment s, 4 floats each
+    float* abuf = gbuf + OBUF;
+    float* prefix = abuf + OBUF;             // carry entering segment s, 4 floats each
     const float* rin = refl + ray * (int64_t)N;
     const float* gin = grad_echo + ray * (int64_t)Sout;
     float* gout = grad_refl + ray * (int64_t)N;
@@ -393,6 +432,7 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     }
     __syncwarp();
     M2 vin = M2{0.f, 0.f, 0.f, 0.f};
+    float unused = 0.f;
     for (int s = nseg - 1; s >= 0; --s) {
         const int c0 = s * SEG, ncol = min(SEG, Sout - c0);
         for (int idx = lane; idx < SEG; idx += 32) {
@@ -400,13 +440,14 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
             bool ok = idx < ncol;
             rbuf[pad(idx)] = (c >= 1 && ok) ? __ldg(rin + c - 1) : 0.f;
             gbuf[pad(idx)] = ok ? __ldg(gin + c) : 0.f;
+            abuf[pad(idx)] = 1.f;
         }
         __syncwarp();
         float r[CHUNK];
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) r[i] = rbuf[pad(lane * CHUNK + i)];
         M2 cs = M2{prefix[4 * s], prefix[4 * s + 1], prefix[4 * s + 2], prefix[4 * s + 3]};
-        vin = backward_chunk(r, cs, vin, gbuf, lane);
+        vin = backward_chunk<LOSS_GRAD>(r, cs, vin, gbuf, abuf, 0.f, 0, unused, lane);
         __syncwarp();
         for (int idx = lane; idx < ncol; idx += 32) {
             int c = c0 + idx;
@@ -414,6 +455,27 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
         }
         __syncwarp();
     }
+}
+
+// sum of per-ray partials -> one float (fixed order, single block)
+__global__ void reduce_sum_kernel(const float* __restrict__ partial, int64_t n, float scale, float* __restrict__ out) {
+    __shared__ double warp_part[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_part[w];
+        out[0] = (float)(t * (double)scale);
+    }
+}
+
+cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, cudaStream_t st) {
+    reduce_sum_kernel<<<1, 1024, 0, st>>>(partial, n, scale, out);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -426,60 +488,50 @@ static int warps_per_block(int64_t total_rays) {
     return 1;
 }
 
-template <int SAMPLER, int LAYOUT, bool POSE64>
-static cudaError_t launch_fwd_t(const RenderParams& p, cudaStream_t st) {
-    int wpb = warps_per_block(p.total_rays);
-    size_t smem = (size_t)wpb * (ZBUF + OBUF) * sizeof(float);
-    int64_t grid = (p.total_rays + wpb - 1) / wpb;
-    render_fwd_kernel<SAMPLER, LAYOUT, POSE64><<<(unsigned)grid, wpb * 32, smem, st>>>(p);
-    return cudaGetLastError();
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t smem) {
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaSuccess;
 }
 
 cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st) {
-#define DIFFUS_FWD_CASE(S, L, P64) \
-    if (sampler == S && layout == L && pose64 == (P64 ? 1 : 0)) return launch_fwd_t<S, L, P64>(p, st);
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, false)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, true)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, false)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, true)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, false)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, true)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false)
-    DIFFUS_FWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, true)
-#undef DIFFUS_FWD_CASE
+    int wpb = warps_per_block(p.total_rays);
+    size_t smem = ((size_t)p.att_slots + (size_t)wpb * FWD_SMEM_PER_WARP) * sizeof(float);
+    unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
+    DIFFUS_DISPATCH(auto k = render_fwd_kernel<S_, L_, P64_>; cudaError_t e = ensure_smem(k, smem);
+                    if (e != cudaSuccess) return e; k<<<grid, wpb * 32, smem, st>>>(p); return cudaGetLastError())
     return cudaErrorInvalidValue;
 }
 
-template <int SAMPLER, int LAYOUT, bool POSE64, bool PG, bool VG>
-static cudaError_t launch_bwd_t(const RenderParams& p, cudaStream_t st) {
-    int wpb = warps_per_block(p.total_rays);
-    size_t smem = (size_t)wpb * BWD_SMEM_PER_WARP * sizeof(float);
-    int64_t grid = (p.total_rays + wpb - 1) / wpb;
-    render_bwd_kernel<SAMPLER, LAYOUT, POSE64, PG, VG><<<(unsigned)grid, wpb * 32, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
-template <int SAMPLER, int LAYOUT, bool POSE64>
-static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, cudaStream_t st) {
-    if (SAMPLER == DIFFUS_SAMPLER_NEAREST) pg = false;     // no pose gradient exists (round+long cuts the graph)
-    if (pg && vg) return launch_bwd_t<SAMPLER, LAYOUT, POSE64, SAMPLER == DIFFUS_SAMPLER_TRILINEAR, true>(p, st);
-    if (pg) return launch_bwd_t<SAMPLER, LAYOUT, POSE64, SAMPLER == DIFFUS_SAMPLER_TRILINEAR, false>(p, st);
-    return launch_bwd_t<SAMPLER, LAYOUT, POSE64, false, true>(p, st);
+template <int S_, int L_, bool P64_, int LOSS>
+static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigned grid, int threads, size_t smem,
+                                cudaStream_t st) {
+    constexpr bool TRI = S_ == DIFFUS_SAMPLER_TRILINEAR;
+#define DIFFUS_BWD_GO(PG, VG)                                                   \
+    {                                                                           \
+        auto k = render_bwd_kernel<S_, L_, P64_, PG, VG, LOSS>;                 \
+        cudaError_t e = ensure_smem(k, smem);                                   \
+        if (e != cudaSuccess) return e;                                         \
+        k<<<grid, threads, smem, st>>>(p);                                      \
+        return cudaGetLastError();                                              \
+    }
+    if (!TRI) pg = false;                      // no pose gradient exists (round+long cuts the graph)
+    if (pg && vg) DIFFUS_BWD_GO(TRI, true)
+    if (pg) DIFFUS_BWD_GO(TRI, false)
+    if (vg) DIFFUS_BWD_GO(false, true)
+    DIFFUS_BWD_GO(false, false)                // loss / frame only
+#undef DIFFUS_BWD_GO
 }
 
 cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, bool vol_grad,
                               cudaStream_t st) {
-#define DIFFUS_BWD_CASE(S, L, P64) \
-    if (sampler == S && layout == L && pose64 == (P64 ? 1 : 0)) return launch_bwd_g<S, L, P64>(p, pose_grad, vol_grad, st);
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, false)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, true)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, false)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, true)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, false)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, true)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false)
-    DIFFUS_BWD_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, true)
-#undef DIFFUS_BWD_CASE
+    int wpb = warps_per_block(p.total_rays);
+    size_t smem = ((size_t)p.att_slots + (size_t)wpb * BWD_SMEM_PER_WARP) * sizeof(float);
+    unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
+    const bool mse = p.target != nullptr;
+    DIFFUS_DISPATCH(if (mse) return launch_bwd_g<S_, L_, P64_, LOSS_MSE>(p, pose_grad, vol_grad, grid, wpb * 32, smem, st);
+                    return launch_bwd_g<S_, L_, P64_, LOSS_GRAD>(p, pose_grad, vol_grad, grid, wpb * 32, smem, st))
     return cudaErrorInvalidValue;
 }
 
@@ -494,12 +546,9 @@ cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n
                             cudaStream_t st) {
     int wpb = warps_per_block(n_rays);
     int nseg = (N + 1 + SEG - 1) / SEG;
-    size_t smem = (size_t)wpb * (2 * OBUF + 4 * nseg) * sizeof(float);
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(echo_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    size_t smem = (size_t)wpb * (3 * OBUF + 4 * nseg) * sizeof(float);
+    cudaError_t e = ensure_smem(echo_bwd_kernel, smem);
+    if (e != cudaSuccess) return e;
     echo_bwd_kernel<<<(unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, smem, st>>>(refl, grad_echo, n_rays, N, grad_refl);
     return cudaGetLastError();
 }

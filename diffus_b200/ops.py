@@ -150,6 +150,7 @@ def render_bwd(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Optional[
         b.fwd.seg_prefix = _ptr(prefix)
         b.grad_frame = grad_frame.data_ptr()
         b.grad_volume, b.grad_sources, b.grad_directions = _ptr(gvol), _ptr(gsrc), _ptr(gdir)
+        b.target, b.loss, b.fwd.frame = None, None, None
         wbytes = lib.diffus_render_bwd_workspace_bytes(C.byref(b))
         ws = torch.empty((max(wbytes, 1),), dtype=torch.uint8, device=dev)
         b.workspace, b.workspace_bytes = ws.data_ptr(), wbytes
@@ -201,6 +202,102 @@ def _render_backward(ctx, grad_frame, grad_prefix):
 
 
 torch.library.register_autograd("diffus::render_fwd", _render_backward, setup_context=_render_setup)
+
+
+# ---------------------------------------------------------------------------------------
+# fused forward + MSE loss + backward: one gather pass per pose-recovery / training step
+# ---------------------------------------------------------------------------------------
+@torch.library.custom_op("diffus::render_mse", mutates_args=())
+def render_mse(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
+               directions: torch.Tensor, target: torch.Tensor, n_samples: int, start: int, alpha: float,
+               sampler: int, product_f32: bool, need_volume: bool, need_pose: bool,
+               want_frame: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """loss = mean((frame - target)^2) with d loss/d volume, d loss/d sources, d loss/d directions.
+
+    Returns ``(loss (1,), frame or empty, grad_volume or empty, grad_sources or empty,
+    grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns this is ONE kernel
+    launch (+ two tiny reductions); longer rays first run the forward kernel for the
+    512-column segment prefixes.
+    """
+    dev = _require_cuda(volume, bricks, sources, directions, target)
+    _check_inputs(volume, bricks, dims, sources, directions)
+    lib = _lib.load()
+    b = DiffusRenderBwdArgs()
+    with torch.cuda.device(dev):
+        P, R = _fill_render_args(b.fwd, volume, bricks, dims, sources, directions, n_samples, start, alpha,
+                                 sampler, product_f32)
+        sout = n_samples - start
+        if tuple(target.shape) != (P, R, sout) or target.dtype != torch.float32 or not target.is_contiguous():
+            raise _lib.DiffusError(f"target must be contiguous float32 {(P, R, sout)}")
+        need_pose = need_pose and sampler == SAMPLER_TRILINEAR
+        launches = 0
+        prefix = None
+        if _nseg(sout) > 1:
+            _, prefix = render_fwd(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
+                                   product_f32, True)
+        n = P * R * sout
+        def empty():                      # outputs of a custom op must not alias each other
+            return torch.empty((0,), dtype=torch.float32, device=dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        frame = torch.empty((P, R, sout), dtype=torch.float32, device=dev) if want_frame else empty()
+        gvol = torch.zeros(tuple(dims), dtype=torch.float32, device=dev) if need_volume else empty()
+        gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else empty()
+        gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else empty()
+        b.fwd.frame = _ptr(frame)
+        b.fwd.seg_prefix = _ptr(prefix)
+        b.grad_frame = None
+        b.grad_volume, b.grad_sources, b.grad_directions = _ptr(gvol), _ptr(gsrc), _ptr(gdir)
+        b.target, b.grad_scale, b.loss_scale, b.loss = target.data_ptr(), 2.0 / n, 1.0 / n, loss.data_ptr()
+        wbytes = lib.diffus_render_bwd_workspace_bytes(C.byref(b))
+        ws = torch.empty((max(wbytes, 1),), dtype=torch.uint8, device=dev)
+        b.workspace, b.workspace_bytes = ws.data_ptr(), wbytes
+        _lib.check(lib.diffus_render_backward(C.byref(b), _stream(dev)), "diffus_render_backward (fused MSE)")
+        _count(2 + (2 if start > 0 else 0) + (1 if need_pose else 0))
+    return loss, frame, gvol, gsrc, gdir
+
+
+@render_mse.register_fake
+def _(volume, bricks, dims, sources, directions, target, n_samples, start, alpha, sampler, product_f32, need_volume,
+      need_pose, want_frame):
+    P, R = sources.shape[0], directions.shape[-2]
+    need_pose = need_pose and sampler == SAMPLER_TRILINEAR
+    def e():
+        return volume.new_empty((0,), dtype=torch.float32)
+    return (volume.new_empty((1,), dtype=torch.float32),
+            volume.new_empty((P, R, n_samples - start), dtype=torch.float32) if want_frame else e(),
+            volume.new_empty(tuple(dims), dtype=torch.float32) if need_volume else e(),
+            volume.new_empty((P, 3), dtype=torch.float32) if need_pose else e(),
+            volume.new_empty((P, R, 3), dtype=torch.float32) if need_pose else e())
+
+
+class RenderMSELoss(torch.autograd.Function):
+    """Autograd wrapper of the fused step: the gradients are produced in the forward call."""
+
+    @staticmethod
+    def forward(ctx, volume, bricks, dims, sources, directions, target, n_samples, start, alpha, sampler,
+                product_f32, want_frame):
+        need_volume = ctx.needs_input_grad[0]
+        need_pose = (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) and sampler == SAMPLER_TRILINEAR
+        loss, frame, gvol, gsrc, gdir = render_mse(volume.detach(), bricks, dims, sources.detach(),
+                                                   directions.detach(), target, n_samples, start, alpha, sampler,
+                                                   product_f32, need_volume, need_pose, want_frame)
+        ctx.save_for_backward(gvol, gsrc, gdir)
+        ctx.flags = (need_volume, need_pose, sources.dtype, directions.dtype, directions.dim())
+        ctx.mark_non_differentiable(frame)
+        return loss.reshape(()), frame
+
+    @staticmethod
+    def backward(ctx, gloss, gframe):
+        gvol, gsrc, gdir = ctx.saved_tensors
+        need_volume, need_pose, sdt, ddt, ddim = ctx.flags
+        out_v = gvol * gloss if need_volume and ctx.needs_input_grad[0] else None
+        out_s = out_d = None
+        if need_pose and ctx.needs_input_grad[3]:
+            out_s = (gsrc * gloss).to(sdt)
+        if need_pose and ctx.needs_input_grad[4]:
+            d = gdir if ddim == 3 else gdir.sum(0)
+            out_d = (d * gloss).to(ddt)
+        return out_v, None, None, out_s, out_d, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------

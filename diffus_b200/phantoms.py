@@ -57,9 +57,15 @@ def mri_phantom(n: int = 256, kind: str = "t1", seed: int = 0) -> torch.Tensor:
 
 
 def intensity_to_impedance(mri: torch.Tensor) -> torch.Tensor:
-    """A smooth strictly positive stand-in for a trained MLP: air -> 400, tissue ~1.5e6."""
+    """A smooth strictly positive stand-in for a trained MLP.
+
+    Background (intensity 0) maps to coupling gel / water (1.48e6 Rayl) rather than air: a
+    probe is in contact with tissue, and an air gap (Z = 400, |r| ~ 1) makes the layered-medium
+    echo P01/P11 resonate to values of 1e3 and more, which says nothing about a renderer.
+    Tissue lands in 1.5e6 .. 1.7e6, so |r| stays below ~0.07 as in the reference's tissue tables.
+    """
     u = mri / 2500.0
-    return (400.0 + 1.45e6 * torch.tanh(4 * u) + 2.5e5 * u).contiguous()
+    return (1.48e6 + 2.2e5 * torch.tanh(2 * u)).contiguous()
 
 
 def fan_directions(median: torch.Tensor, normal_hint: torch.Tensor, opening_angle: float,

@@ -98,6 +98,36 @@ def render_frames(volume, sources: torch.Tensor, directions: torch.Tensor, num_s
     return frame
 
 
+def render_mse_loss(volume, sources: torch.Tensor, directions: torch.Tensor, target: torch.Tensor,
+                    num_samples: int, attenuation_coeff: float = 0.5, start=0, *, sampler: str = "trilinear",
+                    return_frame: bool = False):
+    """``mse_loss(render_frames(...), target)`` as ONE fused forward + loss + backward pass.
+
+    The step every pose-recovery / MLP-training loop of the reference runs (render, compare
+    with the real frames, back-propagate): the kernel gathers each sample once, evaluates
+    the frame, the loss and the reverse scan in shared memory, and hands autograd the
+    finished gradients.  Returns the scalar loss (differentiable w.r.t. ``volume`` and, for
+    the trilinear sampler, ``sources`` / ``directions``), plus the frames if asked.
+    """
+    bricks = None
+    if isinstance(volume, PreparedVolume):
+        bricks, volume = volume.bricks, volume.volume
+    device = volume.device
+    sid = _sampler_id(sampler)
+    src, dirs, product_f32 = _canon_pose(sources, directions, device)
+    if src.dim() == 1:
+        src = src.unsqueeze(0)
+    vol32 = (volume if volume.dtype == torch.float32 else volume.float()).contiguous()
+    start_i = _resolve_start(start, num_samples)
+    tgt = target.to(torch.float32).contiguous()
+    if tgt.dim() == 2:
+        tgt = tgt.unsqueeze(0)
+    loss, frame = ops.RenderMSELoss.apply(vol32, bricks, list(volume.shape), src.contiguous(), dirs.contiguous(), tgt,
+                                          int(num_samples), int(start_i), float(attenuation_coeff), sid, product_f32,
+                                          bool(return_frame))
+    return (loss, frame) if return_frame else loss
+
+
 def _resolve_start(start, num_samples: int) -> int:
     """``src/renderer.py:237-240``: a float start is a fraction of ``num_samples``."""
     if type(start) is float:

@@ -93,7 +93,8 @@ typedef struct DiffusRenderArgs {
  * accumulate semantics of src/renderer.py:758's backward) and, for the trilinear sampler,
  * d loss / d source and d loss / d directions.  Any of the three outputs may be NULL. */
 typedef struct DiffusRenderBwdArgs {
-    DiffusRenderArgs fwd;       /* same inputs as the forward; fwd.frame may be NULL;
+    DiffusRenderArgs fwd;       /* same inputs as the forward; fwd.frame is only written in the
+                                   fused-loss mode below and may be NULL;
                                    fwd.seg_prefix = the buffer the forward filled (required
                                    when S-start > 512)                                        */
     const float* grad_frame;    /* (P,R,S-start)                                             */
@@ -101,6 +102,15 @@ typedef struct DiffusRenderBwdArgs {
     float* grad_sources;        /* (P,3) overwritten; trilinear only                         */
     float* grad_directions;     /* (P,R,3) overwritten; trilinear only (per pose, also when
                                    the directions were shared)                                */
+    /* Fused forward + MSE loss + backward (one gather pass): when `target` is not NULL,
+     * grad_frame is ignored and the kernel itself renders the frame and uses
+     * d loss / d frame = grad_scale * (frame - target).  Optional outputs: fwd.frame (the
+     * rendered frames) and loss[0] = loss_scale * sum((frame - target)^2).  With the mean
+     * over n = P*R*(S-start) elements: grad_scale = 2/n, loss_scale = 1/n.               */
+    const float* target;        /* (P,R,S-start) or NULL                                     */
+    float grad_scale;
+    float loss_scale;
+    float* loss;                /* 1 float or NULL                                           */
     void* workspace;            /* diffus_render_bwd_workspace_bytes() bytes                 */
     int64_t workspace_bytes;
 } DiffusRenderBwdArgs;
