@@ -59,7 +59,7 @@ RenderParams pack(const DiffusRenderArgs* a) {
     p.S = a->n_samples;
     p.start = a->start;
     p.Sout = a->n_samples - a->start;
-    p.nseg = (p.Sout + SEG - 1) / SEG;
+    p.nprefix = (p.Sout + PREFIX_STRIDE - 1) / PREFIX_STRIDE - 1;
     p.att_slots = (p.Sout + 3) / 4 * 4;
     p.alpha = a->attenuation;
     p.frame = a->frame;
@@ -181,7 +181,7 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     if (!pose_grad && !vol_grad && !(mse && (b->loss || a->frame))) return DIFFUS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     RenderParams p = pack(a);
-    if (p.nseg > 1 && !a->seg_prefix) return DIFFUS_E_NULL;
+    if (p.nprefix > 0 && !a->seg_prefix) return DIFFUS_E_NULL;
     BwdWorkspace w = bwd_workspace(b, b->workspace);
     if (w.bytes > 0 && (!b->workspace || b->workspace_bytes < w.bytes)) return DIFFUS_E_WORKSPACE;
     const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;

@@ -25,14 +25,26 @@
 
 namespace diffus {
 
-constexpr int SEG = 512;    // columns per segment (= 32 lanes x CHUNK)
-constexpr int CHUNK = 16;   // columns per lane in the chunk phase
 constexpr unsigned FULL = 0xffffffffu;
 
-// padded shared-memory slot: stride-17 rows make the lane*16+i pattern conflict free
-__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
-constexpr int ZBUF = SEG + 1 + (SEG + 1) / 16 + 3;   // slots 0..SEG (slot 0 = sample c0-1)
-constexpr int OBUF = SEG + SEG / 16 + 3;             // slots 0..SEG-1
+// Geometry of one warp pass: 32 lanes x CH consecutive columns per lane.  The forward uses
+// CH = 16 (one warp scan per 512 columns); the backward keeps per-column prefixes in
+// registers for its reverse sweep and uses CH = 8 to stay at 5+ CTAs per SM without spills.
+template <int CH>
+struct Geo {
+    static constexpr int CHUNK = CH;
+    static constexpr int SEG = 32 * CH;
+    // padded shared-memory slot: rows of CH+1 floats make the lane*CH+i pattern conflict free
+    __device__ __forceinline__ static int pad(int i) { return i + i / CH; }
+    static constexpr int ZBUF = SEG + 1 + (SEG + 1) / CH + 3;   // slots 0..SEG (slot 0 = sample c0-1)
+    static constexpr int OBUF = SEG + SEG / CH + 3;             // slots 0..SEG-1
+};
+using FwdGeo = Geo<16>;
+using BwdGeo = Geo<8>;
+// The forward saves its transfer-matrix carry at every PREFIX_STRIDE columns; the backward
+// gathers PREFIX_STRIDE columns at a time and walks them as BWD_SUB sub-segments of BwdGeo::SEG.
+constexpr int PREFIX_STRIDE = FwdGeo::SEG;
+constexpr int BWD_SUB = PREFIX_STRIDE / BwdGeo::SEG;
 
 struct M2 {          // [[a, b], [c, d]]
     float a, b, c, d;
@@ -242,11 +254,12 @@ struct RenderParams {
     int64_t dir_pose_stride;
     int product_f32;
     int64_t n_poses, n_rays, total_rays;
-    int S, start, Sout, nseg;
+    int S, start, Sout;
+    int nprefix;                // saved prefixes per ray: ceil(Sout / PREFIX_STRIDE) - 1
     int att_slots;              // floats reserved at the start of dynamic smem for the attenuation table
     float alpha;
     float* frame;
-    float* seg_prefix;          // (total_rays, nseg-1, 4) or null
+    float* seg_prefix;          // (total_rays, nprefix, 4) or null
     const float* median;        // (P) replacement for r_1 when start > 0, else null
     // backward
     const float* grad_frame;

@@ -30,17 +30,20 @@ __device__ __forceinline__ M2 warp_exclusive_prefix(const M2& chunk_total, const
 }
 
 // Forward chunk phase for one segment.  `r[i]` must hold the coefficient of column
-// c0 + lane*16 + i (0 for columns that do not exist).  Writes echo (NaN -> 0) to obuf and
-// returns the updated carry (prefix through the last column of the segment).
-__device__ __forceinline__ M2 forward_chunk(const float r[CHUNK], M2 carry, float* obuf, int lane) {
+// c0 + lane*CH + i (0 for columns that do not exist).  Writes echo (NaN -> 0) to obuf and
+// returns the updated carry (prefix through the last column of the segment); `mid` gets
+// the prefix before the segment's middle column (lane 16's exclusive prefix).
+template <class G>
+__device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, float* obuf, int lane, M2& mid) {
     M2 T = m2_identity();
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) T = m2_mul_interface(T, r[i]);
+    for (int i = 0; i < G::CHUNK; ++i) T = m2_mul_interface(T, r[i]);
     M2 P = warp_exclusive_prefix(T, carry, lane);
+    mid = m2_shfl(P, 16);
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) {
+    for (int i = 0; i < G::CHUNK; ++i) {
         P = m2_mul_interface(P, r[i]);
-        obuf[lane * (CHUNK + 1) + i] = nan_to_num(echo_of(P.b, fast_rcp(P.d)));
+        obuf[lane * (G::CHUNK + 1) + i] = nan_to_num(echo_of(P.b, fast_rcp(P.d)));
     }
     return m2_shfl(P, 31);
 }
@@ -53,15 +56,16 @@ __device__ __forceinline__ M2 forward_chunk(const float r[CHUNK], M2 carry, floa
 constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 
 // Backward chunk phase for one segment.
-//   r[i]        coefficient of column c0 + lane*16 + i (0 where the column does not exist)
+//   r[i]        coefficient of column c0 + lane*CH + i (0 where the column does not exist)
 //   gbuf/abuf   see above; on return gbuf holds d loss / d r per column
 //   carry       forward prefix P through the column before the segment
 //   vin         adjoint flowing into the segment's last column from later segments
 //   ncol_lane   number of existing columns in this lane's chunk (for the loss sum)
 // returns the adjoint flowing out of the segment's first column (into the previous segment)
-template <int LOSS>
-__device__ __forceinline__ M2 backward_chunk(const float r[CHUNK], const M2& carry, const M2& vin, float* gbuf,
+template <class G_, int LOSS>
+__device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              float* abuf, float grad_scale, int ncol_lane, float& loss_acc, int lane) {
+    constexpr int CHUNK = G_::CHUNK;
     const int base = lane * (CHUNK + 1);
     M2 T = m2_identity();
 #pragma unroll
@@ -140,14 +144,15 @@ __device__ __forceinline__ void fill_attenuation(float* att, int Sout, float alp
     __syncthreads();
 }
 
-// lane's 16 reflection coefficients from the padded impedance buffer (slot s holds sample c0 + s - 1)
+// lane's CH reflection coefficients from the padded impedance buffer (slot s holds sample c0 + s - 1)
+template <class G>
 __device__ __forceinline__ void chunk_reflections(const float* zbuf, int c0, int ncol, const float* median, float med,
-                                                  int lane, float r[CHUNK]) {
-    const int cl = lane * CHUNK;
-    float zp = zbuf[pad(cl)];
+                                                  int lane, float r[G::CHUNK], int col_off = 0) {
+    const int cl = col_off + lane * G::CHUNK;
+    float zp = zbuf[G::pad(cl)];
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) {
-        float zc = zbuf[pad(cl + i + 1)];
+    for (int i = 0; i < G::CHUNK; ++i) {
+        float zc = zbuf[G::pad(cl + i + 1)];
         int c = c0 + cl + i;
         float ri = reflection(zp, zc);
         if (c == 1 && median) ri = med;
@@ -159,10 +164,17 @@ __device__ __forceinline__ void chunk_reflections(const float* zbuf, int c0, int
 // ---------------------------------------------------------------------------------------
 // forward render
 // ---------------------------------------------------------------------------------------
-constexpr int FWD_SMEM_PER_WARP = ZBUF + OBUF;
+constexpr int FWD_SMEM_PER_WARP = FwdGeo::ZBUF + FwdGeo::OBUF;
+
+__device__ __forceinline__ void store_prefix(const RenderParams& p, int64_t ray, int col, const M2& m) {
+    // prefix before column `col` (a positive multiple of PREFIX_STRIDE below Sout)
+    float4* sp = (float4*)(p.seg_prefix + (ray * p.nprefix + (col / PREFIX_STRIDE - 1)) * 4);
+    *sp = make_float4(m.a, m.b, m.c, m.d);
+}
 
 template <int SAMPLER, int LAYOUT, bool POSE64>
 __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
+    using G = FwdGeo;
     extern __shared__ float smem[];
     float* att = smem;
     fill_attenuation(att, p.Sout, p.alpha);
@@ -170,18 +182,19 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
     float* zbuf = smem + p.att_slots + warp * FWD_SMEM_PER_WARP;
-    float* obuf = zbuf + ZBUF;
+    float* obuf = zbuf + G::ZBUF;
     const int64_t pose = ray / p.n_rays;
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
     const float med = p.median ? __ldg(p.median + pose) : 0.f;
     float* out = p.frame + ray * (int64_t)p.Sout;
     if (lane == 0) zbuf[0] = 0.f;
+    const int nseg = (p.Sout + G::SEG - 1) / G::SEG;
 
     M2 carry = m2_identity();
-    for (int s = 0; s < p.nseg; ++s) {
-        const int c0 = s * SEG;
-        const int ncol = min(SEG, p.Sout - c0);
+    for (int s = 0; s < nseg; ++s) {
+        const int c0 = s * G::SEG;
+        const int ncol = min(G::SEG, p.Sout - c0);
         // gather phase: lane = consecutive sample
         const int ntile = (ncol + 31) >> 5;
 #pragma unroll 4
@@ -191,26 +204,24 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
                 int k = p.start + c0 + idx;
                 float g[3];
                 float z = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
-                zbuf[pad(idx + 1)] = z;
+                zbuf[G::pad(idx + 1)] = z;
             }
         }
         __syncwarp();
         // chunk phase: lane = 16 consecutive columns
-        float r[CHUNK];
-        chunk_reflections(zbuf, c0, ncol, p.median, med, lane, r);
-        carry = forward_chunk(r, carry, obuf, lane);
-        if (p.seg_prefix && s + 1 < p.nseg && lane == 0) {
-            float4* sp = (float4*)(p.seg_prefix + (ray * (p.nseg - 1) + s) * 4);
-            *sp = make_float4(carry.a, carry.b, carry.c, carry.d);
-        }
+        float r[G::CHUNK];
+        chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r);
+        M2 mid;
+        carry = forward_chunk<G>(r, carry, obuf, lane, mid);
+        if (p.seg_prefix && lane == 0 && c0 + G::SEG < p.Sout) store_prefix(p, ray, c0 + G::SEG, carry);
         __syncwarp();
         // tile phase: attenuate and write, lane = consecutive column
 #pragma unroll 4
         for (int t = 0; t < ntile; ++t) {
             int idx = t * 32 + lane;
-            if (idx < ncol) out[c0 + idx] = __fmul_rn(obuf[pad(idx)], att[c0 + idx]);
+            if (idx < ncol) out[c0 + idx] = __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]);
         }
-        if (lane == 0) zbuf[pad(0)] = zbuf[pad(SEG)];   // sample c0+SEG-1 becomes the next segment's left neighbour
+        if (lane == 0) zbuf[G::pad(0)] = zbuf[G::pad(G::SEG)];   // sample c0+SEG-1 becomes the next segment's left neighbour
         __syncwarp();
     }
 }
@@ -218,7 +229,10 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
 // ---------------------------------------------------------------------------------------
 // backward render (optionally fused with the forward and an MSE loss)
 // ---------------------------------------------------------------------------------------
-constexpr int BWD_SMEM_PER_WARP = ZBUF + 2 * OBUF + 3 * SEG;
+// buffers for PREFIX_STRIDE columns in the backward's padding (rows of CHUNK+1 floats)
+constexpr int BWD_ZBUF = PREFIX_STRIDE + 1 + (PREFIX_STRIDE + 1) / BwdGeo::CHUNK + 3;
+constexpr int BWD_OBUF = PREFIX_STRIDE + PREFIX_STRIDE / BwdGeo::CHUNK + 3;
+constexpr int BWD_SMEM_PER_WARP = BWD_ZBUF + 2 * BWD_OBUF + 3 * PREFIX_STRIDE;
 
 template <int SAMPLER, bool POSE64>
 __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const RaySetup<POSE64>& rs, int k, float zbar) {
@@ -246,6 +260,8 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
 
 template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS>
 __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p) {
+    using G = BwdGeo;
+    constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
     extern __shared__ float smem[];
     float* att = smem;
     fill_attenuation(att, p.Sout, p.alpha);
@@ -253,9 +269,9 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
     float* zbuf = smem + p.att_slots + warp * BWD_SMEM_PER_WARP;
-    float* gbuf = zbuf + ZBUF;               // target / upstream gradient in, d loss / d r out
-    float* abuf = gbuf + OBUF;               // attenuation in, frame out (LOSS_MSE)
-    float* dz = abuf + OBUF;                 // [3][SEG] spatial gradient of Z at each sample
+    float* gbuf = zbuf + BWD_ZBUF;           // target / upstream gradient in, d loss / d r out
+    float* abuf = gbuf + BWD_OBUF;           // attenuation in, frame out (LOSS_MSE)
+    float* dz = abuf + BWD_OBUF;             // [3][SS] spatial gradient of Z at each sample
     const int64_t pose = ray / p.n_rays;
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
@@ -263,69 +279,94 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     const float* gin = (LOSS == LOSS_MSE ? p.target : p.grad_frame) + ray * (int64_t)p.Sout;
     float* fout = (LOSS == LOSS_MSE && p.frame) ? p.frame + ray * (int64_t)p.Sout : nullptr;
     if (lane == 0) zbuf[0] = 0.f;
+    const int nss = (p.Sout + SS - 1) / SS;
 
     M2 vin = M2{0.f, 0.f, 0.f, 0.f};
-    float carry_rbar = 0.f, carry_z = 0.f;   // column c0+SEG of the later segment: its d loss/d r and its impedance
+    float carry_rbar = 0.f, carry_z = 0.f;   // first column of the later pass: its d loss/d r and its impedance
     float acc_s[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
     float loss_acc = 0.f;
 
-    for (int s = p.nseg - 1; s >= 0; --s) {
-        const int c0 = s * SEG;
-        const int ncol = min(SEG, p.Sout - c0);
+    for (int s = nss - 1; s >= 0; --s) {
+        const int c0 = s * SS;
+        const int ncol = min(SS, p.Sout - c0);
         const int ntile = (ncol + 31) >> 5;
-        // gather phase (nothing but the segment prefixes is saved by the forward)
+        const int nsub = (ncol + G::SEG - 1) / G::SEG;
+        // gather phase: one pass over the volume for these columns
 #pragma unroll 2
-        for (int t = 0; t < SEG / 32; ++t) {
+        for (int t = 0; t < nsub * (G::SEG / 32); ++t) {
             int idx = t * 32 + lane;
             float gval = 0.f, aval = 0.f;
             if (idx < ncol) {
                 int c = c0 + idx, k = p.start + c;
                 float g[3];
                 float z = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
-                zbuf[pad(idx + 1)] = z;
-                if (POSE_GRAD) { dz[idx] = g[0]; dz[SEG + idx] = g[1]; dz[2 * SEG + idx] = g[2]; }
+                zbuf[G::pad(idx + 1)] = z;
+                if (POSE_GRAD) { dz[idx] = g[0]; dz[SS + idx] = g[1]; dz[2 * SS + idx] = g[2]; }
                 gval = __ldg(gin + c);
                 aval = att[c];
             }
-            gbuf[pad(idx)] = gval;           // columns that do not exist carry no gradient
-            abuf[pad(idx)] = aval;
+            gbuf[G::pad(idx)] = gval;        // columns that do not exist carry no gradient
+            abuf[G::pad(idx)] = aval;
         }
-        if (s > 0 && lane == 0) {            // left neighbour of the segment's first column
+        if (s > 0 && lane == 0) {            // left neighbour of the pass's first column
             int k = p.start + c0 - 1;
             float g[3];
-            zbuf[pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
+            zbuf[G::pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
         }
         __syncwarp();
 
-        float r[CHUNK];
-        chunk_reflections(zbuf, c0, ncol, p.median, med, lane, r);
-        M2 carry = m2_identity();
+        // forward prefixes entering each sub-segment (the first one comes from the forward kernel)
+        M2 carry[BWD_SUB];
+        carry[0] = m2_identity();
         if (s > 0) {
-            float4 c4 = __ldg((const float4*)(p.seg_prefix + (ray * (p.nseg - 1) + (s - 1)) * 4));
-            carry = M2{c4.x, c4.y, c4.z, c4.w};
+            float4 c4 = __ldg((const float4*)(p.seg_prefix + (ray * p.nprefix + (s - 1)) * 4));
+            carry[0] = M2{c4.x, c4.y, c4.z, c4.w};
         }
-        vin = backward_chunk<LOSS>(r, carry, vin, gbuf, abuf, p.grad_scale, ncol - lane * CHUNK, loss_acc, lane);
+        float r[G::CHUNK];
+#pragma unroll
+        for (int h = 0; h + 1 < BWD_SUB; ++h) {
+            if (h + 1 < nsub) {
+                chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, h * G::SEG);
+                M2 T = m2_identity();
+#pragma unroll
+                for (int i = 0; i < G::CHUNK; ++i) T = m2_mul_interface(T, r[i]);
+                M2 E = warp_exclusive_prefix(T, carry[h], lane);
+                carry[h + 1] = m2_shfl(m2_mul(E, T), 31);
+            } else {
+                carry[h + 1] = carry[h];
+            }
+        }
+        // reverse scan, last sub-segment first
+#pragma unroll
+        for (int h = BWD_SUB - 1; h >= 0; --h) {
+            if (h < nsub) {
+                const int off = h * G::SEG;
+                chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, off);
+                vin = backward_chunk<G, LOSS>(r, carry[h], vin, gbuf + G::pad(off), abuf + G::pad(off), p.grad_scale,
+                                              ncol - off - lane * G::CHUNK, loss_acc, lane);
+            }
+        }
         __syncwarp();
 
         // tile phase: d loss / d Z per sample, then pose partials and the volume scatter
-        float next_carry_rbar = gbuf[pad(0)], next_carry_z = zbuf[pad(1)];
+        float next_carry_rbar = gbuf[G::pad(0)], next_carry_z = zbuf[G::pad(1)];
         for (int t = 0; t < ntile; ++t) {
             int idx = t * 32 + lane;
             if (idx < ncol) {
                 int c = c0 + idx;
-                if (fout) fout[c] = abuf[pad(idx)];
-                float zc = zbuf[pad(idx + 1)];
+                if (fout) fout[c] = abuf[G::pad(idx)];
+                float zc = zbuf[G::pad(idx + 1)];
                 float zbar = 0.f;
                 // as the right-hand impedance of its own column's interface
                 if (c >= 1 && !(c == 1 && p.median)) {
-                    float zp = zbuf[pad(idx)];
+                    float zp = zbuf[G::pad(idx)];
                     float sum = zp + zc;
-                    zbar += gbuf[pad(idx)] * fast_div(2.f * zp, sum * sum);
+                    zbar += gbuf[G::pad(idx)] * fast_div(2.f * zp, sum * sum);
                 }
                 // as the left-hand impedance of the next column's interface
                 if (c + 1 < p.Sout && !(c == 0 && p.median)) {
                     float zn, rb;
-                    if (idx + 1 < ncol) { zn = zbuf[pad(idx + 2)]; rb = gbuf[pad(idx + 1)]; }
+                    if (idx + 1 < ncol) { zn = zbuf[G::pad(idx + 2)]; rb = gbuf[G::pad(idx + 1)]; }
                     else { zn = carry_z; rb = carry_rbar; }
                     float sum = zc + zn;
                     zbar -= rb * fast_div(2.f * zn, sum * sum);
@@ -336,7 +377,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                     float kf = (float)k;
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        float ga = zbar * dz[a * SEG + idx];
+                        float ga = zbar * dz[a * SS + idx];
                         acc_s[a] += ga;
                         acc_d[a] += kf * ga;
                     }
@@ -344,7 +385,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                 if (VOL_GRAD && zbar != 0.f) scatter_volume_grad<SAMPLER, POSE64>(p, rs, k, zbar);
             }
         }
-        if (p.first_rbar && s == 0 && lane == 0) p.first_rbar[ray] = gbuf[pad(1)];
+        if (p.first_rbar && s == 0 && lane == 0) p.first_rbar[ray] = gbuf[G::pad(1)];
         carry_rbar = __shfl_sync(FULL, next_carry_rbar, 0);
         carry_z = __shfl_sync(FULL, next_carry_z, 0);
         __syncwarp();
@@ -371,29 +412,31 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) echo_fwd_kernel(const float* __restrict__ refl, int64_t n_rays, int N,
                                                        float* __restrict__ echo) {
+    using G = FwdGeo;
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= n_rays) return;
-    float* rbuf = smem + warp * (2 * OBUF);
-    float* obuf = rbuf + OBUF;
-    const int Sout = N + 1, nseg = (Sout + SEG - 1) / SEG;
+    float* rbuf = smem + warp * (2 * G::OBUF);
+    float* obuf = rbuf + G::OBUF;
+    const int Sout = N + 1, nseg = (Sout + G::SEG - 1) / G::SEG;
     const float* rin = refl + ray * (int64_t)N;
     float* out = echo + ray * (int64_t)Sout;
     M2 carry = m2_identity();
     for (int s = 0; s < nseg; ++s) {
-        const int c0 = s * SEG, ncol = min(SEG, Sout - c0);
-        for (int idx = lane; idx < SEG; idx += 32) {
+        const int c0 = s * G::SEG, ncol = min(G::SEG, Sout - c0);
+        for (int idx = lane; idx < G::SEG; idx += 32) {
             int c = c0 + idx;
-            rbuf[pad(idx)] = (c >= 1 && idx < ncol) ? __ldg(rin + c - 1) : 0.f;
+            rbuf[G::pad(idx)] = (c >= 1 && idx < ncol) ? __ldg(rin + c - 1) : 0.f;
         }
         __syncwarp();
-        float r[CHUNK];
+        float r[G::CHUNK];
 #pragma unroll
-        for (int i = 0; i < CHUNK; ++i) r[i] = rbuf[pad(lane * CHUNK + i)];
-        carry = forward_chunk(r, carry, obuf, lane);
+        for (int i = 0; i < G::CHUNK; ++i) r[i] = rbuf[G::pad(lane * G::CHUNK + i)];
+        M2 mid;
+        carry = forward_chunk<G>(r, carry, obuf, lane, mid);
         __syncwarp();
-        for (int idx = lane; idx < ncol; idx += 32) out[c0 + idx] = obuf[pad(idx)];
+        for (int idx = lane; idx < ncol; idx += 32) out[c0 + idx] = obuf[G::pad(idx)];
         __syncwarp();
     }
 }
@@ -401,31 +444,32 @@ __global__ void __launch_bounds__(128) echo_fwd_kernel(const float* __restrict__
 // two passes over the segments: forward to collect the prefixes, then the reverse scan
 __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__ refl, const float* __restrict__ grad_echo,
                                                        int64_t n_rays, int N, float* __restrict__ grad_refl) {
+    using G = BwdGeo;
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= n_rays) return;
-    const int Sout = N + 1, nseg = (Sout + SEG - 1) / SEG;
-    float* rbuf = smem + warp * (3 * OBUF + 4 * nseg);
-    float* gbuf = rbuf + OBUF;
-    float* abuf = gbuf + OBUF;
-    float* prefix = abuf + OBUF;             // carry entering segment s, 4 floats each
+    const int Sout = N + 1, nseg = (Sout + G::SEG - 1) / G::SEG;
+    float* rbuf = smem + warp * (3 * G::OBUF + 4 * nseg);
+    float* gbuf = rbuf + G::OBUF;
+    float* abuf = gbuf + G::OBUF;
+    float* prefix = abuf + G::OBUF;          // carry entering segment s, 4 floats each
     const float* rin = refl + ray * (int64_t)N;
     const float* gin = grad_echo + ray * (int64_t)Sout;
     float* gout = grad_refl + ray * (int64_t)N;
     M2 carry = m2_identity();
     for (int s = 0; s < nseg; ++s) {
-        const int c0 = s * SEG, ncol = min(SEG, Sout - c0);
+        const int c0 = s * G::SEG, ncol = min(G::SEG, Sout - c0);
         if (lane == 0) { prefix[4 * s] = carry.a; prefix[4 * s + 1] = carry.b; prefix[4 * s + 2] = carry.c; prefix[4 * s + 3] = carry.d; }
         if (s + 1 == nseg) break;
-        for (int idx = lane; idx < SEG; idx += 32) {
+        for (int idx = lane; idx < G::SEG; idx += 32) {
             int c = c0 + idx;
-            rbuf[pad(idx)] = (c >= 1 && idx < ncol) ? __ldg(rin + c - 1) : 0.f;
+            rbuf[G::pad(idx)] = (c >= 1 && idx < ncol) ? __ldg(rin + c - 1) : 0.f;
         }
         __syncwarp();
         M2 T = m2_identity();
 #pragma unroll
-        for (int i = 0; i < CHUNK; ++i) T = m2_mul_interface(T, rbuf[pad(lane * CHUNK + i)]);
+        for (int i = 0; i < G::CHUNK; ++i) T = m2_mul_interface(T, rbuf[G::pad(lane * G::CHUNK + i)]);
         M2 P = warp_exclusive_prefix(T, carry, lane);
         carry = m2_shfl(m2_mul(P, T), 31);
         __syncwarp();
@@ -434,24 +478,24 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     M2 vin = M2{0.f, 0.f, 0.f, 0.f};
     float unused = 0.f;
     for (int s = nseg - 1; s >= 0; --s) {
-        const int c0 = s * SEG, ncol = min(SEG, Sout - c0);
-        for (int idx = lane; idx < SEG; idx += 32) {
+        const int c0 = s * G::SEG, ncol = min(G::SEG, Sout - c0);
+        for (int idx = lane; idx < G::SEG; idx += 32) {
             int c = c0 + idx;
             bool ok = idx < ncol;
-            rbuf[pad(idx)] = (c >= 1 && ok) ? __ldg(rin + c - 1) : 0.f;
-            gbuf[pad(idx)] = ok ? __ldg(gin + c) : 0.f;
-            abuf[pad(idx)] = 1.f;
+            rbuf[G::pad(idx)] = (c >= 1 && ok) ? __ldg(rin + c - 1) : 0.f;
+            gbuf[G::pad(idx)] = ok ? __ldg(gin + c) : 0.f;
+            abuf[G::pad(idx)] = 1.f;
         }
         __syncwarp();
-        float r[CHUNK];
+        float r[G::CHUNK];
 #pragma unroll
-        for (int i = 0; i < CHUNK; ++i) r[i] = rbuf[pad(lane * CHUNK + i)];
+        for (int i = 0; i < G::CHUNK; ++i) r[i] = rbuf[G::pad(lane * G::CHUNK + i)];
         M2 cs = M2{prefix[4 * s], prefix[4 * s + 1], prefix[4 * s + 2], prefix[4 * s + 3]};
-        vin = backward_chunk<LOSS_GRAD>(r, cs, vin, gbuf, abuf, 0.f, 0, unused, lane);
+        vin = backward_chunk<G, LOSS_GRAD>(r, cs, vin, gbuf, abuf, 0.f, 0, unused, lane);
         __syncwarp();
         for (int idx = lane; idx < ncol; idx += 32) {
             int c = c0 + idx;
-            if (c >= 1) gout[c - 1] = gbuf[pad(idx)];
+            if (c >= 1) gout[c - 1] = gbuf[G::pad(idx)];
         }
         __syncwarp();
     }
@@ -537,7 +581,7 @@ cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, in
 
 cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* echo, cudaStream_t st) {
     int wpb = warps_per_block(n_rays);
-    size_t smem = (size_t)wpb * 2 * OBUF * sizeof(float);
+    size_t smem = (size_t)wpb * 2 * FwdGeo::OBUF * sizeof(float);
     echo_fwd_kernel<<<(unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, smem, st>>>(refl, n_rays, N, echo);
     return cudaGetLastError();
 }
@@ -545,8 +589,8 @@ cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* ech
 cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n_rays, int N, float* grad_refl,
                             cudaStream_t st) {
     int wpb = warps_per_block(n_rays);
-    int nseg = (N + 1 + SEG - 1) / SEG;
-    size_t smem = (size_t)wpb * (3 * OBUF + 4 * nseg) * sizeof(float);
+    int nseg = (N + 1 + BwdGeo::SEG - 1) / BwdGeo::SEG;
+    size_t smem = (size_t)wpb * (3 * BwdGeo::OBUF + 4 * nseg) * sizeof(float);
     cudaError_t e = ensure_smem(echo_bwd_kernel, smem);
     if (e != cudaSuccess) return e;
     echo_bwd_kernel<<<(unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, smem, st>>>(refl, grad_echo, n_rays, N, grad_refl);

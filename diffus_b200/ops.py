@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (LAYOUT_BRICK, LAYOUT_LINEAR, MLP_NPARAMS, POSE_F32, POSE_F64, SAMPLER_NEAREST,
                    SAMPLER_TRILINEAR, DiffusRenderArgs, DiffusRenderBwdArgs)
 
-SEG = 512  # columns per scan segment (csrc/common.cuh)
+SEG = 512  # PREFIX_STRIDE of csrc/common.cuh: the forward saves a 2x2 prefix every SEG columns
 
 _LAUNCHES = 0  # kernels enqueued through this module (bench.py reports it as gpu_launches)
 

@@ -81,8 +81,8 @@ typedef struct DiffusRenderArgs {
     int32_t sampler;            /* DIFFUS_SAMPLER_*                                          */
     float attenuation;          /* alpha: frame[k] = echo[k] * exp(-alpha k), k from 0 after crop */
     float* frame;               /* out (P,R,S-start)                                         */
-    float* seg_prefix;          /* out, optional: (P,R,nseg-1,4) transfer-matrix prefixes at
-                                   512-column segment boundaries, consumed by the backward;
+    float* seg_prefix;          /* out, optional: (P,R,ceil((S-start)/512)-1,4) transfer-matrix
+                                   prefixes at every 512th column, consumed by the backward;
                                    may be NULL (always unused when S-start <= 512)           */
     void* workspace;            /* diffus_render_workspace_bytes() bytes, needed iff start>0 */
     int64_t workspace_bytes;

@@ -216,7 +216,8 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
 
     lf, ff, gvf, gsf, gdf = run(True)
     lu, fu, gvu, gsu, gdu = run(False)
-    assert torch.equal(ff, fu), "fused kernel renders a different frame than the forward kernel"
+    # same arithmetic, different scan tree (the backward walks 8-column chunks): agreement to rounding
+    torch.testing.assert_close(ff, fu, rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(lf.item(), l64.item(), rtol=1e-4)
     np.testing.assert_allclose(lf.item(), lu.item(), rtol=1e-5)
     assert_grad_close(gvf.cpu().numpy(), 3.0 * want[0].numpy(), "fused d/dvolume")

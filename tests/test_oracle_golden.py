@@ -1,0 +1,136 @@
+"""CPU: the oracle (oracle/port.py) against the golden fixtures produced by the unmodified reference."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+
+def _start(g, name):
+    s = float(g[f"{name}_start"])
+    return s if bool(g[f"{name}_start_is_float"]) else int(s)
+
+
+def test_known_answer_echoes(golden_echo):
+    g = golden_echo
+    for name in ("nan_lead", "total_reflection", "air_tissue_air", "doc_example"):
+        Z = torch.tensor(g[f"ka_{name}_Z"])
+        r = port.reflection_coeff(Z[:, :-1], Z[:, 1:])
+        np.testing.assert_array_equal(np.isnan(r.numpy()), np.isnan(g[f"ka_{name}_r"]))
+        np.testing.assert_allclose(np.nan_to_num(r.numpy()), np.nan_to_num(g[f"ka_{name}_r"]), rtol=1e-15)
+        np.testing.assert_array_equal(port.echo_dense_solve(r).numpy(), g[f"ka_{name}_echo"])     # bit-exact: same LAPACK calls
+        np.testing.assert_allclose(port.echo_closed_form(r).numpy(), g[f"ka_{name}_echo"], rtol=0, atol=1e-14)
+    # the values SURVEY.md appendix B quotes from the reference
+    np.testing.assert_allclose(g["ka_doc_example_echo"][0], [0, 1 / 3, 0.21212121], atol=1e-6)
+    np.testing.assert_allclose(g["ka_total_reflection_echo"][0], [0, 0.0323, -0.9355, -0.9355, -0.9355, -0.9355], atol=1e-4)
+    assert (g["ka_nan_lead_echo"] == 0).all()
+
+
+def test_notebook_phantom(golden_echo):
+    g = golden_echo
+    zt = torch.tensor(g["phantom_Z"])
+    r = port.reflection_coeff(zt[:, 1:], zt[:, :-1])          # the notebook's argument order
+    np.testing.assert_array_equal(r.numpy(), g["phantom_r"])
+    np.testing.assert_array_equal(port.echo_dense_solve(r).numpy(), g["phantom_echo"])
+    np.testing.assert_allclose(port.echo_closed_form(r).numpy(), g["phantom_echo"], atol=2e-6)
+    np.testing.assert_array_equal(torch.cumsum(port.surface_return_dense(r), 1).numpy(), g["phantom_cumulative"])
+    np.testing.assert_allclose(port.delays_us(r.shape[1] + 1).numpy(), g["phantom_delays"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["rand_a", "rand_b", "rand_c"])
+def test_random_coefficients(golden_echo, name):
+    g = golden_echo
+    r = torch.tensor(g[f"{name}_r"])
+    np.testing.assert_array_equal(port.echo_dense_solve(r).numpy(), g[f"{name}_echo64"])
+    np.testing.assert_allclose(port.echo_closed_form(r).numpy(), g[f"{name}_echo64"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_array_equal(port.echo_dense_solve(r.float()).numpy(), g[f"{name}_echo32"])
+    # the reference's own float32 run sits ~1e-6 from its float64 run: the floor any fp32 kernel is judged against
+    assert np.abs(g[f"{name}_echo32"] - g[f"{name}_echo64"]).max() < 2e-5 * max(1.0, np.abs(g[f"{name}_echo64"]).max())
+
+
+@pytest.mark.parametrize("name", ["a0", "a7", "afrac", "b0", "b5", "c0", "d0"])
+def test_plot_beam_frame_nearest(golden_frames, name):
+    g = golden_frames
+    vol = torch.tensor(g[f"{name}_volume"])
+    src = torch.tensor(g[f"{name}_source"])
+    dirs = torch.tensor(g[f"{name}_dirs"])
+    S, alpha, start = int(g[f"{name}_S"]), float(g[f"{name}_alpha"]), _start(g, name)
+    x, y, z, f = port.plot_beam_frame(vol.double(), src, dirs.double(), S, alpha, start=start)
+    np.testing.assert_array_equal(x.numpy(), g[f"{name}_x"])
+    np.testing.assert_array_equal(y.numpy(), g[f"{name}_y"])
+    np.testing.assert_array_equal(z.numpy(), g[f"{name}_z"])
+    np.testing.assert_allclose(f.numpy(), g[f"{name}_frame64"], rtol=0, atol=1e-13)
+    # literal algorithm, float32, bit-exact against the reference's float32 run
+    _, _, _, fd = port.plot_beam_frame(vol, src, dirs, S, alpha, start=start, propagation="dense")
+    np.testing.assert_array_equal(fd.numpy(), g[f"{name}_frame32"])
+    xs, ys, zs, imp = port.sample_nearest(vol, port.ray_points(src, dirs, S))
+    np.testing.assert_array_equal(port.reflection_coeff(imp[:, :-1], imp[:, 1:]).numpy(), g[f"{name}_refl"])
+
+
+@pytest.mark.parametrize("name", ["t0", "t1", "t2"])
+def test_trilinear_frames_and_gradients(golden_tri, name):
+    g = golden_tri
+    vol = torch.tensor(g[f"{name}_volume"]).double().requires_grad_(True)
+    src = torch.tensor(g[f"{name}_source"]).double().requires_grad_(True)
+    dirs = torch.tensor(g[f"{name}_dirs"]).double().requires_grad_(True)
+    x, y, z, f = port.plot_beam_frame(vol, src, dirs, int(g[f"{name}_S"]), float(g[f"{name}_alpha"]), sampler="trilinear")
+    np.testing.assert_allclose(f.detach().numpy(), g[f"{name}_frame64"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(x.numpy(), g[f"{name}_x"])
+    gv, gs, gd = torch.autograd.grad((f * torch.tensor(g[f"{name}_w"])).sum(), [vol, src, dirs])
+    for got, key in ((gv, "grad_volume"), (gs, "grad_source"), (gd, "grad_dirs")):
+        want = g[f"{name}_{key}"]
+        assert np.abs(got.numpy() - want).max() <= 1e-9 * max(np.abs(want).max(), 1e-30), key
+
+
+def test_nearest_volume_gradient(golden_tri):
+    g = golden_tri
+    vol = torch.tensor(g["t0_volume"]).double().requires_grad_(True)
+    _, _, _, f = port.plot_beam_frame(vol, torch.tensor(g["t0_source"]), torch.tensor(g["t0_dirs"]).double(), 36, 1e-3)
+    np.testing.assert_allclose(f.detach().numpy(), g["n0_frame64"], atol=1e-13)
+    (gv,) = torch.autograd.grad((f * torch.tensor(g["n0_w"])).sum(), [vol])
+    assert np.abs(gv.numpy() - g["n0_grad_volume"]).max() <= 1e-9 * np.abs(g["n0_grad_volume"]).max()
+
+
+def test_cone_directions(golden_cone):
+    from diffus_b200.cone import generate_cone_directions
+    g = golden_cone
+    for i in range(5):
+        d, ang, n = g[f"cone{i}_d"], float(g[f"cone{i}_angle"]), int(g[f"cone{i}_n"])
+        np.testing.assert_array_equal(port.generate_cone_directions(d, ang, n).numpy(), g[f"cone{i}_dirs"])
+        got = generate_cone_directions(d, ang, n)          # the product's host function
+        assert got.dtype == torch.float32 and got.shape == (n, 3)
+        np.testing.assert_array_equal(got.numpy(), g[f"cone{i}_dirs"])
+
+
+def test_mlp(golden_mlp):
+    g = golden_mlp
+    p = [torch.tensor(g[k]) for k in ("param_model_0_weight", "param_model_0_bias", "param_model_2_weight",
+                                      "param_model_2_bias", "param_model_4_weight", "param_model_4_bias")]
+    y = port.mlp_forward(torch.tensor(g["x"]), *p)
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-5, atol=1e-6)
+    y64 = port.mlp_forward(torch.tensor(g["x"]).double(), *[q.double() for q in p])
+    np.testing.assert_allclose(y64.numpy(), g["y64"], rtol=1e-12)
+
+
+def test_splat(golden_splat):
+    g = golden_splat
+    x, y, z, val = (torch.tensor(g[k]) for k in ("x", "y", "z", "val"))
+    for sigma in (0.5, 1.0):
+        img = port.splat(x, y, z, val, H=64, W=64, sigma=sigma)
+        np.testing.assert_allclose(img.numpy(), g[f"img_sigma{sigma}"], rtol=1e-6, atol=1e-7)
+
+
+def test_closed_form_equals_dense_on_layered_medium():
+    """The identity the CUDA kernels rest on, at a size the dense form still reaches, fp64, incl. gradients."""
+    g = torch.Generator().manual_seed(0)
+    layers = 1.4e6 + 0.3e6 * torch.rand((4, 8), generator=g, dtype=torch.float64)
+    Z = layers.repeat_interleave(12, dim=1) * (1 + 0.005 * torch.randn((4, 96), generator=g, dtype=torch.float64))
+    r = port.reflection_coeff(Z[:, :-1], Z[:, 1:]).requires_grad_(True)
+    a, b = port.echo_dense_solve(r), port.echo_closed_form(r)
+    np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=0, atol=1e-13)
+    w = torch.randn(a.shape, generator=g, dtype=torch.float64)
+    (ga,) = torch.autograd.grad((a * w).sum(), r, retain_graph=True)
+    (gb,) = torch.autograd.grad((b * w).sum(), r)
+    np.testing.assert_allclose(ga.numpy(), gb.numpy(), rtol=0, atol=1e-11)
