@@ -51,18 +51,18 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled every 100 ms while the GPU is under the benchmark load."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.mark = index, [], None, 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -72,10 +72,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def begin_region(self):
+        self.mark = len(self.rows)
+
+    def count(self):
+        return len(self.rows) - self.mark
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -83,7 +88,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.mark:]:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -162,12 +167,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     W, K = max(args.warmup, 3), args.steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                  # nvidia-smi needs a moment to come up: start before the warm-up
     for _ in range(W):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.begin_region()
     launches0 = ops.launch_count()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -190,6 +196,13 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms_total = e0.elapsed_time(e1)
+    if rank == 0:
+        # a short run can end before nvidia-smi delivers a sample: keep the same load on (untimed) until it has
+        t_hold = time.perf_counter()
+        while sampler.proc is not None and sampler.count() < 3 and time.perf_counter() - t_hold < 4.0:
+            for _ in range(20):
+                step_device()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     times = torch.tensor([ms_total, e2e_ms_total, step_ms], dtype=torch.float64, device=dev)
@@ -311,7 +324,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=1024, help="poses per GPU per step")

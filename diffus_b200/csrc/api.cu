@@ -61,6 +61,7 @@ RenderParams pack(const DiffusRenderArgs* a) {
     p.Sout = a->n_samples - a->start;
     p.nprefix = (p.Sout + PREFIX_STRIDE - 1) / PREFIX_STRIDE - 1;
     p.att_slots = (p.Sout + 3) / 4 * 4;
+    p.att_slots_padded = (p.Sout + p.Sout / BwdGeo::CHUNK + 8) / 4 * 4;
     p.alpha = a->attenuation;
     p.frame = a->frame;
     p.seg_prefix = a->seg_prefix;
@@ -93,6 +94,7 @@ struct BwdWorkspace {
     float* dir_scratch;
     float* first_rbar;
     float* loss_partial;
+    void* reduce_ws;
     int64_t bytes;
 };
 BwdWorkspace bwd_workspace(const DiffusRenderBwdArgs* b, void* base) {
@@ -117,6 +119,8 @@ BwdWorkspace bwd_workspace(const DiffusRenderBwdArgs* b, void* base) {
     if (b->target && b->loss) {
         w.loss_partial = (float*)((char*)base + off);
         off += align_up(rays * 4, 256);
+        w.reduce_ws = (char*)base + off;
+        off += align_up(reduce_sum_workspace_bytes(), 256);
     }
     w.bytes = off;
     return w;
@@ -211,7 +215,7 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
         if (ce != cudaSuccess) return (int32_t)ce;
     }
     if (w.loss_partial) {
-        ce = launch_reduce_sum(w.loss_partial, a->n_poses * a->n_rays, b->loss_scale, b->loss, st);
+        ce = launch_reduce_sum(w.loss_partial, a->n_poses * a->n_rays, b->loss_scale, b->loss, w.reduce_ws, st);
         if (ce != cudaSuccess) return (int32_t)ce;
     }
     return DIFFUS_OK;

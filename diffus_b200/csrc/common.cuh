@@ -226,24 +226,48 @@ __device__ __forceinline__ float tri_combine(const float z[8], const TriCell& c,
     return c0 * gx + c1 * fx;
 }
 
+// A sample split into "issue the loads" and "combine", so a gather loop can keep the next
+// tile's eight loads in flight while it combines the current one (software pipelining).
+template <int SAMPLER, int LAYOUT>
+struct Fetch {
+    float z[SAMPLER == DIFFUS_SAMPLER_NEAREST ? 1 : 8];
+    float f[3];
+    bool inside[3];
+
+    __device__ __forceinline__ void issue(const VolumeView& v, float p0, float p1, float p2) {
+        if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+            int i = nearest_index(p0, v.D), j = nearest_index(p1, v.H), k = nearest_index(p2, v.W);
+            z[0] = __ldg(v.data + voxel_offset<LAYOUT>(v, i, j, k));
+        } else {
+            TriCell c;
+            tri_axis(p0, v.D, c.i0[0], c.i1[0], f[0], inside[0]);
+            tri_axis(p1, v.H, c.i0[1], c.i1[1], f[1], inside[1]);
+            tri_axis(p2, v.W, c.i0[2], c.i1[2], f[2], inside[2]);
+            uint32_t off[8];
+            tri_offsets<LAYOUT>(v, c, off);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) z[q] = __ldg(v.data + off[q]);
+        }
+    }
+    template <bool GRAD>
+    __device__ __forceinline__ float finish(float g[3]) const {
+        if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+            if (GRAD) { g[0] = g[1] = g[2] = 0.f; }
+            return z[0];
+        } else {
+            TriCell c;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { c.f[a] = f[a]; c.inside[a] = inside[a]; }
+            return tri_combine<GRAD>(z, c, g);
+        }
+    }
+};
+
 template <int SAMPLER, int LAYOUT, bool GRAD>
 __device__ __forceinline__ float sample_volume(const VolumeView& v, float p0, float p1, float p2, float g[3]) {
-    if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
-        int i = nearest_index(p0, v.D), j = nearest_index(p1, v.H), k = nearest_index(p2, v.W);
-        if (GRAD) { g[0] = g[1] = g[2] = 0.f; }
-        return __ldg(v.data + voxel_offset<LAYOUT>(v, i, j, k));
-    } else {
-        TriCell c;
-        tri_axis(p0, v.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
-        tri_axis(p1, v.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
-        tri_axis(p2, v.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
-        uint32_t off[8];
-        tri_offsets<LAYOUT>(v, c, off);
-        float z[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) z[q] = __ldg(v.data + off[q]);
-        return tri_combine<GRAD>(z, c, g);
-    }
+    Fetch<SAMPLER, LAYOUT> fe;
+    fe.issue(v, p0, p1, p2);
+    return fe.template finish<GRAD>(g);
 }
 
 // kernel parameter block (host fills it from the C-ABI structs)
@@ -257,6 +281,7 @@ struct RenderParams {
     int S, start, Sout;
     int nprefix;                // saved prefixes per ray: ceil(Sout / PREFIX_STRIDE) - 1
     int att_slots;              // floats reserved at the start of dynamic smem for the attenuation table
+    int att_slots_padded;       // same, for the backward's padded table
     float alpha;
     float* frame;
     float* seg_prefix;          // (total_rays, nprefix, 4) or null

@@ -29,7 +29,8 @@ namespace diffus {
 cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st);
 cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad,
                               bool vol_grad, cudaStream_t st);
-cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, cudaStream_t st);
+int64_t reduce_sum_workspace_bytes();
+cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, void* workspace, cudaStream_t st);
 cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* echo, cudaStream_t st);
 cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n_rays, int N, float* grad_refl,
                             cudaStream_t st);

@@ -7,6 +7,8 @@
 //            index_put_(accumulate=True).  With a target frame the backward kernel also
 //            evaluates the forward and the MSE loss itself, so one launch is a whole
 //            pose-recovery step (fused forward + loss + backward, one gather pass).
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -49,22 +51,25 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
 }
 
 // What the upstream gradient of a column is made of.
-//   LOSS_GRAD : gbuf holds d loss / d frame, abuf the attenuation         -> ebar = g * att
-//   LOSS_MSE  : gbuf holds the target frame, abuf the attenuation; the kernel forms
-//               frame = echo * att, diff = frame - target, ebar = grad_scale * diff * att,
-//               accumulates diff^2 and leaves the frame in abuf
+//   LOSS_GRAD : gbuf holds d loss / d frame                               -> ebar = g * att
+//   LOSS_MSE  : gbuf holds the target frame; the kernel forms frame = echo * att,
+//               diff = frame - target, ebar = grad_scale * diff * att, accumulates diff^2
+//               and (optionally) stores the frame
 constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 
 // Backward chunk phase for one segment.
 //   r[i]        coefficient of column c0 + lane*CH + i (0 where the column does not exist)
-//   gbuf/abuf   see above; on return gbuf holds d loss / d r per column
+//   gbuf        see above; on return gbuf holds d loss / d r per column
+//   att_lane    attenuation of this lane's columns (padded table), or null for 1
+//   frame_lane  where this lane's columns of the frame go (global), or null
 //   carry       forward prefix P through the column before the segment
 //   vin         adjoint flowing into the segment's last column from later segments
-//   ncol_lane   number of existing columns in this lane's chunk (for the loss sum)
+//   ncol_lane   number of existing columns in this lane's chunk (may be <= 0 or > CHUNK)
 // returns the adjoint flowing out of the segment's first column (into the previous segment)
 template <class G_, int LOSS>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
-                                             float* abuf, float grad_scale, int ncol_lane, float& loss_acc, int lane) {
+                                             const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
+                                             float& loss_acc, int lane) {
     constexpr int CHUNK = G_::CHUNK;
     const int base = lane * (CHUNK + 1);
     M2 T = m2_identity();
@@ -83,17 +88,19 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         float e = echo_of(P.b, inv);
         bool finite = fabsf(e) <= FLT_MAX;             // nan_to_num passes no gradient at NaN/inf
         float ge;
+        const float att = att_lane ? att_lane[i] : 1.f;
         if (LOSS == LOSS_MSE) {
-            float att = abuf[base + i];
             float fr = __fmul_rn(nan_to_num(e), att);
             float diff = fr - gbuf[base + i];
-            if (i < ncol_lane) loss_acc += diff * diff;
-            abuf[base + i] = fr;
+            if (i < ncol_lane) {
+                loss_acc += diff * diff;
+                if (frame_lane) frame_lane[i] = fr;      // 8 consecutive floats per lane: whole 32-byte sectors
+            }
             ge = grad_scale * diff * att;
         } else {
-            ge = gbuf[base + i] * abuf[base + i];
+            ge = gbuf[base + i] * att;
         }
-        if (!finite) ge = 0.f;
+        if (!finite || i >= ncol_lane) ge = 0.f;           // columns that do not exist: the table beyond Sout is not filled
         gbuf[base + i] = ge;
         float da = ge * inv, db = -ge * e * inv;       // D = [[0, da], [0, db]]
         B.a += da * G.b; B.b += da * G.d; B.c += db * G.b; B.d += db * G.d;
@@ -141,6 +148,12 @@ __device__ __forceinline__ float reflection(float z_prev, float z_cur) {
 // attenuation table exp(-alpha c), c = 0..Sout-1, shared by the rays of a CTA
 __device__ __forceinline__ void fill_attenuation(float* att, int Sout, float alpha) {
     for (int c = threadIdx.x; c < Sout; c += blockDim.x) att[c] = expf(-alpha * (float)c);
+    __syncthreads();
+}
+
+template <class G>
+__device__ __forceinline__ void fill_attenuation_padded(float* att, int Sout, float alpha) {
+    for (int c = threadIdx.x; c < Sout; c += blockDim.x) att[G::pad(c)] = expf(-alpha * (float)c);
     __syncthreads();
 }
 
@@ -232,7 +245,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
 // buffers for PREFIX_STRIDE columns in the backward's padding (rows of CHUNK+1 floats)
 constexpr int BWD_ZBUF = PREFIX_STRIDE + 1 + (PREFIX_STRIDE + 1) / BwdGeo::CHUNK + 3;
 constexpr int BWD_OBUF = PREFIX_STRIDE + PREFIX_STRIDE / BwdGeo::CHUNK + 3;
-constexpr int BWD_SMEM_PER_WARP = BWD_ZBUF + 2 * BWD_OBUF + 3 * PREFIX_STRIDE;
+constexpr int BWD_SMEM_PER_WARP = BWD_ZBUF + BWD_OBUF + 3 * PREFIX_STRIDE;
 
 template <int SAMPLER, bool POSE64>
 __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const RaySetup<POSE64>& rs, int k, float zbar) {
@@ -263,15 +276,14 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     using G = BwdGeo;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
     extern __shared__ float smem[];
-    float* att = smem;
-    fill_attenuation(att, p.Sout, p.alpha);
+    float* att = smem;                       // padded like the column buffers: conflict free in the chunk phase
+    fill_attenuation_padded<G>(att, p.Sout, p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
-    float* zbuf = smem + p.att_slots + warp * BWD_SMEM_PER_WARP;
+    float* zbuf = smem + p.att_slots_padded + warp * BWD_SMEM_PER_WARP;
     float* gbuf = zbuf + BWD_ZBUF;           // target / upstream gradient in, d loss / d r out
-    float* abuf = gbuf + BWD_OBUF;           // attenuation in, frame out (LOSS_MSE)
-    float* dz = abuf + BWD_OBUF;             // [3][SS] spatial gradient of Z at each sample
+    float* dz = gbuf + BWD_OBUF;             // [3][SS] spatial gradient of Z at each sample
     const int64_t pose = ray / p.n_rays;
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
@@ -291,22 +303,31 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
         const int ncol = min(SS, p.Sout - c0);
         const int ntile = (ncol + 31) >> 5;
         const int nsub = (ncol + G::SEG - 1) / G::SEG;
-        // gather phase: one pass over the volume for these columns
-#pragma unroll 2
-        for (int t = 0; t < nsub * (G::SEG / 32); ++t) {
-            int idx = t * 32 + lane;
-            float gval = 0.f, aval = 0.f;
-            if (idx < ncol) {
-                int c = c0 + idx, k = p.start + c;
-                float g[3];
-                float z = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
-                zbuf[G::pad(idx + 1)] = z;
-                if (POSE_GRAD) { dz[idx] = g[0]; dz[SS + idx] = g[1]; dz[2 * SS + idx] = g[2]; }
-                gval = __ldg(gin + c);
-                aval = att[c];
+        // The target (or upstream-gradient) row streams from HBM: copy it straight into shared
+        // memory with cp.async at the top of the pass so its latency hides behind the gathers.
+        {
+            const int nt = nsub * (G::SEG / 32);
+            for (int t = 0; t < nt; ++t) {
+                int idx = t * 32 + lane;
+                if (idx < ncol) __pipeline_memcpy_async(gbuf + G::pad(idx), gin + c0 + idx, 4);
+                else gbuf[G::pad(idx)] = 0.f;            // columns that do not exist carry no gradient
             }
-            gbuf[G::pad(idx)] = gval;        // columns that do not exist carry no gradient
-            abuf[G::pad(idx)] = aval;
+            __pipeline_commit();
+            // gather phase: one pass over the volume for these columns.  (A cp.async ring for the
+            // gathers themselves was measured slower than plain loads: LDGSTS issues at a quarter of
+            // the LDG rate and adds eight shared-memory reads per sample, profiles/r1_notes.md.)
+#pragma unroll 2
+            for (int t = 0; t < nt; ++t) {
+                int idx = t * 32 + lane;
+                if (idx < ncol) {
+                    int k = p.start + c0 + idx;
+                    float g[3];
+                    float z = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
+                    zbuf[G::pad(idx + 1)] = z;
+                    if (POSE_GRAD) { dz[idx] = g[0]; dz[SS + idx] = g[1]; dz[2 * SS + idx] = g[2]; }
+                }
+            }
+            __pipeline_wait_prior(0);
         }
         if (s > 0 && lane == 0) {            // left neighbour of the pass's first column
             int k = p.start + c0 - 1;
@@ -342,8 +363,10 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             if (h < nsub) {
                 const int off = h * G::SEG;
                 chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, off);
-                vin = backward_chunk<G, LOSS>(r, carry[h], vin, gbuf + G::pad(off), abuf + G::pad(off), p.grad_scale,
-                                              ncol - off - lane * G::CHUNK, loss_acc, lane);
+                const int lane_col = off + lane * G::CHUNK;
+                vin = backward_chunk<G, LOSS>(r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col),
+                                              fout ? fout + c0 + lane_col : nullptr, p.grad_scale, ncol - lane_col,
+                                              loss_acc, lane);
             }
         }
         __syncwarp();
@@ -354,7 +377,6 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             int idx = t * 32 + lane;
             if (idx < ncol) {
                 int c = c0 + idx;
-                if (fout) fout[c] = abuf[G::pad(idx)];
                 float zc = zbuf[G::pad(idx + 1)];
                 float zbar = 0.f;
                 // as the right-hand impedance of its own column's interface
@@ -450,10 +472,9 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= n_rays) return;
     const int Sout = N + 1, nseg = (Sout + G::SEG - 1) / G::SEG;
-    float* rbuf = smem + warp * (3 * G::OBUF + 4 * nseg);
+    float* rbuf = smem + warp * (2 * G::OBUF + 4 * nseg);
     float* gbuf = rbuf + G::OBUF;
-    float* abuf = gbuf + G::OBUF;
-    float* prefix = abuf + G::OBUF;          // carry entering segment s, 4 floats each
+    float* prefix = gbuf + G::OBUF;          // carry entering segment s, 4 floats each
     const float* rin = refl + ray * (int64_t)N;
     const float* gin = grad_echo + ray * (int64_t)Sout;
     float* gout = grad_refl + ray * (int64_t)N;
@@ -484,14 +505,13 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
             bool ok = idx < ncol;
             rbuf[G::pad(idx)] = (c >= 1 && ok) ? __ldg(rin + c - 1) : 0.f;
             gbuf[G::pad(idx)] = ok ? __ldg(gin + c) : 0.f;
-            abuf[G::pad(idx)] = 1.f;
         }
         __syncwarp();
         float r[G::CHUNK];
 #pragma unroll
         for (int i = 0; i < G::CHUNK; ++i) r[i] = rbuf[G::pad(lane * G::CHUNK + i)];
         M2 cs = M2{prefix[4 * s], prefix[4 * s + 1], prefix[4 * s + 2], prefix[4 * s + 3]};
-        vin = backward_chunk<G, LOSS_GRAD>(r, cs, vin, gbuf, abuf, 0.f, 0, unused, lane);
+        vin = backward_chunk<G, LOSS_GRAD>(r, cs, vin, gbuf, nullptr, nullptr, 0.f, ncol - lane * G::CHUNK, unused, lane);
         __syncwarp();
         for (int idx = lane; idx < ncol; idx += 32) {
             int c = c0 + idx;
@@ -501,11 +521,16 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     }
 }
 
-// sum of per-ray partials -> one float (fixed order, single block)
-__global__ void reduce_sum_kernel(const float* __restrict__ partial, int64_t n, float scale, float* __restrict__ out) {
+// sum of per-ray partials -> one float, fixed order: blocks write double partials, the last block to
+// finish (atomic ticket) adds them up in index order
+__global__ void reduce_sum_kernel(const float* __restrict__ partial, int64_t n, float scale, float* __restrict__ out,
+                                  double* __restrict__ block_sums, unsigned* __restrict__ ticket) {
     __shared__ double warp_part[32];
+    __shared__ bool last;
     double acc = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)partial[i];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
@@ -513,12 +538,30 @@ __global__ void reduce_sum_kernel(const float* __restrict__ partial, int64_t n, 
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_part[w];
+        block_sums[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += ((volatile double*)block_sums)[b];
         out[0] = (float)(t * (double)scale);
+        *ticket = 0u;                        // ready for the next launch on this workspace
     }
 }
 
-cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, cudaStream_t st) {
-    reduce_sum_kernel<<<1, 1024, 0, st>>>(partial, n, scale, out);
+constexpr int REDUCE_BLOCKS = 64;
+int64_t reduce_sum_workspace_bytes() { return REDUCE_BLOCKS * sizeof(double) + 256; }
+
+cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, void* workspace, cudaStream_t st) {
+    double* sums = (double*)workspace;
+    unsigned* ticket = (unsigned*)((char*)workspace + REDUCE_BLOCKS * sizeof(double));
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    int blocks = (int)max((int64_t)1, min((int64_t)REDUCE_BLOCKS, n / 1024));
+    reduce_sum_kernel<<<blocks, 256, 0, st>>>(partial, n, scale, out, sums, ticket);
     return cudaGetLastError();
 }
 
@@ -571,7 +614,7 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
 cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, bool vol_grad,
                               cudaStream_t st) {
     int wpb = warps_per_block(p.total_rays);
-    size_t smem = ((size_t)p.att_slots + (size_t)wpb * BWD_SMEM_PER_WARP) * sizeof(float);
+    size_t smem = ((size_t)p.att_slots_padded + (size_t)wpb * BWD_SMEM_PER_WARP) * sizeof(float);
     unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
     const bool mse = p.target != nullptr;
     DIFFUS_DISPATCH(if (mse) return launch_bwd_g<S_, L_, P64_, LOSS_MSE>(p, pose_grad, vol_grad, grid, wpb * 32, smem, st);
@@ -590,7 +633,7 @@ cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n
                             cudaStream_t st) {
     int wpb = warps_per_block(n_rays);
     int nseg = (N + 1 + BwdGeo::SEG - 1) / BwdGeo::SEG;
-    size_t smem = (size_t)wpb * (3 * BwdGeo::OBUF + 4 * nseg) * sizeof(float);
+    size_t smem = (size_t)wpb * (2 * BwdGeo::OBUF + 4 * nseg) * sizeof(float);
     cudaError_t e = ensure_smem(echo_bwd_kernel, smem);
     if (e != cudaSuccess) return e;
     echo_bwd_kernel<<<(unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, smem, st>>>(refl, grad_echo, n_rays, N, grad_refl);
