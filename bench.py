@@ -265,7 +265,7 @@ def cpu_sample_step(vol, src, dirs, target):
     _, _, _, f = port.plot_beam_frame(vol, s, d, N_SAMPLES, ALPHA, sampler="trilinear", propagation="dense")
     loss = torch.nn.functional.mse_loss(f, target)
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
 
 
 def cpu_scene(n_rays):
@@ -298,6 +298,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if os.environ.get("OMP_NUM_THREADS") and not os.environ.get("DIFFUS_REF_CHILD"):
+        # torchrun pins OMP_NUM_THREADS=1; the reference arm is entitled to every host thread, and
+        # torch.set_num_threads() after start-up makes the batched LAPACK solves crawl, so re-exec clean
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+        env["DIFFUS_REF_CHILD"] = "1"
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), *sys.argv[1:]], env=env, capture_output=True, text=True)
+        sys.stdout.write(out.stdout)
+        sys.stderr.write(out.stderr[-2000:])
+        sys.stdout.flush()
+        return
     K, W = args.steps, args.warmup
     vol, s, d, target = cpu_scene(args.cpu_rays)
     for _ in range(min(W, 1)):
@@ -329,7 +339,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=1024, help="poses per GPU per step")
     ap.add_argument("--layout", default="brick", choices=["linear", "brick"])
-    ap.add_argument("--cpu-rays", type=int, default=4, help="rays in the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=8, help="rays in the bounded CPU sample (~2 GB and ~0.5 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

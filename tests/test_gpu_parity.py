@@ -309,6 +309,47 @@ def test_mlp_volume_masked_and_large():
         assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), name)
 
 
+def test_mlp_render_training_step_vs_oracle():
+    """Config 4 in miniature: MLP -> volume -> frames -> MSE; weight and pose gradients vs fp64 autograd of the oracle."""
+    from diffus_b200 import ImpedanceEstimator
+    from diffus_b200.phantoms import mri_phantom, pose_sweep
+    from diffus_b200.training import mlp_render_mse_loss, train_step
+    from oracle import port
+    n, S, alpha = 24, 40, 1e-3
+    torch.manual_seed(5)
+    model = ImpedanceEstimator(1)
+    with torch.no_grad():                                  # keep the impedances positive and tissue-like
+        model.model[4].bias.fill_(1.5)
+        model.model[4].weight.mul_(0.3)
+    mri = mri_phantom(n, "t2", seed=2) / 1000.0
+    sources, dirs = pose_sweep(3, n_rays=5, n=n, seed=9)
+    g = torch.Generator().manual_seed(3)
+    targets = 0.01 * torch.randn((3, 5, S), generator=g)
+    ref = ImpedanceEstimator(1).double()
+    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    Z64 = ref.model(mri.double().reshape(-1, 1)).reshape(mri.shape) * 1e6
+    s64 = sources.double().requires_grad_(True)
+    f64 = _oracle_frames(Z64, s64, dirs.double(), S, alpha, 0, "trilinear")
+    l64 = (f64 - targets.double()).square().mean()
+    l64.backward()
+    m = model.to(dev())
+    s = sources.to(dev()).requires_grad_(True)
+    for bricks in (True, False):
+        m.zero_grad()
+        s.grad = None
+        loss = mlp_render_mse_loss(m, mri.to(dev()), s, dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6, bricks=bricks)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), l64.item(), rtol=2e-4)
+        for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"d/d{name} (bricks={bricks})", rtol=3e-4)
+        assert_grad_close(s.grad.cpu().numpy(), s64.grad.numpy(), "d/dsources", rtol=3e-4)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    l0 = train_step(m, opt, mri.to(dev()), sources.to(dev()), dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
+    for _ in range(10):
+        l1 = train_step(m, opt, mri.to(dev()), sources.to(dev()), dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
+    assert l1 < l0
+
+
 def test_full_size_properties_config1():
     """BASELINE config 1 at full size (256^3, 128 x 512): properties that need no oracle run."""
     from diffus_b200 import UltrasoundRenderer, PreparedVolume, render_frames
