@@ -126,8 +126,13 @@ __device__ __forceinline__ uint32_t voxel_offset(const VolumeView& v, int i, int
 
 // a / b without the IEEE slow path (<= 2 ulp): the reference's own float32 run is ~1e-5 of
 // peak away from its float64 run, so correctly-rounded division buys nothing here
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ float fast_rcp(float b) { return __fdividef(1.f, b); }
+// One MUFU.RCP, no range fix-ups (__fdividef adds a scaling branch for |b| > 2^126, never met here).
+__device__ __forceinline__ float fast_rcp(float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return r;
+}
+__device__ __forceinline__ float fast_div(float a, float b) { return a * fast_rcp(b); }
 // echo of a prefix: P[0][1] / P[1][1] (same rounding in the forward and in the fused backward)
 __device__ __forceinline__ float echo_of(float pb, float inv_pd) { return __fmul_rn(pb, inv_pd); }
 

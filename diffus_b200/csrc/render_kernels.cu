@@ -62,6 +62,11 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 //   gbuf        see above; on return gbuf holds d loss / d r per column
 //   att_lane    attenuation of this lane's columns (padded table), or null for 1
 //   frame_lane  where this lane's columns of the frame go (global), or null
+//   z_lane      impedances around this lane's columns (slot j = sample before column j), or null.
+//               When given, gbuf receives w_c = 2 rbar_c / (Z_{c-1} + Z_c)^2 instead of rbar_c, so
+//               that d loss / d Z_c = w_c Z_{c-1} - w_{c+1} Z_{c+1} in the tile phase; `skip_mask`
+//               bit i set = column i has no direct Z dependence (column 0, or the median-replaced one)
+//   rbar1       if not null, lane 0 stores rbar of its column 1 there (the median's gradient)
 //   carry       forward prefix P through the column before the segment
 //   vin         adjoint flowing into the segment's last column from later segments
 //   ncol_lane   number of existing columns in this lane's chunk (may be <= 0 or > CHUNK)
@@ -69,7 +74,8 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 template <class G_, int LOSS>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
-                                             float& loss_acc, int lane) {
+                                             float& loss_acc, int lane, const float* z_lane = nullptr,
+                                             unsigned skip_mask = 0u, float* rbar1 = nullptr) {
     constexpr int CHUNK = G_::CHUNK;
     const int base = lane * (CHUNK + 1);
     M2 T = m2_identity();
@@ -119,6 +125,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     M2 An = m2_shfl_down(As, 1), Bn = m2_shfl_down(Bs, 1);
     M2 V = (lane == 31) ? vin : m2_add(m2_mul(vin, An), Bn);
     M2 vout = m2_add(m2_mul(vin, As), Bs);             // valid on lane 0
+    float z_hi = z_lane ? z_lane[G_::pad(CHUNK)] : 0.f;   // sample of the chunk's last column
 #pragma unroll
     for (int i = CHUNK - 1; i >= 0; --i) {
         M2 Q = Pck[i >> 1];                            // prefix before column i
@@ -134,7 +141,18 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         float mb = Q.a * Pbar.b + Q.c * Pbar.d;
         float mc = Q.b * Pbar.a + Q.d * Pbar.c;
         float rbar = -4.f * r[i] * ma + mb - mc;
-        gbuf[base + i] = (rbar == rbar) ? rbar : 0.f;
+        rbar = (rbar == rbar) ? rbar : 0.f;
+        if (z_lane) {
+            if (rbar1 && i == 1 && lane == 0) *rbar1 = rbar;
+            float z_lo = z_lane[i];
+            float sum = z_lo + z_hi;
+            float w = 2.f * rbar * fast_rcp(sum * sum);
+            if (i >= ncol_lane || ((skip_mask >> i) & 1u)) w = 0.f;
+            gbuf[base + i] = w;
+            z_hi = z_lo;
+        } else {
+            gbuf[base + i] = rbar;
+        }
         V = m2_mul_interface_t(Pbar, r[i]);
     }
     return m2_shfl(vout, 0);
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     const int nss = (p.Sout + SS - 1) / SS;
 
     M2 vin = M2{0.f, 0.f, 0.f, 0.f};
-    float carry_rbar = 0.f, carry_z = 0.f;   // first column of the later pass: its d loss/d r and its impedance
+    float carry_w = 0.f, carry_z = 0.f;      // first column of the later pass: its weight w and its impedance
     float acc_s[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
     float loss_acc = 0.f;
 
@@ -364,37 +382,32 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                 const int off = h * G::SEG;
                 chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, off);
                 const int lane_col = off + lane * G::CHUNK;
+                // columns without a direct impedance dependence: column 0 and the median-replaced column 1
+                unsigned skip = 0u;
+                if (c0 + lane_col == 0) skip = p.median ? 3u : 1u;
                 vin = backward_chunk<G, LOSS>(r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col),
                                               fout ? fout + c0 + lane_col : nullptr, p.grad_scale, ncol - lane_col,
-                                              loss_acc, lane);
+                                              loss_acc, lane, zbuf + G::pad(lane_col), skip,
+                                              (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr);
             }
         }
         __syncwarp();
 
-        // tile phase: d loss / d Z per sample, then pose partials and the volume scatter
-        float next_carry_rbar = gbuf[G::pad(0)], next_carry_z = zbuf[G::pad(1)];
+        // tile phase: d loss / d Z_c = w_c Z_{c-1} - w_{c+1} Z_{c+1}, then pose partials and the volume scatter.
+        // The column after the last one lives in the later pass: park its weight and impedance in the spare slots.
+        const float next_carry_w = gbuf[G::pad(0)], next_carry_z = zbuf[G::pad(1)];
+        __syncwarp();
+        if (lane == 0) {
+            gbuf[G::pad(ncol)] = (c0 + ncol < p.Sout) ? carry_w : 0.f;
+            zbuf[G::pad(ncol + 1)] = carry_z;
+        }
+        __syncwarp();
         for (int t = 0; t < ntile; ++t) {
             int idx = t * 32 + lane;
             if (idx < ncol) {
-                int c = c0 + idx;
-                float zc = zbuf[G::pad(idx + 1)];
-                float zbar = 0.f;
-                // as the right-hand impedance of its own column's interface
-                if (c >= 1 && !(c == 1 && p.median)) {
-                    float zp = zbuf[G::pad(idx)];
-                    float sum = zp + zc;
-                    zbar += gbuf[G::pad(idx)] * fast_div(2.f * zp, sum * sum);
-                }
-                // as the left-hand impedance of the next column's interface
-                if (c + 1 < p.Sout && !(c == 0 && p.median)) {
-                    float zn, rb;
-                    if (idx + 1 < ncol) { zn = zbuf[G::pad(idx + 2)]; rb = gbuf[G::pad(idx + 1)]; }
-                    else { zn = carry_z; rb = carry_rbar; }
-                    float sum = zc + zn;
-                    zbar -= rb * fast_div(2.f * zn, sum * sum);
-                }
+                float zbar = gbuf[G::pad(idx)] * zbuf[G::pad(idx)] - gbuf[G::pad(idx + 1)] * zbuf[G::pad(idx + 2)];
                 if (!(zbar == zbar)) zbar = 0.f;
-                int k = p.start + c;
+                int k = p.start + c0 + idx;
                 if (POSE_GRAD) {
                     float kf = (float)k;
 #pragma unroll
@@ -407,9 +420,8 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                 if (VOL_GRAD && zbar != 0.f) scatter_volume_grad<SAMPLER, POSE64>(p, rs, k, zbar);
             }
         }
-        if (p.first_rbar && s == 0 && lane == 0) p.first_rbar[ray] = gbuf[G::pad(1)];
-        carry_rbar = __shfl_sync(FULL, next_carry_rbar, 0);
-        carry_z = __shfl_sync(FULL, next_carry_z, 0);
+        carry_w = next_carry_w;
+        carry_z = next_carry_z;
         __syncwarp();
     }
     if (POSE_GRAD) {

@@ -93,8 +93,7 @@ def _check_inputs(volume, bricks, dims, sources, directions):
 # ---------------------------------------------------------------------------------------
 # render
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("diffus::render_fwd", mutates_args=())
-def render_fwd(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
+def render_fwd_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
                directions: torch.Tensor, n_samples: int, start: int, alpha: float, sampler: int,
                product_f32: bool, save_prefix: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     dev = _require_cuda(volume, bricks, sources, directions)
@@ -119,6 +118,13 @@ def render_fwd(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[
     return frame, prefix
 
 
+@torch.library.custom_op("diffus::render_fwd", mutates_args=())
+def render_fwd(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
+               directions: torch.Tensor, n_samples: int, start: int, alpha: float, sampler: int,
+               product_f32: bool, save_prefix: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    return render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler, product_f32, save_prefix)
+
+
 @render_fwd.register_fake
 def _(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler, product_f32, save_prefix):
     P, R = sources.shape[0], directions.shape[-2]
@@ -129,8 +135,7 @@ def _(volume, bricks, dims, sources, directions, n_samples, start, alpha, sample
     return frame, prefix
 
 
-@torch.library.custom_op("diffus::render_bwd", mutates_args=())
-def render_bwd(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int],
+def render_bwd_impl(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int],
                sources: torch.Tensor, directions: torch.Tensor, prefix: torch.Tensor, n_samples: int, start: int,
                alpha: float, sampler: int, product_f32: bool, need_volume: bool,
                need_pose: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -158,6 +163,14 @@ def render_bwd(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Optional[
         _lib.check(lib.diffus_render_backward(C.byref(b), _stream(dev)), "diffus_render_backward")
         _count((1 if (need_volume or need_pose) else 0) + (2 if start > 0 else 0) + (1 if need_pose else 0))
     return gvol, gsrc, gdir
+
+
+@torch.library.custom_op("diffus::render_bwd", mutates_args=())
+def render_bwd(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int],
+               sources: torch.Tensor, directions: torch.Tensor, prefix: torch.Tensor, n_samples: int, start: int,
+               alpha: float, sampler: int, product_f32: bool, need_volume: bool,
+               need_pose: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    return render_bwd_impl(grad_frame, volume, bricks, dims, sources, directions, prefix, n_samples, start, alpha, sampler, product_f32, need_volume, need_pose)
 
 
 @render_bwd.register_fake
@@ -204,11 +217,42 @@ def _render_backward(ctx, grad_frame, grad_prefix):
 torch.library.register_autograd("diffus::render_fwd", _render_backward, setup_context=_render_setup)
 
 
+class RenderFunction(torch.autograd.Function):
+    """Eager-mode autograd wrapper of render_fwd/render_bwd that skips the dispatcher (the registered
+    ``diffus::render_fwd`` op carries the same autograd for torch.compile / fake-tensor users)."""
+
+    @staticmethod
+    def forward(ctx, volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler, product_f32):
+        frame, prefix = render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
+                                        product_f32, True)
+        ctx.save_for_backward(volume, sources, directions, prefix)
+        ctx.bricks = bricks
+        ctx.meta = (list(dims), n_samples, start, alpha, sampler, product_f32)
+        return frame
+
+    @staticmethod
+    def backward(ctx, grad_frame):
+        volume, sources, directions, prefix = ctx.saved_tensors
+        dims, n_samples, start, alpha, sampler, product_f32 = ctx.meta
+        need_volume = ctx.needs_input_grad[0]
+        need_pose = (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) and sampler == SAMPLER_TRILINEAR
+        gvol = gsrc = gdir = None
+        if need_volume or need_pose:
+            gv, gs, gd = render_bwd_impl(grad_frame, volume, ctx.bricks, dims, sources, directions, prefix, n_samples,
+                                         start, alpha, sampler, product_f32, need_volume, need_pose)
+            if need_volume:
+                gvol = gv
+            if need_pose and ctx.needs_input_grad[3]:
+                gsrc = gs.to(sources.dtype)
+            if need_pose and ctx.needs_input_grad[4]:
+                gdir = (gd if directions.dim() == 3 else gd.sum(0)).to(directions.dtype)
+        return gvol, None, None, gsrc, gdir, None, None, None, None, None
+
+
 # ---------------------------------------------------------------------------------------
 # fused forward + MSE loss + backward: one gather pass per pose-recovery / training step
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("diffus::render_mse", mutates_args=())
-def render_mse(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
+def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
                directions: torch.Tensor, target: torch.Tensor, n_samples: int, start: int, alpha: float,
                sampler: int, product_f32: bool, need_volume: bool, need_pose: bool,
                want_frame: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -233,8 +277,8 @@ def render_mse(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[
         launches = 0
         prefix = None
         if _nseg(sout) > 1:
-            _, prefix = render_fwd(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
-                                   product_f32, True)
+            _, prefix = render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
+                                        product_f32, True)
         n = P * R * sout
         def empty():                      # outputs of a custom op must not alias each other
             return torch.empty((0,), dtype=torch.float32, device=dev)
@@ -254,6 +298,14 @@ def render_mse(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[
         _lib.check(lib.diffus_render_backward(C.byref(b), _stream(dev)), "diffus_render_backward (fused MSE)")
         _count(2 + (2 if start > 0 else 0) + (1 if need_pose else 0))
     return loss, frame, gvol, gsrc, gdir
+
+
+@torch.library.custom_op("diffus::render_mse", mutates_args=())
+def render_mse(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
+               directions: torch.Tensor, target: torch.Tensor, n_samples: int, start: int, alpha: float,
+               sampler: int, product_f32: bool, need_volume: bool, need_pose: bool,
+               want_frame: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    return render_mse_impl(volume, bricks, dims, sources, directions, target, n_samples, start, alpha, sampler, product_f32, need_volume, need_pose, want_frame)
 
 
 @render_mse.register_fake
@@ -278,9 +330,9 @@ class RenderMSELoss(torch.autograd.Function):
                 product_f32, want_frame):
         need_volume = ctx.needs_input_grad[0]
         need_pose = (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) and sampler == SAMPLER_TRILINEAR
-        loss, frame, gvol, gsrc, gdir = render_mse(volume.detach(), bricks, dims, sources.detach(),
-                                                   directions.detach(), target, n_samples, start, alpha, sampler,
-                                                   product_f32, need_volume, need_pose, want_frame)
+        loss, frame, gvol, gsrc, gdir = render_mse_impl(volume.detach(), bricks, dims, sources.detach(),
+                                                        directions.detach(), target, n_samples, start, alpha, sampler,
+                                                        product_f32, need_volume, need_pose, want_frame)
         ctx.save_for_backward(gvol, gsrc, gdir)
         ctx.flags = (need_volume, need_pose, sources.dtype, directions.dtype, directions.dim())
         ctx.mark_non_differentiable(frame)
@@ -336,8 +388,7 @@ def trace_values(volume, bricks, dims, sources, directions, n_samples, sampler, 
 # ---------------------------------------------------------------------------------------
 # echo traces on explicit reflection coefficients
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("diffus::echo_fwd", mutates_args=())
-def echo_fwd(refl: torch.Tensor) -> torch.Tensor:
+def echo_fwd_impl(refl: torch.Tensor) -> torch.Tensor:
     dev = _require_cuda(refl)
     lib = _lib.load()
     r = refl.contiguous().float()
@@ -349,13 +400,17 @@ def echo_fwd(refl: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@torch.library.custom_op("diffus::echo_fwd", mutates_args=())
+def echo_fwd(refl: torch.Tensor) -> torch.Tensor:
+    return echo_fwd_impl(refl)
+
+
 @echo_fwd.register_fake
 def _(refl):
     return refl.new_empty((refl.shape[0], refl.shape[1] + 1), dtype=torch.float32)
 
 
-@torch.library.custom_op("diffus::echo_bwd", mutates_args=())
-def echo_bwd(refl: torch.Tensor, grad_echo: torch.Tensor) -> torch.Tensor:
+def echo_bwd_impl(refl: torch.Tensor, grad_echo: torch.Tensor) -> torch.Tensor:
     dev = _require_cuda(refl, grad_echo)
     lib = _lib.load()
     r = refl.contiguous().float()
@@ -367,6 +422,11 @@ def echo_bwd(refl: torch.Tensor, grad_echo: torch.Tensor) -> torch.Tensor:
                    "diffus_echo_backward")
         _count(1)
     return out
+
+
+@torch.library.custom_op("diffus::echo_bwd", mutates_args=())
+def echo_bwd(refl: torch.Tensor, grad_echo: torch.Tensor) -> torch.Tensor:
+    return echo_bwd_impl(refl, grad_echo)
 
 
 @echo_bwd.register_fake
@@ -432,8 +492,7 @@ def from_bricks(bricks: torch.Tensor, dims) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------
 # MLP
 # ---------------------------------------------------------------------------------------
-@torch.library.custom_op("diffus::mlp_fwd", mutates_args=())
-def mlp_fwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], out_scale: float,
+def mlp_fwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], out_scale: float,
             fill: float) -> torch.Tensor:
     dev = _require_cuda(params, x, mask)
     lib = _lib.load()
@@ -451,13 +510,18 @@ def mlp_fwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor],
     return out
 
 
+@torch.library.custom_op("diffus::mlp_fwd", mutates_args=())
+def mlp_fwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], out_scale: float,
+            fill: float) -> torch.Tensor:
+    return mlp_fwd_impl(params, x, mask, out_scale, fill)
+
+
 @mlp_fwd.register_fake
 def _(params, x, mask, out_scale, fill):
     return x.new_empty(x.shape, dtype=torch.float32)
 
 
-@torch.library.custom_op("diffus::mlp_bwd", mutates_args=())
-def mlp_bwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
+def mlp_bwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
             out_scale: float) -> torch.Tensor:
     dev = _require_cuda(params, x, mask, grad_out)
     lib = _lib.load()
@@ -476,6 +540,12 @@ def mlp_bwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor],
                        "diffus_mlp_backward")
             _count(2)
     return gp
+
+
+@torch.library.custom_op("diffus::mlp_bwd", mutates_args=())
+def mlp_bwd(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
+            out_scale: float) -> torch.Tensor:
+    return mlp_bwd_impl(params, x, mask, grad_out, out_scale)
 
 
 @mlp_bwd.register_fake

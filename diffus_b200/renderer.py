@@ -92,9 +92,12 @@ def render_frames(volume, sources: torch.Tensor, directions: torch.Tensor, num_s
     vol32 = volume if volume.dtype == torch.float32 else volume.float()
     start_i = _resolve_start(start, num_samples)
     need_grad = torch.is_grad_enabled() and (vol32.requires_grad or src.requires_grad or dirs.requires_grad)
-    frame, _ = ops.render_fwd(vol32.contiguous(), bricks, list(volume.shape), src.contiguous(), dirs.contiguous(),
-                              int(num_samples), int(start_i), float(attenuation_coeff), sid, product_f32,
-                              bool(need_grad))
+    if need_grad:
+        return ops.RenderFunction.apply(vol32.contiguous(), bricks, list(volume.shape), src.contiguous(),
+                                        dirs.contiguous(), int(num_samples), int(start_i), float(attenuation_coeff),
+                                        sid, product_f32)
+    frame, _ = ops.render_fwd_impl(vol32.contiguous(), bricks, list(volume.shape), src.contiguous(), dirs.contiguous(),
+                                   int(num_samples), int(start_i), float(attenuation_coeff), sid, product_f32, False)
     return frame
 
 
