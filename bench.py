@@ -101,6 +101,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(P, layout):
+    """DRAM bytes per launch of the fused kernel from the committed ncu capture, if it is the same workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            t = json.load(f)["render_bwd_kernel_fused_mse"]
+        if (t["poses"], t["rays"], t["samples"], t["layout"]) == (P, N_RAYS, N_SAMPLES, layout):
+            return t["bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def build_scene(device, n_poses, seed):
     from diffus_b200.phantoms import intensity_to_impedance, mri_phantom, pose_sweep
     vol = intensity_to_impedance(mri_phantom(VOL_N, "t1", seed=0))
@@ -241,7 +253,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "kernels_ms": {"fused_step(render_bwd_kernel+reduce_rays+reduce_sum)": step_ms},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(P, args.layout), "peak_source": peak_src,
                          "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
                          "bytes_note": "SURVEY 8(d) counts 72 B/sample for forward+backward done as two passes "
                                        "(2 x (8 gathers x 4 B + 4 B)); the fused kernel gathers once and reads the "

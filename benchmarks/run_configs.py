@@ -74,6 +74,16 @@ def main():
                 return s.grad, d.grad
             ms = timed(step, args.iters)
             report("2: single frame fwd+bwd (pose-recovery step), fused kernel through autograd", ms, 65536, 1, 36)
+            from diffus_b200 import ops
+            s1, d1 = src.reshape(1, 3).contiguous(), dirs.contiguous()
+            ms = timed(lambda: ops.render_mse_impl(vol, None, [256, 256, 256], s1, d1, tgt, 512, 0, 1e-4, 1, False, False,
+                                                   True, False), args.iters)
+            report("2: same, raw op call (no autograd bookkeeping)", ms, 65536, 1, 36)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = ops.render_mse_impl(vol, None, [256, 256, 256], s1, d1, tgt, 512, 0, 1e-4, 1, False, False, True, False)
+            ms = timed(g.replay, args.iters)
+            report("2: same, captured in a CUDA graph (device time of one pose-recovery step)", ms, 65536, 1, 36)
     if "3f" in want:
         vol = PreparedVolume(intensity_to_impedance(mri_phantom(256, "t1")).to(dev))
         s, d = pose_sweep(1024, 128, 256, seed=1)
@@ -96,9 +106,12 @@ def main():
             tgt = render_frames(PreparedVolume(model.impedance_volume(mri, None, 1e6, 400.0) * 1.01), s, d, 512, 1e-4,
                                 sampler="trilinear")
 
-        def step():
+        def step(sampler="trilinear"):
             model.zero_grad(set_to_none=True)
-            mlp_render_mse_loss(model, mri, s, d, tgt, 512, 1e-4, out_scale=1e6).backward()
+            mlp_render_mse_loss(model, mri, s, d, tgt, 512, 1e-4, out_scale=1e6, sampler=sampler).backward()
+        ms_near = timed(lambda: step("nearest"), max(3, args.iters // 4))
+        report("4: MLP(256^3) -> 4096 frames -> MSE -> d/dweights, NEAREST sampler (the reference's own training form)",
+               ms_near, P * 65536, P, 12)
         ms = timed(step, max(3, args.iters // 4))
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(); Z = model.impedance_volume(mri, None, 1e6, 400.0); e[1].record()
