@@ -78,6 +78,9 @@ SIGNATURES = {
     "diffus_mlp_forward": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp]),
     "diffus_mlp_bwd_workspace_bytes": (_i64, [_i64]),
     "diffus_mlp_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _i64, _vp]),
+    "diffus_splat_workspace_bytes": (_i64, [_i32, _i32]),
+    "diffus_splat_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _i64, _vp]),
+    "diffus_splat_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "diffus_brick_elems": (_i64, [_P(_i32 * 3)]),
     "diffus_volume_to_bricks": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
     "diffus_bricks_to_volume": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),

@@ -276,6 +276,29 @@ int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* 
     return cuda_rc(launch_mlp_bwd(params, x, mask, grad_out, n, out_scale, grad_params, workspace, (cudaStream_t)stream));
 }
 
+int64_t diffus_splat_workspace_bytes(int32_t H, int32_t W) { return (H < 1 || W < 1) ? 0 : splat_workspace_bytes(H, W); }
+
+int32_t diffus_splat_forward(const float* c0, const float* c1, const float* c2, const float* intensities, int64_t n,
+                             int32_t H, int32_t W, float sigma, float* out, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+    if (!c0 || !c1 || !c2 || !intensities || !out) return DIFFUS_E_NULL;
+    if (n < 1 || n >= ((int64_t)1 << 32) - 1 || H < 1 || W < 1 || !(sigma > 0.f)) return DIFFUS_E_SHAPE;
+    if (((int)(6.f * sigma) | 1) > 63) return DIFFUS_E_UNSUPPORTED;
+    if (!workspace || workspace_bytes < splat_workspace_bytes(H, W)) return DIFFUS_E_WORKSPACE;
+    return cuda_rc(launch_splat_fwd(c0, c1, c2, intensities, n, H, W, sigma, out, workspace, (cudaStream_t)stream));
+}
+
+int32_t diffus_splat_backward(const float* c0, const float* c1, const float* c2, const float* intensities, int64_t n,
+                              int32_t H, int32_t W, float sigma, const float* grad_out, float* grad_intensities,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!c0 || !c1 || !c2 || !intensities || !grad_out || !grad_intensities) return DIFFUS_E_NULL;
+    if (n < 1 || n >= ((int64_t)1 << 32) - 1 || H < 1 || W < 1 || !(sigma > 0.f)) return DIFFUS_E_SHAPE;
+    if (((int)(6.f * sigma) | 1) > 63) return DIFFUS_E_UNSUPPORTED;
+    if (!workspace || workspace_bytes < splat_workspace_bytes(H, W)) return DIFFUS_E_WORKSPACE;
+    return cuda_rc(launch_splat_bwd(c0, c1, c2, intensities, n, H, W, sigma, grad_out, grad_intensities, workspace,
+                                    (cudaStream_t)stream));
+}
+
 int64_t diffus_brick_elems(const int32_t dim[3]) {
     if (!dim) return 0;
     int64_t nbi = (dim[0] + BRICK_I - 1) / BRICK_I, nbj = (dim[1] + BRICK_J - 1) / BRICK_J,

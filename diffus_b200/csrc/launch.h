@@ -48,6 +48,13 @@ cudaError_t launch_cone_directions(const double* median, int64_t n_poses, int64_
 cudaError_t launch_to_bricks(const float* linear, const int32_t dim[3], float* bricks, cudaStream_t st);
 cudaError_t launch_from_bricks(const float* bricks, const int32_t dim[3], float* linear, cudaStream_t st);
 
+// splat_kernels.cu
+int64_t splat_workspace_bytes(int H, int W);
+cudaError_t launch_splat_fwd(const float* c0, const float* c1, const float* c2, const float* val, int64_t n, int H, int W,
+                             float sigma, float* out, void* ws, cudaStream_t st);
+cudaError_t launch_splat_bwd(const float* c0, const float* c1, const float* c2, const float* val, int64_t n, int H, int W,
+                             float sigma, const float* grad_out, float* grad_val, void* ws, cudaStream_t st);
+
 // mlp_kernels.cu
 cudaError_t launch_mlp_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
                            float fill, float* out, cudaStream_t st);

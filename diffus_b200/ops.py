@@ -490,6 +490,49 @@ def from_bricks(bricks: torch.Tensor, dims) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------
+# scan conversion (differentiable_splat)
+# ---------------------------------------------------------------------------------------
+def _splat_call(fwd: bool, coords, val, H, W, sigma, grad_out=None):
+    dev = _require_cuda(*coords, val, grad_out)
+    lib = _lib.load()
+    c = [t.reshape(-1).to(torch.float32).contiguous() for t in coords]
+    v = val.reshape(-1).to(torch.float32).contiguous()
+    n = v.numel()
+    with torch.cuda.device(dev):
+        wbytes = lib.diffus_splat_workspace_bytes(H, W)
+        ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+        if fwd:
+            out = torch.empty((W, H), dtype=torch.float32, device=dev)
+            _lib.check(lib.diffus_splat_forward(c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(), v.data_ptr(), n, H, W,
+                                                float(sigma), out.data_ptr(), ws.data_ptr(), wbytes, _stream(dev)),
+                       "diffus_splat_forward")
+            _count(4)
+        else:
+            g = grad_out.to(torch.float32).contiguous()
+            out = torch.empty((n,), dtype=torch.float32, device=dev)
+            _lib.check(lib.diffus_splat_backward(c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(), v.data_ptr(), n, H, W,
+                                                 float(sigma), g.data_ptr(), out.data_ptr(), ws.data_ptr(), wbytes,
+                                                 _stream(dev)), "diffus_splat_backward")
+            _count(6)
+    return out
+
+
+class SplatFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, z, intensities, H, W, sigma):
+        ctx.save_for_backward(x, y, z, intensities)
+        ctx.meta = (H, W, sigma)
+        return _splat_call(True, (x, y, z), intensities, H, W, sigma)
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, y, z, val = ctx.saved_tensors
+        H, W, sigma = ctx.meta
+        g = _splat_call(False, (x, y, z), val, H, W, sigma, grad).reshape(val.shape).to(val.dtype)
+        return None, None, None, g, None, None, None
+
+
+# ---------------------------------------------------------------------------------------
 # MLP
 # ---------------------------------------------------------------------------------------
 def mlp_fwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], out_scale: float,

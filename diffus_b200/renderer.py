@@ -259,6 +259,34 @@ def propagate_full_rays_batched(refLR: torch.Tensor) -> torch.Tensor:
     return torch.cumsum(echo, dim=1)
 
 
+def differentiable_splat(x, y, z, intensities, H=256, W=256, sigma=2.0):
+    """Splat ray samples onto the 2-D plane of highest coordinate variance (reference ``src/renderer.py:694-737``).
+
+    Same recipe as the reference -- axes of largest variance, round + clamp to pixels, non-accumulating write
+    (for duplicate pixels the last sample wins), Gaussian blur of image and hit mask, ratio, transposed -- with
+    the axis choice made on the device (no ``.item()`` syncs).  Differentiable w.r.t. ``intensities``.
+    """
+    return ops.SplatFunction.apply(x, y, z, intensities, int(H), int(W), float(sigma))
+
+
+def rotate_around_apex(x, z, apex, median):
+    """Rotate fan points so that the median direction maps onto [0, 1] (reference ``src/renderer.py:655-692``).
+
+    Same arithmetic as the reference (which shifts x by the hard-wired 128, not by the apex): a 2x2 rotation of
+    two coordinate arrays -- element-wise work on the caller's device that feeds :func:`differentiable_splat`.
+    """
+    device = x.device
+    x_shifted = x - 128
+    z_shifted = z
+    median_vec = torch.tensor(median, dtype=torch.float32, device=device)
+    median_vec = median_vec / median_vec.norm()
+    angle = torch.atan2(median_vec[0], median_vec[1])
+    cos_a, sin_a = torch.cos(angle), torch.sin(angle)
+    x_rot = cos_a * x_shifted - sin_a * z_shifted + apex[0]
+    z_rot = sin_a * x_shifted + cos_a * z_shifted + apex[1]
+    return x_rot, z_rot
+
+
 def custom_nearest_sampler(Z: torch.Tensor, points: torch.Tensor, visualize: bool = False, sampler: str = "prop",
                            start: int = 100):
     """Nearest-voxel lookup at explicit points (reference ``src/renderer.py:741-819``).

@@ -164,6 +164,22 @@ int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* 
                             float* grad_params, void* workspace, int64_t workspace_bytes,
                             void* stream);
 
+/* Scan conversion: differentiable_splat (src/renderer.py:694-737).  c0,c1,c2 are the three coordinate
+ * arrays (float32, n each -- the reference casts x, y, z to float32, :709-710), intensities n float32.
+ * The two axes of largest variance are picked on the device; pixels are rounded and clamped; duplicate
+ * pixels keep the sample with the highest index (the reference's non-accumulating indexed write); image
+ * and hit mask are blurred with the normalised (int(6 sigma)|1)^2 Gaussian; out is (W,H) =
+ * (blur(image) / (blur(mask) + 1e-8))^T.  Backward: grad_out (W,H) -> grad_intensities (n), every
+ * duplicate receiving its pixel's gradient, as torch's index_put_ backward does. */
+int64_t diffus_splat_workspace_bytes(int32_t H, int32_t W);
+int32_t diffus_splat_forward(const float* c0, const float* c1, const float* c2, const float* intensities,
+                             int64_t n, int32_t H, int32_t W, float sigma, float* out, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+int32_t diffus_splat_backward(const float* c0, const float* c1, const float* c2, const float* intensities,
+                              int64_t n, int32_t H, int32_t W, float sigma, const float* grad_out,
+                              float* grad_intensities, void* workspace, int64_t workspace_bytes,
+                              void* stream);
+
 /* LINEAR (D,H,W) -> BRICK copy of a volume (and back, for gradients). dst holds
  * diffus_brick_elems(dim) floats. */
 int64_t diffus_brick_elems(const int32_t dim[3]);

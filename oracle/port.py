@@ -268,13 +268,18 @@ def mlp_forward(x, w1, b1, w2, b2, w3, b3):
 # ----------------------------------------------------------------------------------------
 
 
-def splat(x, y, z, intensities, H=256, W=256, sigma=2.0):
+def splat(x, y, z, intensities, H=256, W=256, sigma=2.0, last_wins=True):
     """``differentiable_splat`` (``src/renderer.py:694-737``).
 
     Pick the two axes of largest coordinate variance (descending); round+clamp to pixels;
-    NON-accumulating indexed write of intensities and ones (duplicates: one write wins);
-    blur both with a normalised separable Gaussian of size ``int(6 sigma) | 1``; divide;
-    return transposed.
+    NON-accumulating indexed write of intensities and ones; blur both with a normalised
+    separable Gaussian of size ``int(6 sigma) | 1``; divide; return transposed.
+
+    Duplicate pixels: ``index_put_(accumulate=False)`` leaves WHICH write survives undefined
+    (torch 2.11's CPU kernel is parallel: measured here, the first and the last duplicate
+    both win, depending on thread chunking).  ``last_wins=True`` pins the sequential
+    reading -- the sample with the highest flat index survives -- while keeping torch's
+    backward, in which every duplicate receives its pixel's gradient.
     """
     import torch.nn.functional as F
     coords = [x, y, z]
@@ -287,6 +292,12 @@ def splat(x, y, z, intensities, H=256, W=256, sigma=2.0):
     wgt = torch.zeros_like(img)
     i0 = torch.clamp(c0.round().long(), 0, W - 1)
     i1 = torch.clamp(c1.round().long(), 0, H - 1)
+    if last_wins:
+        flat = (i1 * W + i0).reshape(-1)
+        order = torch.arange(flat.numel())
+        winner = torch.full((H * W,), -1, dtype=torch.long).scatter_reduce(0, flat, order, "amax", include_self=True)
+        vflat = val.reshape(-1)
+        val = (vflat + (vflat.detach()[winner[flat]] - vflat.detach())).reshape(val.shape)   # value of the winner, own gradient
     img[0, 0, i1, i0] += val
     wgt[0, 0, i1, i0] += 1
     size = int(6 * sigma) | 1

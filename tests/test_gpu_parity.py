@@ -350,6 +350,44 @@ def test_mlp_render_training_step_vs_oracle():
     assert l1 < l0
 
 
+def test_splat_golden_and_gradient(golden_splat):
+    """differentiable_splat (row f1): golden images from the reference; duplicates: last sample wins; gradient vs oracle."""
+    from diffus_b200 import differentiable_splat
+    from oracle import port
+    g = golden_splat
+    x, y, z = (torch.tensor(g[k], device=dev()) for k in ("x", "y", "z"))
+    val = torch.tensor(g["val"], device=dev())
+    for sigma in (0.5, 1.0):
+        img = differentiable_splat(x, y, z, val, H=64, W=64, sigma=sigma)
+        assert img.shape == (64, 64)
+        np.testing.assert_allclose(img.cpu().numpy(), g[f"img_sigma{sigma}"], rtol=1e-5, atol=1e-6)
+    # float coordinates (after rotate_around_apex), many duplicate pixels, axis choice y-z, non-square image
+    gen = torch.Generator().manual_seed(4)
+    n = 5000
+    cx = torch.full((n,), 7.25)
+    cy = torch.rand(n, generator=gen) * 70 - 3
+    cz = torch.rand(n, generator=gen) * 40 - 2
+    v = torch.randn(n, generator=gen)
+    v64 = v.clone().requires_grad_(True)
+    want = port.splat(cx, cy, cz, v64, H=40, W=72, sigma=2.0)
+    w = torch.randn(want.shape, generator=gen)
+    (gw,) = torch.autograd.grad((want * w).sum(), v64)
+    vd = v.to(dev()).requires_grad_(True)
+    got = differentiable_splat(cx.to(dev()), cy.to(dev()), cz.to(dev()), vd, H=40, W=72, sigma=2.0)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=2e-5, atol=2e-6)
+    (got * w.to(dev())).sum().backward()
+    assert_grad_close(vd.grad.cpu().numpy(), gw.numpy(), "d splat / d intensities", rtol=2e-5)
+    # end to end with the renderer's own outputs, as every HEAD-era notebook does
+    from diffus_b200 import UltrasoundRenderer
+    from diffus_b200.phantoms import layered_phantom, config1_pose
+    vol = layered_phantom(64, seed=1)
+    src, dirs = config1_pose(64, 24)
+    xi, yi, zi, frame = UltrasoundRenderer(80, 1e-3).plot_beam_frame(vol.to(dev()), src.to(dev()), dirs.to(dev()), plot=False)
+    img = differentiable_splat(xi, yi, zi, frame, H=64, W=64, sigma=0.5)
+    ref_img = port.splat(xi.cpu(), yi.cpu(), zi.cpu(), frame.cpu(), H=64, W=64, sigma=0.5)
+    np.testing.assert_allclose(img.cpu().numpy(), ref_img.numpy(), rtol=2e-5, atol=2e-6)
+
+
 def test_full_size_properties_config1():
     """BASELINE config 1 at full size (256^3, 128 x 512): properties that need no oracle run."""
     from diffus_b200 import UltrasoundRenderer, PreparedVolume, render_frames

@@ -71,3 +71,14 @@ def test_mlp_and_splat_live(ref):
     with RL.quiet():
         img = ref.renderer.differentiable_splat(xs, ys, zs, val, H=48, W=48, sigma=1.0)
     np.testing.assert_allclose(port.splat(xs, ys, zs, val, H=48, W=48, sigma=1.0).numpy(), img.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_rotate_around_apex_live(ref):
+    from diffus_b200 import rotate_around_apex
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(7, 11, generator=g) * 200
+    z = torch.rand(7, 11, generator=g) * 200
+    want = ref.renderer.rotate_around_apex(x.reshape(-1), z.reshape(-1), (120.0, 4.0), (0.3, -0.9))
+    got = rotate_around_apex(x.reshape(-1), z.reshape(-1), (120.0, 4.0), (0.3, -0.9))
+    np.testing.assert_allclose(got[0].numpy(), want[0].numpy(), rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(got[1].numpy(), want[1].numpy(), rtol=1e-6, atol=1e-4)
