@@ -590,6 +590,9 @@ static int warps_per_block(int64_t total_rays) {
 template <typename K>
 static cudaError_t ensure_smem(K kernel, size_t smem) {
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    // ask for the largest shared-memory carveout so the CTA count per SM is set by our buffers, not the default split
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     if (smem > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     return cudaSuccess;
 }
