@@ -113,6 +113,15 @@ def main():
         report("4: MLP(256^3) -> 4096 frames -> MSE -> d/dweights, NEAREST sampler (the reference's own training form)",
                ms_near, P * 65536, P, 12)
         ms = timed(step, max(3, args.iters // 4))
+        from diffus_b200 import ops
+        from diffus_b200.impedance import pack_params
+        pk = pack_params(model).detach()
+        for name, path in (("cuda cores", ops.MLP_PATH_CUDA_CORES), ("tcgen05 3xTF32", ops.MLP_PATH_TENSOR)):
+            with ops.mlp_path(path):
+                t_ms = timed(lambda: ops.mlp_fwd_impl(pk, mri.reshape(-1), None, 1e6, 400.0), args.iters)
+            print(json.dumps({"config": f"4: MLP forward over 256^3 voxels, {name}", "ms": t_ms,
+                              "gvoxels_per_s": mri.numel() / (t_ms * 1e-3) / 1e9,
+                              "tflops_layer2": mri.numel() * 2048 / (t_ms * 1e-3) / 1e12}), flush=True)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(); Z = model.impedance_volume(mri, None, 1e6, 400.0); e[1].record()
         gz = torch.randn_like(Z); e[2].record(); Z.backward(gz); e[3].record(); torch.cuda.synchronize()

@@ -76,6 +76,7 @@ SIGNATURES = {
     "diffus_echo_backward": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "diffus_cone_directions": (_i32, [_vp, _i64, _i64, _f64, _vp, _vp]),
     "diffus_mlp_forward": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp]),
+    "diffus_mlp_forward_ex": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _vp, _i32, _vp]),
     "diffus_mlp_bwd_workspace_bytes": (_i64, [_i64]),
     "diffus_mlp_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _i64, _vp]),
     "diffus_splat_workspace_bytes": (_i64, [_i32, _i32]),

@@ -258,11 +258,20 @@ int32_t diffus_cone_directions(const double* median, int64_t n_poses, int64_t n_
     return cuda_rc(launch_cone_directions(median, n_poses, n_rays, opening_angle, out, (cudaStream_t)stream));
 }
 
-int32_t diffus_mlp_forward(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
-                           float fill, float* out, void* stream) {
+int32_t diffus_mlp_forward_ex(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
+                              float fill, float* out, int32_t path, void* stream) {
     if (!params || !x || !out) return DIFFUS_E_NULL;
     if (n < 1) return DIFFUS_E_SHAPE;
+    if (path < DIFFUS_MLP_PATH_AUTO || path > DIFFUS_MLP_PATH_TENSOR) return DIFFUS_E_ENUM;
+    // volumes go through the tcgen05 kernel (128-voxel tiles); a handful of samples is not worth a TMEM allocation
+    const bool tensor = path == DIFFUS_MLP_PATH_TENSOR || (path == DIFFUS_MLP_PATH_AUTO && n >= 16384);
+    if (tensor) return cuda_rc(launch_mlp_fwd_tc(params, x, mask, n, out_scale, fill, out, (cudaStream_t)stream));
     return cuda_rc(launch_mlp_fwd(params, x, mask, n, out_scale, fill, out, (cudaStream_t)stream));
+}
+
+int32_t diffus_mlp_forward(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
+                           float fill, float* out, void* stream) {
+    return diffus_mlp_forward_ex(params, x, mask, n, out_scale, fill, out, DIFFUS_MLP_PATH_AUTO, stream);
 }
 
 int64_t diffus_mlp_bwd_workspace_bytes(int64_t n) { return n < 1 ? 0 : mlp_bwd_workspace_bytes(n); }

@@ -58,6 +58,8 @@ cudaError_t launch_splat_bwd(const float* c0, const float* c1, const float* c2, 
 // mlp_kernels.cu
 cudaError_t launch_mlp_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
                            float fill, float* out, cudaStream_t st);
+cudaError_t launch_mlp_fwd_tc(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
+                              float fill, float* out, cudaStream_t st);
 int64_t mlp_bwd_workspace_bytes(int64_t n);
 cudaError_t launch_mlp_bwd(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
                            float out_scale, float* grad_params, void* workspace, cudaStream_t st);

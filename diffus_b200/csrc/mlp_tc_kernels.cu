@@ -1,0 +1,180 @@
+// Impedance MLP forward with layer 2 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Of Linear(1,32)-ReLU-Linear(32,32)-ReLU-Linear(32,1) only layer 2 is a dense contraction:
+//     H2pre[128 voxels x 32] = H1[128 x 32] * W2^T[32 x 32]          per 128-voxel tile.
+// A single TF32 pass cannot hold the renderer's tolerance (impedances enter the reflection coefficient as
+// a difference of nearly equal numbers), so the product is evaluated as the 3xTF32 split
+//     H1 W2^T ~= H1_hi W2_hi^T + H1_lo W2_hi^T + H1_hi W2_lo^T ,   x_hi = x & 0xffffe000, x_lo = x - x_hi,
+// accumulated in fp32 in TMEM (relative error ~2^-21 per product).  Layers 1 and 3 (an outer and an inner
+// product) stay on the CUDA cores: each thread owns one voxel, builds its row of H1 (hi and lo) directly in
+// the canonical K-major shared-memory layout the tensor core reads (8-row x 16-byte core matrices, no
+// swizzle), and after the MMAs reads its row of H2pre back from TMEM with one tcgen05.ld (32x32b.x32).
+//
+// One elected thread issues 12 tcgen05.mma (M=128, N=32, K=8) per tile and commits them to an mbarrier.
+#include "common.cuh"
+#include "launch.h"
+
+namespace diffus {
+
+namespace {
+
+constexpr int TILE_M = 128, HID = 32;
+constexpr int OFF_W1 = 0, OFF_B1 = 32, OFF_W2 = 64, OFF_B2 = 64 + 1024, OFF_W3 = OFF_B2 + 32, OFF_B3 = OFF_W3 + 32;
+// canonical K-major layout, no swizzle: [k_chunk of 4 floats][row group of 8][row in group][4 floats]
+constexpr uint32_t A_SBO = 128, A_LBO = (TILE_M / 8) * 128;     // bytes: next 8-row group, next 16-byte K chunk
+constexpr uint32_t B_SBO = 128, B_LBO = (HID / 8) * 128;
+constexpr int A_FLOATS = TILE_M * HID, B_FLOATS = HID * HID;
+constexpr int SMEM_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS + 4 * HID + 4;
+constexpr uint32_t TMEM_COLS = 32;
+// instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((addr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;                                     // descriptor version for sm_100
+    return d;                                                   // base_offset 0, layout_type 0 = no swizzle
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(TILE_M) mlp_fwd_tc_kernel(const float* __restrict__ params, const float* __restrict__ x,
+                                                            const uint8_t* __restrict__ mask, int64_t n, float out_scale,
+                                                            float fill, float* __restrict__ out) {
+    extern __shared__ __align__(128) float smem[];
+    float* a_hi = smem;
+    float* a_lo = a_hi + A_FLOATS;
+    float* b_hi = a_lo + A_FLOATS;
+    float* b_lo = b_hi + B_FLOATS;
+    float* w1 = b_lo + B_FLOATS;
+    float* b1 = w1 + HID;
+    float* b2 = b1 + HID;
+    float* w3 = b2 + HID;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid < HID) {
+        w1[tid] = params[OFF_W1 + tid];
+        b1[tid] = params[OFF_B1 + tid];
+        b2[tid] = params[OFF_B2 + tid];
+        w3[tid] = params[OFF_W3 + tid];
+    }
+    const float b3 = params[OFF_B3];
+    // W2 (out j, in i) is already "N x K, K-major": B[n][k] = W2[n][k]
+    for (int e = tid; e < B_FLOATS; e += TILE_M) {
+        int nn = e >> 5, k = e & 31;
+        float v = params[OFF_W2 + e], hi = tf32_hi(v);
+        int idx = (k >> 2) * (B_LBO / 4) + (nn >> 3) * (B_SBO / 4) + (nn & 7) * 4 + (k & 3);
+        b_hi[idx] = hi;
+        b_lo[idx] = v - hi;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // W2 tiles: generic-proxy writes -> tensor-core reads
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const uint32_t tmem = tmem_base_slot;
+    const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
+    const uint32_t bar_s = smem_u32(&bar);
+    uint32_t phase = 0;
+
+    const int64_t n_tiles = (n + TILE_M - 1) / TILE_M;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t idx = tile * TILE_M + tid;
+        const float xv = idx < n ? __ldg(x + idx) : 0.f;
+        // layer 1 on the CUDA cores, written straight into the tensor core's operand layout
+        float* row_hi = a_hi + (tid >> 3) * (A_SBO / 4) + (tid & 7) * 4;
+        float* row_lo = a_lo + (tid >> 3) * (A_SBO / 4) + (tid & 7) * 4;
+#pragma unroll
+        for (int kc = 0; kc < HID / 4; ++kc) {
+            float h[4], hi[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = fmaxf(fmaf(w1[4 * kc + j], xv, b1[4 * kc + j]), 0.f);
+                hi[j] = tf32_hi(h[j]);
+            }
+            *(float4*)(row_hi + kc * (A_LBO / 4)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *(float4*)(row_lo + kc * (A_LBO / 4)) = make_float4(h[0] - hi[0], h[1] - hi[1], h[2] - hi[2], h[3] - hi[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n");
+            uint32_t acc = 0;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t a_s = pass == 1 ? a_lo_s : a_hi_s, b_s = pass == 2 ? b_lo_s : b_hi_s;
+#pragma unroll
+                for (int j = 0; j < HID / 8; ++j) {                    // K = 8 per MMA = two 16-byte chunks
+                    mma_tf32(tmem, smem_desc(a_s + j * 2 * A_LBO, A_LBO, A_SBO), smem_desc(b_s + j * 2 * B_LBO, B_LBO, B_SBO), acc);
+                    acc = 1;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_s) : "memory");
+        }
+        // wait for the accumulator (bounded: a mis-programmed pipeline must fail, not hang the GPU)
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(bar_s), "r"(phase) : "memory");
+        if (!done) __trap();
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);     // this warp's 32 TMEM lanes, 32 columns
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        // layer 3 on the CUDA cores
+        float acc3 = b3;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) acc3 = fmaf(w3[j], fmaxf(__uint_as_float(v[j]) + b2[j], 0.f), acc3);
+        if (idx < n) out[idx] = (mask && !mask[idx]) ? fill : out_scale * acc3;
+        // the next tile overwrites the operand tiles and the accumulator
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TMEM_COLS));
+}
+
+cudaError_t launch_mlp_fwd_tc(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
+                              float fill, float* out, cudaStream_t st) {
+    size_t smem = SMEM_FLOATS * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t tiles = (n + TILE_M - 1) / TILE_M;
+    unsigned grid = (unsigned)max((int64_t)1, min(tiles, (int64_t)148 * 4));
+    mlp_fwd_tc_kernel<<<grid, TILE_M, smem, st>>>(params, x, mask, n, out_scale, fill, out);
+    return cudaGetLastError();
+}
+
+}  // namespace diffus

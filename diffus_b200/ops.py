@@ -535,6 +535,25 @@ class SplatFunction(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------
 # MLP
 # ---------------------------------------------------------------------------------------
+MLP_PATH_AUTO, MLP_PATH_CUDA_CORES, MLP_PATH_TENSOR = 0, 1, 2
+_MLP_PATH = MLP_PATH_AUTO      # tests and benchmarks pin a path through mlp_path(); AUTO = tcgen05 for volumes
+
+
+class mlp_path:
+    """Context manager pinning the MLP forward to the CUDA-core or the tcgen05 kernel (default: automatic)."""
+
+    def __init__(self, path: int):
+        self.path = path
+
+    def __enter__(self):
+        global _MLP_PATH
+        self.saved, _MLP_PATH = _MLP_PATH, self.path
+
+    def __exit__(self, *exc):
+        global _MLP_PATH
+        _MLP_PATH = self.saved
+
+
 def mlp_fwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], out_scale: float,
             fill: float) -> torch.Tensor:
     dev = _require_cuda(params, x, mask)
@@ -547,8 +566,8 @@ def mlp_fwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Ten
     with torch.cuda.device(dev):
         out = torch.empty(x.shape, dtype=torch.float32, device=dev)
         if xc.numel():
-            _lib.check(lib.diffus_mlp_forward(p.data_ptr(), xc.data_ptr(), _ptr(m), xc.numel(), out_scale, fill,
-                                              out.data_ptr(), _stream(dev)), "diffus_mlp_forward")
+            _lib.check(lib.diffus_mlp_forward_ex(p.data_ptr(), xc.data_ptr(), _ptr(m), xc.numel(), out_scale, fill,
+                                                 out.data_ptr(), _MLP_PATH, _stream(dev)), "diffus_mlp_forward")
             _count(1)
     return out
 

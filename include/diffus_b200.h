@@ -155,6 +155,15 @@ int32_t diffus_cone_directions(const double* median, int64_t n_poses, int64_t n_
 #define DIFFUS_MLP_NPARAMS 1153
 int32_t diffus_mlp_forward(const float* params, const float* x, const uint8_t* mask,
                            int64_t n, float out_scale, float fill, float* out, void* stream);
+/* Same with an explicit execution path: layer 2 (the only dense contraction, M x 32 x 32) either as fp32
+ * FMAs on the CUDA cores or as a 3xTF32-split tcgen05.mma with the accumulator in TMEM (fp32-grade
+ * accuracy; 128-voxel tiles).  AUTO = tensor cores for n >= 16384. */
+#define DIFFUS_MLP_PATH_AUTO 0
+#define DIFFUS_MLP_PATH_CUDA_CORES 1
+#define DIFFUS_MLP_PATH_TENSOR 2
+int32_t diffus_mlp_forward_ex(const float* params, const float* x, const uint8_t* mask,
+                              int64_t n, float out_scale, float fill, float* out, int32_t path,
+                              void* stream);
 /* grad_params (1153) is ACCUMULATED into (caller zero-fills): d/dparams of
  * sum_i grad_out[i] * out_scale * mlp(x[i]) over unmasked i.  workspace:
  * diffus_mlp_bwd_workspace_bytes(n) bytes. */

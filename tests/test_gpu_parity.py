@@ -283,6 +283,30 @@ def test_mlp_forward_backward_golden(golden_mlp):
         assert_grad_close(p.grad.cpu().numpy(), want, name)
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 257, 5000, 70001])
+def test_mlp_tensor_core_path_matches_cuda_cores_and_oracle(n):
+    """Layer 2 as 3xTF32 tcgen05.mma (accumulator in TMEM) vs the fp32 CUDA-core kernel vs the fp64 oracle."""
+    from diffus_b200 import ImpedanceEstimator, ops
+    from diffus_b200.impedance import pack_params
+    from oracle import port
+    torch.manual_seed(n)
+    model = ImpedanceEstimator(1)
+    x = torch.randn(n) * 2.0
+    mask = torch.rand(n) > 0.2
+    want = port.mlp_forward(x.double().reshape(-1, 1), *[p.detach().double() for p in model.parameters()]).reshape(-1) * 1e6
+    want = torch.where(mask, want, torch.tensor(400.0, dtype=torch.float64))
+    params = pack_params(model).detach().to(dev())
+    with ops.mlp_path(ops.MLP_PATH_CUDA_CORES):
+        cc = ops.mlp_fwd_impl(params, x.to(dev()), mask.to(dev()), 1e6, 400.0)
+    with ops.mlp_path(ops.MLP_PATH_TENSOR):
+        tc = ops.mlp_fwd_impl(params, x.to(dev()), mask.to(dev()), 1e6, 400.0)
+        tc2 = ops.mlp_fwd_impl(params, x.to(dev()), None, 1.0, 0.0)          # no mask, second launch reuses TMEM cleanly
+    np.testing.assert_allclose(cc.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2.0)
+    np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=2e-5, atol=2.0)
+    want2 = port.mlp_forward(x.double().reshape(-1, 1), *[p.detach().double() for p in model.parameters()]).reshape(-1)
+    np.testing.assert_allclose(tc2.cpu().numpy(), want2.numpy(), rtol=2e-5, atol=2e-6)
+
+
 def test_mlp_volume_masked_and_large():
     from diffus_b200 import ImpedanceEstimator
     from oracle import port
