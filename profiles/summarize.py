@@ -66,7 +66,10 @@ def kernel(rep, samples):
         mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         traffic = dr * mult[ur] + dw * mult[uw]
         print(f"\nDRAM traffic {traffic / 1e6:.1f} MB per launch; {traffic / samples:.2f} B per sample ({samples} samples)\n")
-        src = ncu_csv(rep, "source", ("--kernel-name", "regex:" + re.escape(name.split("<")[0].split()[-1])))
+        base = re.search(r"(\w+)\s*[<(]", name)
+        src = ncu_csv(rep, "source", ("--kernel-name", "regex:" + (base.group(1) if base else ".")))
+        if len(src) < 3:
+            continue
         h = src[1]
         si, ei, wi = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
         ops, tot = collections.Counter(), 0
