@@ -230,6 +230,39 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
         assert gsf is None and gdf is None
 
 
+@pytest.mark.parametrize("dims,R,S,start", [((1, 1, 1), 2, 2, 0), ((2, 3, 1), 3, 5, 3), ((5, 4, 7), 2, 33, 0),
+                                             ((9, 9, 9), 37, 31, 29), ((6, 5, 4), 4, 513, 1), ((7, 3, 5), 3, 1025, 512)])
+@pytest.mark.parametrize("sampler", ["nearest", "trilinear"])
+def test_edge_shapes_vs_oracle(dims, R, S, start, sampler):
+    """Degenerate volumes, two-sample rays, crops that leave two columns, rays that are one column over a pass boundary."""
+    from diffus_b200 import render_frames, render_mse_loss
+    g = torch.Generator().manual_seed(S + R)
+    vol = 1.4e6 + 3e5 * torch.rand(dims, generator=g)
+    src = torch.tensor([[0.3, 0.2, 0.1], [dims[0] * 0.5, dims[1] * 0.4, -1.5]])
+    d = torch.randn((2, R, 3), generator=g)
+    d = d / d.norm(dim=-1, keepdim=True) * 0.7                 # sub-voxel steps: long rays stay near the volume
+    alpha = 1e-3
+    v64 = vol.double().requires_grad_(True)
+    s64 = src.double().requires_grad_(True)
+    d64 = d.double().requires_grad_(True)
+    f64 = _oracle_frames(v64, s64, d64, S, alpha, start, sampler)
+    tgt = torch.zeros_like(f64)
+    want = torch.autograd.grad((f64 - tgt).square().mean(), [v64, s64, d64], allow_unused=True)
+    v = vol.to(dev()).requires_grad_(True)
+    s = src.to(dev()).requires_grad_(True)
+    dd = d.to(dev()).requires_grad_(True)
+    f = render_frames(v, s, dd, S, alpha, start, sampler=sampler)
+    assert f.shape == (2, R, S - start)
+    assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), f"{dims} R={R} S={S} start={start}")
+    loss = render_mse_loss(v, s, dd, tgt.float().to(dev()), S, alpha, start, sampler=sampler)
+    loss.backward()
+    if want[0].abs().max() > 0:
+        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume", rtol=2e-4)
+    if sampler == "trilinear" and want[1] is not None and want[1].abs().max() > 0:
+        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources", rtol=2e-4)
+        assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d/ddirections", rtol=2e-4)
+
+
 def test_shared_directions_and_float64_pose():
     from diffus_b200 import render_frames
     from diffus_b200.phantoms import layered_phantom
