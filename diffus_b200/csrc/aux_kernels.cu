@@ -92,18 +92,17 @@ __global__ void median_backward_kernel(const RenderParams p, const int32_t* __re
             float p0 = rs.coord(0, kk), p1 = rs.coord(1, kk), p2 = rs.coord(2, kk);
             if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
                 int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
-                atomicAdd(p.grad_volume + ((int64_t)i * p.vol.H + j) * p.vol.W + l, zb);
+                atomicAdd(p.grad_volume + voxel_offset<LAYOUT>(p.vol, i, j, l), zb);
             } else {
                 TriCell c;
                 tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
                 tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
                 tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+                uint32_t off[8];
+                tri_offsets<LAYOUT>(p.vol, c, off);
                 for (int q = 0; q < 8; ++q) {
-                    int i = (q & 4) ? c.i1[0] : c.i0[0];
-                    int j = (q & 2) ? c.i1[1] : c.i0[1];
-                    int l = (q & 1) ? c.i1[2] : c.i0[2];
                     float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
-                    if (w != 0.f) atomicAdd(p.grad_volume + ((int64_t)i * p.vol.H + j) * p.vol.W + l, w * zb);
+                    if (w != 0.f) atomicAdd(p.grad_volume + off[q], w * zb);
                 }
             }
         }

@@ -158,6 +158,19 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     return m2_shfl(vout, 0);
 }
 
+// The target / upstream-gradient rows are read exactly once: mark them evict-first in L2 so that the
+// stream does not push the (re-used) impedance and gradient volumes out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async_stream4(float* smem_dst, const float* gmem_src, uint64_t policy) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "l"(policy)
+                 : "memory");
+}
+
 // coefficient of the interface owned by column c from the two impedances around it
 __device__ __forceinline__ float reflection(float z_prev, float z_cur) {
     return __fmul_rn(__fsub_rn(z_cur, z_prev), fast_rcp(__fadd_rn(z_prev, z_cur)));
@@ -265,26 +278,27 @@ constexpr int BWD_ZBUF = PREFIX_STRIDE + 1 + (PREFIX_STRIDE + 1) / BwdGeo::CHUNK
 constexpr int BWD_OBUF = PREFIX_STRIDE + PREFIX_STRIDE / BwdGeo::CHUNK + 3;
 constexpr int BWD_SMEM_PER_WARP = BWD_ZBUF + BWD_OBUF + 3 * PREFIX_STRIDE;
 
-template <int SAMPLER, bool POSE64>
+// d loss / d volume accumulates with red.global.add.f32 (index_put_(accumulate=True) semantics) into a
+// gradient volume that has the SAME layout as the volume being gathered: in the brick layout the 32 lanes
+// of a tile (consecutive samples of a ray) hit ~10 cache lines instead of ~32, and the lines are the
+// neighbours of the ones just gathered.
+template <int SAMPLER, int LAYOUT, bool POSE64>
 __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const RaySetup<POSE64>& rs, int k, float zbar) {
-    // the gradient volume is always LINEAR (it goes back to torch / the MLP backward)
     float p0 = rs.coord(0, k), p1 = rs.coord(1, k), p2 = rs.coord(2, k);
-    const uint32_t HW = (uint32_t)p.vol.H * p.vol.W, W = p.vol.W;
     if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
         int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), kk = nearest_index(p2, p.vol.W);
-        atomicAdd(p.grad_volume + ((uint32_t)i * HW + (uint32_t)j * W + kk), zbar);
+        atomicAdd(p.grad_volume + voxel_offset<LAYOUT>(p.vol, i, j, kk), zbar);
     } else {
         TriCell c;
         tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
         tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
         tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+        uint32_t off[8];
+        tri_offsets<LAYOUT>(p.vol, c, off);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            int i = (q & 4) ? c.i1[0] : c.i0[0];
-            int j = (q & 2) ? c.i1[1] : c.i0[1];
-            int kk = (q & 1) ? c.i1[2] : c.i0[2];
             float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
-            if (w != 0.f) atomicAdd(p.grad_volume + ((uint32_t)i * HW + (uint32_t)j * W + kk), w * zbar);
+            if (w != 0.f) atomicAdd(p.grad_volume + off[q], w * zbar);
         }
     }
 }
@@ -310,6 +324,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     float* fout = (LOSS == LOSS_MSE && p.frame) ? p.frame + ray * (int64_t)p.Sout : nullptr;
     if (lane == 0) zbuf[0] = 0.f;
     const int nss = (p.Sout + SS - 1) / SS;
+    const uint64_t stream_policy = l2_evict_first_policy();
 
     M2 vin = M2{0.f, 0.f, 0.f, 0.f};
     float carry_w = 0.f, carry_z = 0.f;      // first column of the later pass: its weight w and its impedance
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             const int nt = nsub * (G::SEG / 32);
             for (int t = 0; t < nt; ++t) {
                 int idx = t * 32 + lane;
-                if (idx < ncol) __pipeline_memcpy_async(gbuf + G::pad(idx), gin + c0 + idx, 4);
+                if (idx < ncol) cp_async_stream4(gbuf + G::pad(idx), gin + c0 + idx, stream_policy);
                 else gbuf[G::pad(idx)] = 0.f;            // columns that do not exist carry no gradient
             }
             __pipeline_commit();
@@ -417,7 +432,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                         acc_d[a] += kf * ga;
                     }
                 }
-                if (VOL_GRAD && zbar != 0.f) scatter_volume_grad<SAMPLER, POSE64>(p, rs, k, zbar);
+                if (VOL_GRAD && zbar != 0.f) scatter_volume_grad<SAMPLER, LAYOUT, POSE64>(p, rs, k, zbar);
             }
         }
         carry_w = next_carry_w;

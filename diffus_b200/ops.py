@@ -148,7 +148,9 @@ def render_bwd_impl(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Opti
                                  sampler, product_f32)
         grad_frame = grad_frame.contiguous().float()
         need_pose = need_pose and sampler == SAMPLER_TRILINEAR
-        gvol = torch.zeros(tuple(dims), dtype=torch.float32, device=dev) if need_volume else \
+        use_bricks = bricks is not None and bricks.numel() > 0
+        gshape = (bricks.numel(),) if use_bricks else tuple(dims)          # the gradient has the gathered layout
+        gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else \
             torch.empty((0,), dtype=torch.float32, device=dev)
         gsrc = torch.empty((P, 3) if need_pose else (0,), dtype=torch.float32, device=dev)
         gdir = torch.empty((P, R, 3) if need_pose else (0,), dtype=torch.float32, device=dev)
@@ -162,6 +164,8 @@ def render_bwd_impl(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Opti
         b.fwd.workspace, b.fwd.workspace_bytes = None, 0
         _lib.check(lib.diffus_render_backward(C.byref(b), _stream(dev)), "diffus_render_backward")
         _count((1 if (need_volume or need_pose) else 0) + (2 if start > 0 else 0) + (1 if need_pose else 0))
+        if need_volume and use_bricks:
+            gvol = from_bricks(gvol, dims)
     return gvol, gsrc, gdir
 
 
@@ -255,7 +259,8 @@ class RenderFunction(torch.autograd.Function):
 def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
                directions: torch.Tensor, target: torch.Tensor, n_samples: int, start: int, alpha: float,
                sampler: int, product_f32: bool, need_volume: bool, need_pose: bool,
-               want_frame: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+               want_frame: bool, keep_brick_grad: bool = False
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """loss = mean((frame - target)^2) with d loss/d volume, d loss/d sources, d loss/d directions.
 
     Returns ``(loss (1,), frame or empty, grad_volume or empty, grad_sources or empty,
@@ -284,7 +289,9 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
             return torch.empty((0,), dtype=torch.float32, device=dev)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         frame = torch.empty((P, R, sout), dtype=torch.float32, device=dev) if want_frame else empty()
-        gvol = torch.zeros(tuple(dims), dtype=torch.float32, device=dev) if need_volume else empty()
+        use_bricks = bricks is not None and bricks.numel() > 0
+        gshape = (bricks.numel(),) if use_bricks else tuple(dims)          # the gradient has the gathered layout
+        gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else empty()
         gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         b.fwd.frame = _ptr(frame)
@@ -297,6 +304,8 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         b.workspace, b.workspace_bytes = ws.data_ptr(), wbytes
         _lib.check(lib.diffus_render_backward(C.byref(b), _stream(dev)), "diffus_render_backward (fused MSE)")
         _count(2 + (2 if start > 0 else 0) + (1 if need_pose else 0))
+        if need_volume and use_bricks and not keep_brick_grad:
+            gvol = from_bricks(gvol, dims)
     return loss, frame, gvol, gsrc, gdir
 
 

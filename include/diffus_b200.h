@@ -98,7 +98,8 @@ typedef struct DiffusRenderBwdArgs {
                                    fwd.seg_prefix = the buffer the forward filled (required
                                    when S-start > 512)                                        */
     const float* grad_frame;    /* (P,R,S-start)                                             */
-    float* grad_volume;         /* (D,H,W) LINEAR layout, ACCUMULATED into (caller zero-fills) */
+    float* grad_volume;         /* same layout as fwd.volume (LINEAR (D,H,W), or diffus_brick_elems()
+                                   floats for BRICK), ACCUMULATED into (caller zero-fills)    */
     float* grad_sources;        /* (P,3) overwritten; trilinear only                         */
     float* grad_directions;     /* (P,R,3) overwritten; trilinear only (per pose, also when
                                    the directions were shared)                                */
