@@ -39,7 +39,7 @@ def main():
     args = ap.parse_args()
     from diffus_b200 import ImpedanceEstimator, PreparedVolume, UltrasoundRenderer, render_frames, render_mse_loss
     from diffus_b200.phantoms import config1_pose, intensity_to_impedance, layered_phantom, mri_phantom, pose_sweep
-    from diffus_b200.training import mlp_render_mse_loss
+    from diffus_b200.training import TrainingVolume, mlp_render_mse_loss
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     dev = torch.device("cuda:0")
@@ -106,9 +106,11 @@ def main():
             tgt = render_frames(PreparedVolume(model.impedance_volume(mri, None, 1e6, 400.0) * 1.01), s, d, 512, 1e-4,
                                 sampler="trilinear")
 
+        tv = TrainingVolume(mri)
+
         def step(sampler="trilinear"):
             model.zero_grad(set_to_none=True)
-            mlp_render_mse_loss(model, mri, s, d, tgt, 512, 1e-4, out_scale=1e6, sampler=sampler).backward()
+            mlp_render_mse_loss(model, tv, s, d, tgt, 512, 1e-4, out_scale=1e6, sampler=sampler).backward()
         ms_near = timed(lambda: step("nearest"), max(3, args.iters // 4))
         report("4: MLP(256^3) -> 4096 frames -> MSE -> d/dweights, NEAREST sampler (the reference's own training form)",
                ms_near, P * 65536, P, 12)

@@ -391,14 +391,21 @@ def test_mlp_render_training_step_vs_oracle():
     l64.backward()
     m = model.to(dev())
     s = sources.to(dev()).requires_grad_(True)
-    for bricks in (True, False):
+    from diffus_b200 import render_mse_loss
+    from diffus_b200.training import TrainingVolume
+    for mode in ("fused", "prepared", "unfused"):
         m.zero_grad()
         s.grad = None
-        loss = mlp_render_mse_loss(m, mri.to(dev()), s, dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6, bricks=bricks)
+        if mode == "unfused":         # plain composition: MLP op -> linear volume -> render op, through autograd
+            Z = m.impedance_volume(mri.to(dev()), None, out_scale=1e6, fill=400.0)
+            loss = render_mse_loss(Z, s, dirs.to(dev()), targets.to(dev()), S, alpha)
+        else:
+            vol_in = TrainingVolume(mri.to(dev())) if mode == "prepared" else mri.to(dev())
+            loss = mlp_render_mse_loss(m, vol_in, s, dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
         loss.backward()
         np.testing.assert_allclose(loss.item(), l64.item(), rtol=2e-4)
         for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
-            assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"d/d{name} (bricks={bricks})", rtol=3e-4)
+            assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"d/d{name} ({mode})", rtol=3e-4)
         assert_grad_close(s.grad.cpu().numpy(), s64.grad.numpy(), "d/dsources", rtol=3e-4)
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     l0 = train_step(m, opt, mri.to(dev()), sources.to(dev()), dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
