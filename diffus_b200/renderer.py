@@ -64,12 +64,20 @@ class PreparedVolume:
             raise ValueError("volume must be (D,H,W)")
         self.volume = volume if volume.dtype == torch.float32 else volume.float()
         self.volume = self.volume.contiguous()
-        self.bricks = ops.to_bricks(self.volume)
         self.shape = tuple(volume.shape)
+        self.refresh()
 
     def refresh(self) -> "PreparedVolume":
-        self.bricks = ops.to_bricks(self.volume)
+        """Rebuild the brick copy (done automatically when the volume tensor was modified in place)."""
+        self._bricks = ops.to_bricks(self.volume)
+        self._version = self.volume._version
         return self
+
+    @property
+    def bricks(self) -> torch.Tensor:
+        if self.volume._version != self._version:
+            self.refresh()
+        return self._bricks
 
 
 def render_frames(volume, sources: torch.Tensor, directions: torch.Tensor, num_samples: int,
