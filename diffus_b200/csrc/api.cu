@@ -238,6 +238,31 @@ int32_t diffus_trace_values(const DiffusRenderArgs* a, float* out, void* stream)
                                        (cudaStream_t)stream));
 }
 
+int32_t diffus_trace_values_backward(const DiffusRenderArgs* a, const float* grad_values, float* grad_volume,
+                                     float* grad_sources, float* grad_directions, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+    int32_t e = check_render(a, false);
+    if (e) return e;
+    if (!grad_values) return DIFFUS_E_NULL;
+    const bool pose_grad = a->sampler == DIFFUS_SAMPLER_TRILINEAR && (grad_sources || grad_directions);
+    if (!pose_grad && !grad_volume) return DIFFUS_OK;
+    if (pose_grad && (!grad_sources || !grad_directions)) return DIFFUS_E_NULL;
+    const int64_t need = pose_grad ? align_up(a->n_poses * a->n_rays * 12, 256) : 0;
+    if (need > 0 && (!workspace || workspace_bytes < need)) return DIFFUS_E_WORKSPACE;
+    RenderParams p = pack(a);
+    p.start = 0;
+    p.Sout = p.S;
+    p.grad_volume = grad_volume;
+    p.grad_src_partial = (float*)workspace;
+    p.grad_dir = grad_directions;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = launch_trace_values_bwd(p, a->sampler, a->volume.layout, a->pose_dtype == DIFFUS_POSE_F64, grad_values,
+                                             pose_grad, grad_volume != nullptr, st);
+    if (ce != cudaSuccess) return (int32_t)ce;
+    if (pose_grad) return cuda_rc(launch_reduce_rays(p.grad_src_partial, a->n_poses, a->n_rays, grad_sources, st));
+    return DIFFUS_OK;
+}
+
 int32_t diffus_echo_forward(const float* refl, int64_t n_rays, int32_t n_interfaces, float* echo, void* stream) {
     if (!refl || !echo) return DIFFUS_E_NULL;
     if (n_rays < 1 || n_interfaces < 1 || n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;

@@ -167,6 +167,70 @@ cudaError_t launch_trace_values(const RenderParams& p, int sampler, int layout, 
     return cudaErrorInvalidValue;
 }
 
+// Backward of trace_values (what autograd does through the reference's sampler): the gradient of every
+// sampled impedance is scattered into the volume (same layout as the gathers) and, for the trilinear
+// sampler, contracted with the spatial gradient into per-ray pose partials.  One warp per ray.
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD>
+__global__ void trace_values_bwd_kernel(const RenderParams p, const float* __restrict__ gval) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ray >= p.total_rays) return;
+    const int64_t pose = ray / p.n_rays;
+    RaySetup<POSE64> rs;
+    rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
+    float acc_s[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < p.S; k += 32) {
+        float g = __ldg(gval + ray * (int64_t)p.S + k);
+        float p0 = rs.coord(0, k), p1 = rs.coord(1, k), p2 = rs.coord(2, k);
+        if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+            if (VOL_GRAD && g != 0.f) {
+                int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
+                atomicAdd(p.grad_volume + voxel_offset<LAYOUT>(p.vol, i, j, l), g);
+            }
+        } else {
+            TriCell c;
+            tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
+            tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
+            tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+            uint32_t off[8];
+            tri_offsets<LAYOUT>(p.vol, c, off);
+            if (POSE_GRAD) {
+                float z[8], dzv[3];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) z[q] = __ldg(p.vol.data + off[q]);
+                tri_combine<true>(z, c, dzv);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { acc_s[a] += g * dzv[a]; acc_d[a] += (float)k * g * dzv[a]; }
+            }
+            if (VOL_GRAD && g != 0.f) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
+                    if (w != 0.f) atomicAdd(p.grad_volume + off[q], w * g);
+                }
+            }
+        }
+    }
+    if (POSE_GRAD) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float ss = warp_sum(acc_s[a]), dd = warp_sum(acc_d[a]);
+            if (lane == 0) { p.grad_src_partial[ray * 3 + a] = ss; p.grad_dir[ray * 3 + a] = dd; }
+        }
+    }
+}
+
+cudaError_t launch_trace_values_bwd(const RenderParams& p, int sampler, int layout, int pose64, const float* gval,
+                                    bool pose_grad, bool vol_grad, cudaStream_t st) {
+    if (sampler == DIFFUS_SAMPLER_NEAREST) pose_grad = false;
+    unsigned grid = (unsigned)((p.total_rays + 3) / 4);
+#define DIFFUS_TB(PG, VG) trace_values_bwd_kernel<S_, L_, P64_, PG, VG><<<grid, 128, 0, st>>>(p, gval)
+    DIFFUS_DISPATCH(if (pose_grad && vol_grad) DIFFUS_TB(true, true); else if (pose_grad) DIFFUS_TB(true, false);
+                    else DIFFUS_TB(false, true); return cudaGetLastError())
+#undef DIFFUS_TB
+    return cudaErrorInvalidValue;
+}
+
 // ---------------------------------------------------------------------------------------
 // per-ray source partials -> per-pose gradient (atomic-free, fixed order)
 // ---------------------------------------------------------------------------------------

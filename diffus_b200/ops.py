@@ -394,6 +394,57 @@ def trace_values(volume, bricks, dims, sources, directions, n_samples, sampler, 
     return out
 
 
+def trace_values_bwd(grad_values, volume, bricks, dims, sources, directions, n_samples, sampler, product_f32,
+                     need_volume, need_pose):
+    dev = _require_cuda(grad_values, volume, bricks, sources, directions)
+    lib = _lib.load()
+    a = DiffusRenderArgs()
+    with torch.cuda.device(dev):
+        P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, 0, 0.0, sampler, product_f32)
+        need_pose = need_pose and sampler == SAMPLER_TRILINEAR
+        use_bricks = bricks is not None and bricks.numel() > 0
+        g = grad_values.contiguous().float()
+        gvol = torch.zeros((bricks.numel(),) if use_bricks else tuple(dims), dtype=torch.float32, device=dev) \
+            if need_volume else None
+        gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else None
+        gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else None
+        ws = torch.empty((max(P * R * 12 + 256, 256),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.diffus_trace_values_backward(C.byref(a), g.data_ptr(), _ptr(gvol), _ptr(gsrc), _ptr(gdir),
+                                                    ws.data_ptr(), ws.numel(), _stream(dev)),
+                   "diffus_trace_values_backward")
+        _count(1 + (1 if need_pose else 0))
+        if need_volume and use_bricks:
+            gvol = from_bricks(gvol, dims)
+    return gvol, gsrc, gdir
+
+
+class TraceValuesFunction(torch.autograd.Function):
+    """Sampled impedances along rays, differentiable like the reference's sampler."""
+
+    @staticmethod
+    def forward(ctx, volume, bricks, dims, sources, directions, n_samples, sampler, product_f32):
+        ctx.save_for_backward(volume, sources, directions)
+        ctx.bricks = bricks
+        ctx.meta = (list(dims), n_samples, sampler, product_f32)
+        return trace_values(volume, bricks, dims, sources, directions, n_samples, sampler, product_f32)
+
+    @staticmethod
+    def backward(ctx, grad):
+        volume, sources, directions = ctx.saved_tensors
+        dims, n_samples, sampler, product_f32 = ctx.meta
+        need_volume = ctx.needs_input_grad[0]
+        need_pose = (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) and sampler == SAMPLER_TRILINEAR
+        gvol = gsrc = gdir = None
+        if need_volume or need_pose:
+            gvol, gs, gd = trace_values_bwd(grad, volume, ctx.bricks, dims, sources, directions, n_samples, sampler,
+                                            product_f32, need_volume, need_pose)
+            if need_pose and ctx.needs_input_grad[3]:
+                gsrc = gs.to(sources.dtype)
+            if need_pose and ctx.needs_input_grad[4]:
+                gdir = (gd if directions.dim() == 3 else gd.sum(0)).to(directions.dtype)
+        return gvol, None, None, gsrc, gdir, None, None, None
+
+
 # ---------------------------------------------------------------------------------------
 # echo traces on explicit reflection coefficients
 # ---------------------------------------------------------------------------------------

@@ -186,9 +186,11 @@ class UltrasoundRenderer:
         dims = list(vol.shape)
         x, y, z = ops.ray_indices(dims, src, dirs, int(num_samples), 0, product_f32)
         vol32 = (vol if vol.dtype == torch.float32 else vol.float()).contiguous()
-        # values carry no autograd graph: gradients go through plot_beam_frame / render_frames (fused kernels)
-        values = ops.trace_values(vol32.detach(), bricks, dims, src, dirs, int(num_samples), _sampler_id(sampler),
-                                  product_f32)
+        if torch.is_grad_enabled() and (vol32.requires_grad or src.requires_grad or dirs.requires_grad):
+            values = ops.TraceValuesFunction.apply(vol32, bricks, dims, src, dirs, int(num_samples), _sampler_id(sampler),
+                                                   product_f32)
+        else:
+            values = ops.trace_values(vol32, bricks, dims, src, dirs, int(num_samples), _sampler_id(sampler), product_f32)
         return x[0], y[0], z[0], values[0]
 
     def simulate_rays(self, volume: torch.Tensor, source: torch.Tensor, directions: torch.Tensor,

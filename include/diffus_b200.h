@@ -133,6 +133,12 @@ int32_t diffus_ray_indices(const DiffusRenderArgs* args, int64_t* x, int64_t* y,
 /* Sampled impedances along the rays, no propagation: the `values` output of
  * UltrasoundRenderer.trace_ray (src/renderer.py:89-180).  out is (P,R,S) (start ignored). */
 int32_t diffus_trace_values(const DiffusRenderArgs* args, float* out, void* stream);
+/* Its backward (autograd through the reference's sampler, src/renderer.py:758 / grid_sample): grad_values
+ * (P,R,S) -> grad_volume (layout of args->volume, ACCUMULATED), and for the trilinear sampler grad_sources
+ * (P,3) + grad_directions (P,R,3) (both or neither).  workspace: P*R*12 bytes (256-aligned) for pose gradients. */
+int32_t diffus_trace_values_backward(const DiffusRenderArgs* args, const float* grad_values,
+                                     float* grad_volume, float* grad_sources, float* grad_directions,
+                                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* compute_echo_traces (src/renderer.py:439-457, through propagate_full_rays_batched :412-436
  * and prop_single_ray :367-410) on explicit reflection coefficients refl (B,N):

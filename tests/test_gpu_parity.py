@@ -56,6 +56,38 @@ def test_simulate_rays_golden(golden_frames, name):
     np.testing.assert_allclose(R.cpu().numpy(), g[f"{name}_refl"], rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("sampler", ["nearest", "trilinear"])
+def test_simulate_rays_is_differentiable_like_the_reference(sampler):
+    """simulate_rays / trace_ray outputs carry gradients to the volume (and the pose for trilinear), SURVEY 3.2."""
+    from diffus_b200 import PreparedVolume, UltrasoundRenderer
+    from diffus_b200.phantoms import layered_phantom, pose_sweep
+    from oracle import port
+    vol = layered_phantom(20, seed=7)
+    sources, dirs = pose_sweep(1, n_rays=5, n=20, seed=1)
+    src, d = sources[0], dirs[0]
+    S = 30
+    v64, s64, d64 = vol.double().requires_grad_(True), src.double().requires_grad_(True), d.double().requires_grad_(True)
+    pts = port.ray_points(s64, d64, S)
+    imp = (port.sample_nearest if sampler == "nearest" else port.sample_trilinear)(v64, pts)[3]
+    R64 = port.reflection_coeff(imp[:, :-1], imp[:, 1:])
+    w = torch.randn(R64.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    want = torch.autograd.grad((R64 * w).sum(), [v64, s64, d64], allow_unused=True)
+    for prepared in (False, True):
+        v = vol.to(dev()).requires_grad_(True)
+        s = src.to(dev()).requires_grad_(True)
+        dd = d.to(dev()).requires_grad_(True)
+        ren = UltrasoundRenderer(S, 1e-3)
+        x, y, z, R = ren.simulate_rays(PreparedVolume(v) if prepared else v, s, dd, sampler=sampler)
+        np.testing.assert_allclose(R.detach().cpu().numpy(), R64.detach().numpy(), rtol=1e-4, atol=1e-7)
+        (R * w.float().to(dev())).sum().backward()
+        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d R / d volume", rtol=2e-4)
+        if sampler == "trilinear":
+            assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d R / d source", rtol=2e-4)
+            assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d R / d directions", rtol=2e-4)
+        else:
+            assert s.grad is None
+
+
 @pytest.mark.parametrize("name", NEAREST_CASES)
 def test_brick_layout_matches_linear(golden_frames, name):
     from diffus_b200 import PreparedVolume, render_frames
