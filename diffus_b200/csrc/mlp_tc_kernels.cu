@@ -100,9 +100,19 @@ __global__ void __launch_bounds__(TILE_M) mlp_fwd_tc_kernel(const float* __restr
     uint32_t phase = 0;
 
     const int64_t n_tiles = (n + TILE_M - 1) / TILE_M;
+    // the next tile's input is fetched one iteration ahead: its DRAM latency hides behind this tile's work
+    float x_next = 0.f;
+    {
+        const int64_t i0 = (int64_t)blockIdx.x * TILE_M + tid;
+        if (blockIdx.x < n_tiles && i0 < n) x_next = __ldg(x + i0);
+    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t idx = tile * TILE_M + tid;
-        const float xv = idx < n ? __ldg(x + idx) : 0.f;
+        const float xv = x_next;
+        {
+            const int64_t inext = (tile + gridDim.x) * TILE_M + tid;
+            x_next = (tile + gridDim.x < n_tiles && inext < n) ? __ldg(x + inext) : 0.f;
+        }
         // layer 1 on the CUDA cores, written straight into the tensor core's operand layout
         float* row_hi = a_hi + (tid >> 3) * (A_SBO / 4) + (tid & 7) * 4;
         float* row_lo = a_lo + (tid >> 3) * (A_SBO / 4) + (tid & 7) * 4;
@@ -172,7 +182,7 @@ cudaError_t launch_mlp_fwd_tc(const float* params, const float* x, const uint8_t
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t tiles = (n + TILE_M - 1) / TILE_M;
-    unsigned grid = (unsigned)max((int64_t)1, min(tiles, (int64_t)148 * 4));
+    unsigned grid = (unsigned)max((int64_t)1, min(tiles, (int64_t)148 * 5));     // 5 CTAs per SM fit (43 KB of shared memory each)
     mlp_fwd_tc_kernel<<<grid, TILE_M, smem, st>>>(params, x, mask, n, out_scale, fill, out);
     return cudaGetLastError();
 }
