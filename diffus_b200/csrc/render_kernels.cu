@@ -241,7 +241,8 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
         const int ncol = min(G::SEG, p.Sout - c0);
         // gather phase: lane = consecutive sample
         const int ntile = (ncol + 31) >> 5;
-#pragma unroll 4
+        constexpr int GATHER_UNROLL = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 4;
+#pragma unroll GATHER_UNROLL
         for (int t = 0; t < ntile; ++t) {
             int idx = t * 32 + lane;
             if (idx < ncol) {
@@ -348,8 +349,10 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             __pipeline_commit();
             // gather phase: one pass over the volume for these columns.  (A cp.async ring for the
             // gathers themselves was measured slower than plain loads: LDGSTS issues at a quarter of
-            // the LDG rate and adds eight shared-memory reads per sample, profiles/r1_notes.md.)
-#pragma unroll 2
+            // the LDG rate and adds eight shared-memory reads per sample)
+            // The nearest sampler has one load per sample and almost no L1 reuse: keep 8 tiles in flight.
+            constexpr int GATHER_UNROLL = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 2;
+#pragma unroll GATHER_UNROLL
             for (int t = 0; t < nt; ++t) {
                 int idx = t * 32 + lane;
                 if (idx < ncol) {
