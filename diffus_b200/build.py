@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libdiffus_b200.so")
-SOURCES = ["api.cu", "render_kernels.cu", "aux_kernels.cu", "mlp_kernels.cu", "mlp_tc_kernels.cu", "splat_kernels.cu"]
+SOURCES = ["api.cu", "render_kernels.cu", "aux_kernels.cu", "mlp_kernels.cu", "mlp_tc_kernels.cu", "splat_kernels.cu", "preprocess_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "2"]
 

@@ -333,6 +333,21 @@ int32_t diffus_splat_backward(const float* c0, const float* c1, const float* c2,
                                     (cudaStream_t)stream));
 }
 
+int32_t diffus_brain_mask(const float* volume, const int32_t dim[3], float threshold, int32_t iterations, uint8_t* mask,
+                          uint8_t* scratch, void* stream) {
+    if (!volume || !dim || !mask || !scratch) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1 || iterations < 0 || iterations > 64) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_brain_mask(volume, dim, threshold, iterations, mask, scratch, (cudaStream_t)stream));
+}
+
+int32_t diffus_masked_zscore(const float* volume, const uint8_t* mask, int64_t n, float* out, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    if (!volume || !mask || !out) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    if (!workspace || workspace_bytes < 64) return DIFFUS_E_WORKSPACE;
+    return cuda_rc(launch_masked_zscore(volume, mask, n, out, workspace, (cudaStream_t)stream));
+}
+
 int64_t diffus_brick_elems(const int32_t dim[3]) {
     if (!dim) return 0;
     int64_t nbi = (dim[0] + BRICK_I - 1) / BRICK_I, nbj = (dim[1] + BRICK_J - 1) / BRICK_J,

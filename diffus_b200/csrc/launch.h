@@ -57,6 +57,11 @@ cudaError_t launch_splat_fwd(const float* c0, const float* c1, const float* c2, 
 cudaError_t launch_splat_bwd(const float* c0, const float* c1, const float* c2, const float* val, int64_t n, int H, int W,
                              float sigma, const float* grad_out, float* grad_val, void* ws, cudaStream_t st);
 
+// preprocess_kernels.cu
+cudaError_t launch_brain_mask(const float* volume, const int32_t dim[3], float threshold, int iterations, uint8_t* mask,
+                              uint8_t* scratch, cudaStream_t st);
+cudaError_t launch_masked_zscore(const float* volume, const uint8_t* mask, int64_t n, float* out, void* ws, cudaStream_t st);
+
 // mlp_kernels.cu
 cudaError_t launch_mlp_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
                            float fill, float* out, cudaStream_t st);

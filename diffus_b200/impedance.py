@@ -68,16 +68,14 @@ class ImpedanceEstimator(nn.Module):
     @staticmethod
     def compute_impedance_volume(volume: torch.Tensor, model: "ImpedanceEstimator", threshold: float = 50,
                                  mask: torch.Tensor = None) -> torch.Tensor:
-        """Full impedance volume from a trained model (reference ``:39-54``).
+        """Full impedance volume from a trained model (reference ``:39-54``), all on the device.
 
-        z-score inside the mask, MLP x 1e6 on masked voxels, 400.0 (air) elsewhere.  The
-        reference builds the mask with scipy morphology on the CPU (``src/utils.py:12-21``,
-        out of the hot path); pass it as ``mask``, or the plain ``volume > threshold`` is used.
+        ``create_brain_mask`` (threshold + 2 dilations + 2 erosions) -> ``zscore_normalize`` inside the mask ->
+        MLP x 1e6 on masked voxels -> 400.0 (air) elsewhere.  Pass ``mask`` to supply your own.
         """
+        from .utils import create_brain_mask, zscore_normalize
         if mask is None:
-            mask = volume > threshold
-        vol = volume.float()
-        inside = vol[mask > 0]
-        vol_norm = (vol - inside.mean()) / (inside.std() + 1e-8)
+            mask = create_brain_mask(volume, threshold)
+        vol_norm = zscore_normalize(volume, mask)
         with torch.no_grad():
             return model.impedance_volume(vol_norm, mask, out_scale=1e6, fill=400.0).to(volume.dtype)

@@ -196,6 +196,17 @@ int32_t diffus_splat_backward(const float* c0, const float* c1, const float* c2,
                               float* grad_intensities, void* workspace, int64_t workspace_bytes,
                               void* stream);
 
+/* MRI preprocessing in front of the MLP (src/utils.py:12-39, called from compute_impedance_volume,
+ * src/impedance.py:46-47).  diffus_brain_mask: create_brain_mask = (volume > threshold), `iterations`
+ * binary dilations then `iterations` binary erosions (scipy defaults: 6-neighbour cross, border value 0;
+ * the reference uses 2); mask and scratch hold D*H*W bytes each.  diffus_masked_zscore:
+ * zscore_normalize = (volume - mean) / (std + 1e-8), mean and unbiased std over voxels with mask != 0;
+ * workspace >= 64 bytes. */
+int32_t diffus_brain_mask(const float* volume, const int32_t dim[3], float threshold, int32_t iterations,
+                          uint8_t* mask, uint8_t* scratch, void* stream);
+int32_t diffus_masked_zscore(const float* volume, const uint8_t* mask, int64_t n, float* out,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* LINEAR (D,H,W) -> BRICK copy of a volume (and back, for gradients). dst holds
  * diffus_brick_elems(dim) floats. */
 int64_t diffus_brick_elems(const int32_t dim[3]);

@@ -224,12 +224,34 @@ def splat_cases(ref):
     np.savez_compressed(os.path.join(OUT, "splat.npz"), **out)
 
 
+def impedance_volume_cases(ref):
+    I, U = ref.impedance, ref.utils
+    sys.path.insert(0, ROOT)
+    from diffus_b200.phantoms import mri_phantom
+    out = {}
+    vol = mri_phantom(24, "t1", seed=3)
+    vol[2:4, 2:4, 2:4] = 900.0            # an isolated speck: closed by dilation/erosion or not, as scipy decides
+    vol[0, 10:14, 10:14] = 900.0          # touches the border (erosion's border_value=0 matters)
+    torch.manual_seed(0)
+    model = I.ImpedanceEstimator(1)
+    for k, v in model.state_dict().items():
+        out["param_" + k.replace(".", "_")] = _np(v)
+    mask = U.create_brain_mask(vol.numpy(), 50)
+    out["volume"], out["mask"] = _np(vol), _np(mask)
+    out["vol_norm"] = _np(U.zscore_normalize(vol, mask))
+    out["Z"] = _np(I.ImpedanceEstimator.compute_impedance_volume(vol, model, threshold=50))
+    np.savez_compressed(os.path.join(OUT, "impedance_volume.npz"), **out)
+
+
 def main():
     ref = RL.load()
     if ref is None:
         raise SystemExit("reference tree not found at " + RL.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    for fn in (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases):
+    only = sys.argv[1:]
+    for fn in (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases, impedance_volume_cases):
+        if only and fn.__name__ not in only:
+            continue
         fn(ref)
         print("wrote", fn.__name__)
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:

@@ -264,6 +264,51 @@ def mlp_forward(x, w1, b1, w2, b2, w3, b3):
 
 
 # ----------------------------------------------------------------------------------------
+# MRI preprocessing  (src/utils.py:12-39, src/impedance.py:39-54)  -- SURVEY row f4
+# ----------------------------------------------------------------------------------------
+
+
+def create_brain_mask(volume: torch.Tensor, threshold=50, iterations: int = 2) -> torch.Tensor:
+    """``volume > threshold`` then 2 binary dilations and 2 erosions (``src/utils.py:12-21``).
+
+    scipy's defaults restated with shifts: the structuring element is the 6-neighbour cross and everything
+    outside the volume counts as 0 (so erosion eats one layer per pass at the border).
+    """
+    import torch.nn.functional as F
+    m = volume > threshold
+
+    def neighbours(x):
+        p = F.pad(x, (1, 1, 1, 1, 1, 1), value=False)
+        return [p[2:, 1:-1, 1:-1], p[:-2, 1:-1, 1:-1], p[1:-1, 2:, 1:-1], p[1:-1, :-2, 1:-1], p[1:-1, 1:-1, 2:], p[1:-1, 1:-1, :-2]]
+
+    for _ in range(iterations):
+        for nb in neighbours(m):
+            m = m | nb
+    for _ in range(iterations):
+        nbs = neighbours(m)
+        for nb in nbs:
+            m = m & nb
+    return m
+
+
+def zscore_normalize(volume: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """``(volume - mean) / (std + 1e-8)`` over the masked voxels, unbiased std (``src/utils.py:23-39``)."""
+    volume = volume.float()
+    inside = volume[mask > 0]
+    return (volume - inside.mean()) / (inside.std() + 1e-8)
+
+
+def compute_impedance_volume(volume, params, threshold=50):
+    """``ImpedanceEstimator.compute_impedance_volume`` (``src/impedance.py:39-54``): MLP x 1e6 inside the mask, 400 outside."""
+    mask = create_brain_mask(volume, threshold)
+    vn = zscore_normalize(volume, mask)
+    z = mlp_forward(vn[mask].unsqueeze(1), *params).squeeze() * 1e6
+    out = torch.full_like(volume, 400.0)
+    out[mask] = z
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # scan conversion  (src/renderer.py:694-737)  -- SURVEY row f1
 # ----------------------------------------------------------------------------------------
 

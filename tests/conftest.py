@@ -54,6 +54,11 @@ def golden_mlp():
 
 
 @pytest.fixture(scope="session")
+def golden_impvol():
+    return load_golden("impedance_volume.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_splat():
     return load_golden("splat.npz")
 

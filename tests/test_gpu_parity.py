@@ -484,6 +484,25 @@ def test_splat_golden_and_gradient(golden_splat):
     np.testing.assert_allclose(img.cpu().numpy(), ref_img.numpy(), rtol=2e-5, atol=2e-6)
 
 
+def test_compute_impedance_volume_golden(golden_impvol):
+    """Row f4: create_brain_mask + zscore_normalize + MLP x 1e6, against the reference's scipy/torch CPU pipeline."""
+    from diffus_b200 import ImpedanceEstimator
+    from diffus_b200.utils import create_brain_mask, zscore_normalize
+    g = golden_impvol
+    vol = torch.tensor(g["volume"], device=dev())
+    mask = create_brain_mask(vol, 50)
+    assert mask.dtype == torch.bool
+    np.testing.assert_array_equal(mask.cpu().numpy(), g["mask"])
+    vn = zscore_normalize(vol, mask)
+    np.testing.assert_allclose(vn.cpu().numpy(), g["vol_norm"], rtol=2e-5, atol=2e-6)
+    model = ImpedanceEstimator(1)
+    model.load_state_dict({k[len("param_"):].replace("model_", "model.").replace("_weight", ".weight").replace("_bias", ".bias"):
+                           torch.tensor(v) for k, v in g.items() if k.startswith("param_")})
+    Z = ImpedanceEstimator.compute_impedance_volume(vol, model.to(dev()), threshold=50)
+    np.testing.assert_allclose(Z.cpu().numpy(), g["Z"], rtol=5e-5, atol=5.0)
+    assert (Z[~mask] == 400.0).all()
+
+
 def test_full_size_properties_config1():
     """BASELINE config 1 at full size (256^3, 128 x 512): properties that need no oracle run."""
     from diffus_b200 import UltrasoundRenderer, PreparedVolume, render_frames

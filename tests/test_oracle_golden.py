@@ -134,3 +134,14 @@ def test_closed_form_equals_dense_on_layered_medium():
     (ga,) = torch.autograd.grad((a * w).sum(), r, retain_graph=True)
     (gb,) = torch.autograd.grad((b * w).sum(), r)
     np.testing.assert_allclose(ga.numpy(), gb.numpy(), rtol=0, atol=1e-11)
+
+
+def test_preprocessing_and_impedance_volume(golden_impvol):
+    g = golden_impvol
+    vol = torch.tensor(g["volume"])
+    mask = port.create_brain_mask(vol, 50)
+    np.testing.assert_array_equal(mask.numpy(), g["mask"])
+    np.testing.assert_allclose(port.zscore_normalize(vol, mask).numpy(), g["vol_norm"], rtol=1e-6, atol=1e-7)
+    params = [torch.tensor(g[k]) for k in ("param_model_0_weight", "param_model_0_bias", "param_model_2_weight",
+                                           "param_model_2_bias", "param_model_4_weight", "param_model_4_bias")]
+    np.testing.assert_allclose(port.compute_impedance_volume(vol, params).numpy(), g["Z"], rtol=1e-5, atol=1.0)
