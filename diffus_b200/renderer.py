@@ -263,6 +263,29 @@ def compute_echo_traces(refLR: torch.Tensor, spacing: float = 1.0, c: float = 1.
     return echo, delays_us
 
 
+def gaussian_pulse(length: int, sigma: float):
+    """1-D Gaussian pulse normalised to peak 1 (reference ``src/renderer.py:481-496``); host numpy, like the reference."""
+    import numpy as np
+    t = np.linspace(-length // 2, length // 2, length)
+    pulse = np.exp(-0.5 * (t / sigma) ** 2)
+    return pulse / pulse.max()
+
+
+def compute_gaussian_pulse(refLR: torch.Tensor, spacing: float = 1.0, c: float = 1.54e3, length: int = 10, sigma: int = 1,
+                           pulse=None) -> torch.Tensor:
+    """Echo traces convolved with a Gaussian pulse (reference ``src/renderer.py:459-479``).
+
+    Off the hot path (the call is commented out on HEAD, ``:250``): the echo line comes from the scan kernel, the
+    short 1-D convolution is a library ``conv1d`` on the same device.
+    """
+    import torch.nn.functional as F
+    echo_signals, _ = compute_echo_traces(refLR, spacing, c)
+    if pulse is None:
+        pulse = gaussian_pulse(length=length, sigma=sigma)
+        pulse = torch.tensor(pulse, dtype=echo_signals.dtype, device=echo_signals.device).unsqueeze(0).unsqueeze(0)
+    return F.conv1d(echo_signals.unsqueeze(1), pulse, padding=length // 2).squeeze(1)
+
+
 def propagate_full_rays_batched(refLR: torch.Tensor) -> torch.Tensor:
     """Cumulative surface return per truncation depth (reference ``src/renderer.py:412-436``)."""
     echo, _ = compute_echo_traces(refLR)

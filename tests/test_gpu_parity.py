@@ -503,6 +503,19 @@ def test_compute_impedance_volume_golden(golden_impvol):
     assert (Z[~mask] == 400.0).all()
 
 
+def test_compute_gaussian_pulse_vs_oracle():
+    from diffus_b200 import compute_gaussian_pulse, gaussian_pulse
+    from oracle import port
+    g = torch.Generator().manual_seed(3)
+    r = 0.01 * torch.randn((4, 60), generator=g)
+    got = compute_gaussian_pulse(r.to(dev()), length=20, sigma=4)
+    echo = port.echo_closed_form(r.double())
+    pulse = torch.tensor(gaussian_pulse(20, 4), dtype=torch.float64)[None, None]
+    want = torch.nn.functional.conv1d(echo.unsqueeze(1), pulse, padding=10).squeeze(1)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
+
+
 def test_full_size_properties_config1():
     """BASELINE config 1 at full size (256^3, 128 x 512): properties that need no oracle run."""
     from diffus_b200 import UltrasoundRenderer, PreparedVolume, render_frames

@@ -82,3 +82,9 @@ def test_rotate_around_apex_live(ref):
     got = rotate_around_apex(x.reshape(-1), z.reshape(-1), (120.0, 4.0), (0.3, -0.9))
     np.testing.assert_allclose(got[0].numpy(), want[0].numpy(), rtol=1e-6, atol=1e-4)
     np.testing.assert_allclose(got[1].numpy(), want[1].numpy(), rtol=1e-6, atol=1e-4)
+
+
+def test_gaussian_pulse_live(ref):
+    from diffus_b200 import gaussian_pulse
+    for length, sigma in ((10, 1), (20, 4), (7, 2.5)):
+        np.testing.assert_array_equal(gaussian_pulse(length, sigma), ref.renderer.gaussian_pulse(length, sigma))
