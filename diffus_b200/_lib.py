@@ -72,6 +72,7 @@ SIGNATURES = {
     "diffus_render_backward": (_i32, [_P(DiffusRenderBwdArgs), _vp]),
     "diffus_ray_indices": (_i32, [_P(DiffusRenderArgs), _vp, _vp, _vp, _vp]),
     "diffus_trace_values": (_i32, [_P(DiffusRenderArgs), _vp, _vp]),
+    "diffus_sample_points": (_i32, [_P(DiffusVolume), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "diffus_trace_values_backward": (_i32, [_P(DiffusRenderArgs), _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "diffus_echo_forward": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "diffus_echo_backward": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),

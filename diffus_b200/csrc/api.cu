@@ -238,6 +238,20 @@ int32_t diffus_trace_values(const DiffusRenderArgs* a, float* out, void* stream)
                                        (cudaStream_t)stream));
 }
 
+int32_t diffus_sample_points(const DiffusVolume* volume, const float* points, int64_t n, int32_t sampler, float* values,
+                             int64_t* x, int64_t* y, int64_t* z, void* stream) {
+    if (!volume || !points || !values) return DIFFUS_E_NULL;
+    int32_t e = check_volume(*volume);
+    if (e) return e;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    if (sampler != DIFFUS_SAMPLER_NEAREST && sampler != DIFFUS_SAMPLER_TRILINEAR) return DIFFUS_E_ENUM;
+    if ((x || y || z) && !(x && y && z)) return DIFFUS_E_NULL;
+    DiffusRenderArgs a{};
+    a.volume = *volume;
+    RenderParams p = pack(&a);
+    return cuda_rc(launch_sample_points(p, sampler, volume->layout, points, n, values, x, y, z, (cudaStream_t)stream));
+}
+
 int32_t diffus_trace_values_backward(const DiffusRenderArgs* a, const float* grad_values, float* grad_volume,
                                      float* grad_sources, float* grad_directions, void* workspace,
                                      int64_t workspace_bytes, void* stream) {

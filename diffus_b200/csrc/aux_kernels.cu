@@ -167,6 +167,32 @@ cudaError_t launch_trace_values(const RenderParams& p, int sampler, int layout, 
     return cudaErrorInvalidValue;
 }
 
+// custom_nearest_sampler on explicit points (reference src/renderer.py:741-819): points (n,3) in voxel
+// coordinates -> clamped nearest-voxel indices and the sampled values (nearest or trilinear).
+template <int SAMPLER, int LAYOUT>
+__global__ void sample_points_kernel(const VolumeView vol, const float* __restrict__ pts, int64_t n, float* __restrict__ val,
+                                     int64_t* __restrict__ x, int64_t* __restrict__ y, int64_t* __restrict__ z) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        float p0 = pts[t * 3], p1 = pts[t * 3 + 1], p2 = pts[t * 3 + 2];
+        if (x) {
+            x[t] = nearest_index(p0, vol.D);
+            y[t] = nearest_index(p1, vol.H);
+            z[t] = nearest_index(p2, vol.W);
+        }
+        float g[3];
+        val[t] = sample_volume<SAMPLER, LAYOUT, false>(vol, p0, p1, p2, g);
+    }
+}
+
+cudaError_t launch_sample_points(const RenderParams& p, int sampler, int layout, const float* pts, int64_t n, float* val,
+                                 int64_t* x, int64_t* y, int64_t* z, cudaStream_t st) {
+    unsigned grid = (unsigned)max((int64_t)1, min((int64_t)148 * 16, (n + 255) / 256));
+    const int pose64 = 0;
+    DIFFUS_DISPATCH(sample_points_kernel<S_, L_><<<grid, 256, 0, st>>>(p.vol, pts, n, val, x, y, z); (void)P64_;
+                    return cudaGetLastError())
+    return cudaErrorInvalidValue;
+}
+
 // Backward of trace_values (what autograd does through the reference's sampler): the gradient of every
 // sampled impedance is scattered into the volume (same layout as the gathers) and, for the trilinear
 // sampler, contracted with the spatial gradient into per-ray pose partials.  One warp per ray.

@@ -42,6 +42,8 @@ cudaError_t launch_median_backward(const RenderParams& p, int sampler, int layou
                                    const int32_t* argmedian, bool pose_grad, bool vol_grad, cudaStream_t st);
 cudaError_t launch_ray_indices(const RenderParams& p, int pose64, int64_t* x, int64_t* y, int64_t* z, cudaStream_t st);
 cudaError_t launch_trace_values(const RenderParams& p, int sampler, int layout, int pose64, float* out, cudaStream_t st);
+cudaError_t launch_sample_points(const RenderParams& p, int sampler, int layout, const float* pts, int64_t n, float* val,
+                                 int64_t* x, int64_t* y, int64_t* z, cudaStream_t st);
 cudaError_t launch_trace_values_bwd(const RenderParams& p, int sampler, int layout, int pose64, const float* gval,
                                     bool pose_grad, bool vol_grad, cudaStream_t st);
 cudaError_t launch_reduce_rays(const float* partial, int64_t n_poses, int64_t n_rays, float* out, cudaStream_t st);

@@ -38,8 +38,9 @@ class ImpedanceEstimator(nn.Module):
             return out.reshape(x.shape)
         if x.is_cuda:
             raise NotImplementedError("the fused MLP kernels cover input_dim == 1 float32 (every use in the reference)")
-        # CPU tensors: parameter bookkeeping only (state-dict round trips, tiny supervised fits)
-        return self.model(x)
+        from ._lib import DiffusError
+        raise DiffusError("ImpedanceEstimator runs only on CUDA tensors (sm_100a kernels); there is no CPU fallback -- "
+                          "move the model and its inputs to the GPU")
 
     def impedance_volume(self, volume: torch.Tensor, mask: torch.Tensor = None, out_scale: float = 1.0,
                          fill: float = 0.0) -> torch.Tensor:

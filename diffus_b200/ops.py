@@ -394,6 +394,28 @@ def trace_values(volume, bricks, dims, sources, directions, n_samples, sampler, 
     return out
 
 
+def sample_points(volume: torch.Tensor, points: torch.Tensor, sampler: int):
+    """Values and clamped nearest indices at explicit points (..., 3); volume (D,H,W) float32 CUDA."""
+    dev = _require_cuda(volume, points)
+    lib = _lib.load()
+    v = volume.detach().float().contiguous()
+    pts = points.detach().float().reshape(-1, 3).contiguous()
+    n = pts.shape[0]
+    vol = _lib.DiffusVolume()
+    vol.data = v.data_ptr()
+    vol.dim[0], vol.dim[1], vol.dim[2] = v.shape
+    vol.layout = LAYOUT_LINEAR
+    with torch.cuda.device(dev):
+        val = torch.empty((n,), dtype=torch.float32, device=dev)
+        idx = torch.empty((3, n), dtype=torch.int64, device=dev)
+        if n:
+            _lib.check(lib.diffus_sample_points(C.byref(vol), pts.data_ptr(), n, sampler, val.data_ptr(), idx[0].data_ptr(),
+                                                idx[1].data_ptr(), idx[2].data_ptr(), _stream(dev)), "diffus_sample_points")
+            _count(1)
+    shape = points.shape[:-1]
+    return idx[0].reshape(shape), idx[1].reshape(shape), idx[2].reshape(shape), val.reshape(shape)
+
+
 def trace_values_bwd(grad_values, volume, bricks, dims, sources, directions, n_samples, sampler, product_f32,
                      need_volume, need_pose):
     dev = _require_cuda(grad_values, volume, bricks, sources, directions)

@@ -322,17 +322,13 @@ def rotate_around_apex(x, z, apex, median):
 
 def custom_nearest_sampler(Z: torch.Tensor, points: torch.Tensor, visualize: bool = False, sampler: str = "prop",
                            start: int = 100):
-    """Nearest-voxel lookup at explicit points (reference ``src/renderer.py:741-819``).
+    """Volume lookup at explicit points (reference ``src/renderer.py:741-819``).
 
-    ``points`` (B, S, 3) in voxel coordinates -> ``x, y, z`` int64 (B, S) and values (B, S).
-    This is the explicit-points entry of the reference; the renderer never materialises
-    ``points`` (ray setup is fused into the march kernel), so this helper is plain index
-    arithmetic on the caller's device.  ``visualize`` is ignored (no matplotlib here).
+    ``points`` (B, S, 3) in voxel coordinates -> ``x, y, z`` int64 (B, S) clamped nearest indices and values (B, S).
+    ``sampler='prop'`` (the reference's default) is the nearest lookup; ``'trilinear'`` the notebook-era one.
+    ``visualize`` and ``start`` only drove the reference's matplotlib debug plot and are ignored.  The renderer
+    itself never materialises ``points`` (ray setup is fused into the march kernels).
     """
-    D, H, W = Z.shape
-    pts = points.float()
-    B, S, _ = pts.shape
-    x = torch.clamp(pts[..., 0].round().long(), 0, D - 1)
-    y = torch.clamp(pts[..., 1].round().long(), 0, H - 1)
-    z = torch.clamp(pts[..., 2].round().long(), 0, W - 1)
-    return x, y, z, Z[x, y, z]
+    if points.dim() != 3 or points.shape[-1] != 3:
+        raise ValueError("points must be (batch, samples, 3)")
+    return ops.sample_points(Z, points, _sampler_id(sampler))

@@ -133,7 +133,11 @@ int32_t diffus_ray_indices(const DiffusRenderArgs* args, int64_t* x, int64_t* y,
 /* Sampled impedances along the rays, no propagation: the `values` output of
  * UltrasoundRenderer.trace_ray (src/renderer.py:89-180).  out is (P,R,S) (start ignored). */
 int32_t diffus_trace_values(const DiffusRenderArgs* args, float* out, void* stream);
-/* Its backward (autograd through the reference's sampler, src/renderer.py:758 / grid_sample): grad_values
+/* custom_nearest_sampler on explicit points (src/renderer.py:741-819): points (n,3) float32 voxel coordinates
+ * -> values (n) and, if x, y, z are given, the clamped nearest-voxel indices (n each, int64). */
+int32_t diffus_sample_points(const DiffusVolume* volume, const float* points, int64_t n, int32_t sampler,
+                             float* values, int64_t* x, int64_t* y, int64_t* z, void* stream);
+/* Backward of diffus_trace_values (autograd through the reference's sampler, src/renderer.py:758 / grid_sample): grad_values
  * (P,R,S) -> grad_volume (layout of args->volume, ACCUMULATED), and for the trilinear sampler grad_sources
  * (P,3) + grad_directions (P,R,3) (both or neither).  workspace: P*R*12 bytes (256-aligned) for pose gradients. */
 int32_t diffus_trace_values_backward(const DiffusRenderArgs* args, const float* grad_values,

@@ -516,6 +516,31 @@ def test_compute_gaussian_pulse_vs_oracle():
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
 
 
+def test_custom_nearest_sampler_explicit_points():
+    from diffus_b200 import custom_nearest_sampler
+    from oracle import port
+    g = torch.Generator().manual_seed(8)
+    vol = torch.rand((9, 7, 11), generator=g)
+    pts = torch.rand((4, 13, 3), generator=g) * torch.tensor([12.0, 10.0, 14.0]) - 2.0
+    pts[0, 0] = torch.tensor([2.5, 3.5, 4.5])                     # round-half-even ties
+    x, y, z, v = custom_nearest_sampler(vol.to(dev()), pts.to(dev()))
+    xo, yo, zo, vo = port.sample_nearest(vol, pts)
+    assert torch.equal(x.cpu(), xo) and torch.equal(y.cpu(), yo) and torch.equal(z.cpu(), zo)
+    assert torch.equal(v.cpu(), vo)
+    _, _, _, vt = custom_nearest_sampler(vol.to(dev()), pts.to(dev()), sampler="trilinear")
+    np.testing.assert_allclose(vt.cpu().numpy(), port.sample_trilinear(vol.double(), pts.double())[3].numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_train_model_runs_on_the_gpu():
+    """ImpedanceEstimator.train_model (reference src/impedance.py:19-37) on a tissue table, through the MLP kernels."""
+    from diffus_b200 import ImpedanceEstimator
+    X = torch.tensor([[-1.2], [-0.3], [0.4], [1.5]], device=dev())
+    y = torch.tensor([[1.38], [1.52], [1.60], [1.68]], device=dev())
+    torch.manual_seed(0)
+    model = ImpedanceEstimator.train_model(X, y, epochs=300, lr=1e-2)
+    assert torch.nn.functional.mse_loss(model(X), y).item() < 1e-3
+
+
 def test_full_size_properties_config1():
     """BASELINE config 1 at full size (256^3, 128 x 512): properties that need no oracle run."""
     from diffus_b200 import UltrasoundRenderer, PreparedVolume, render_frames
