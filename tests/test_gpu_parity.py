@@ -295,6 +295,62 @@ def test_edge_shapes_vs_oracle(dims, R, S, start, sampler):
         assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d/ddirections", rtol=2e-4)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_configurations_vs_oracle(seed):
+    """Seeded sweep over shapes, samplers, layouts, crops, pose dtypes and shared/own fans: frames, loss and every
+    gradient against the fp64 oracle, through the fused and the unfused autograd paths."""
+    import random
+    from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
+    rnd = random.Random(seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    dims = (rnd.randint(3, 40), rnd.randint(3, 40), rnd.randint(3, 40))
+    P, R = rnd.randint(1, 4), rnd.randint(2, 9)
+    S = rnd.choice([2, 3, 17, 32, 33, 64, 100, 255, 256, 257, 511, 512, 513, 700, 1024, 1100])
+    start = rnd.choice([0, 0, 0, 1, S // 3, max(S - 2, 0)]) if S > 3 else 0
+    sampler = rnd.choice(["nearest", "trilinear"])
+    prepared = rnd.random() < 0.5
+    shared = rnd.random() < 0.3
+    pose64 = rnd.random() < 0.25
+    alpha = rnd.choice([0.0, 1e-4, 1e-2, 0.5])
+    base = 1.4e6 + 2e5 * torch.rand((max(dims[0] // 5, 1), max(dims[1] // 5, 1), max(dims[2] // 5, 1)), generator=g)
+    vol = torch.nn.functional.interpolate(base[None, None], size=dims, mode="nearest")[0, 0].contiguous()
+    vol = vol * (1 + 0.003 * torch.randn(dims, generator=g))
+    centre = torch.tensor([d / 2.0 for d in dims])
+    src = centre + (torch.rand((P, 3), generator=g) - 0.5) * torch.tensor(dims, dtype=torch.float32) * 1.2
+    d = torch.randn((R, 3) if shared else (P, R, 3), generator=g)
+    d = d / d.norm(dim=-1, keepdim=True) * min(1.0, 1.5 * max(dims) / S)        # keep long rays near the volume
+    pdt = torch.float64 if pose64 else torch.float32
+    v64 = vol.double().requires_grad_(True)
+    s64 = src.to(pdt).double().requires_grad_(True)
+    d64 = d.to(pdt).double().requires_grad_(True)
+    f64 = _oracle_frames(v64, s64, d64, S, alpha, start, sampler)
+    tgt = (f64.detach() * 0.5).float()
+    l64 = (f64 - tgt.double()).square().mean()
+    want = torch.autograd.grad(l64, [v64, s64, d64], allow_unused=True)
+    what = f"seed {seed}: dims={dims} P={P} R={R} S={S} start={start} {sampler} prepared={prepared} shared={shared} pose64={pose64}"
+    for fused in (True, False):
+        v = vol.to(dev()).requires_grad_(True)
+        s = src.to(pdt).to(dev()).requires_grad_(True)
+        dd = d.to(pdt).to(dev()).requires_grad_(True)
+        vv = PreparedVolume(v) if prepared else v
+        if fused:
+            loss, f = render_mse_loss(vv, s, dd, tgt.to(dev()), S, alpha, start, sampler=sampler, return_frame=True)
+        else:
+            f = render_frames(vv, s, dd, S, alpha, start, sampler=sampler)
+            loss = torch.nn.functional.mse_loss(f, tgt.to(dev()))
+        loss.backward()
+        assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), what)
+        np.testing.assert_allclose(loss.item(), l64.item(), rtol=2e-4, atol=1e-12, err_msg=what)
+        if want[0].abs().max() > 0:
+            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), what + " d/dvolume", rtol=3e-4)
+        if sampler == "trilinear":
+            if want[1].abs().max() > 0:
+                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), what + " d/dsources", rtol=3e-4)
+                assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), what + " d/ddirections", rtol=3e-4)
+        else:
+            assert s.grad is None and dd.grad is None
+
+
 def test_shared_directions_and_float64_pose():
     from diffus_b200 import render_frames
     from diffus_b200.phantoms import layered_phantom
