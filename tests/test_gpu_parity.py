@@ -630,6 +630,63 @@ def test_full_size_properties_config1():
     assert -0.09 < f.min().item() < -0.07 and 0.06 < f.max().item() < 0.075
 
 
+def test_full_size_pose_sweep_properties_config3():
+    """BASELINE config 3 at full size (1024 poses x 128 x 512 on 256^3): oracle-free checks of the batched fused path."""
+    from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
+    from diffus_b200.phantoms import intensity_to_impedance, mri_phantom, pose_sweep
+    vol = intensity_to_impedance(mri_phantom(256, "t1", seed=0)).to(dev())
+    src, dirs = pose_sweep(1024, 128, 256, seed=5)
+    src, dirs = src.to(dev()), dirs.to(dev())
+    pv = PreparedVolume(vol)
+    frames = render_frames(pv, src, dirs, 512, 1e-4, sampler="trilinear")
+    assert frames.shape == (1024, 128, 512) and torch.isfinite(frames).all()
+    # poses are independent: any pose rendered alone gives the same frame, in either layout
+    for p in (0, 17, 900, 1023):
+        assert torch.equal(render_frames(pv, src[p:p + 1], dirs[p:p + 1], 512, 1e-4, sampler="trilinear")[0], frames[p])
+        assert torch.equal(render_frames(vol, src[p:p + 1], dirs[p:p + 1], 512, 1e-4, sampler="trilinear")[0], frames[p])
+    # fused step: loss equals the unfused loss; zero loss and zero gradients at the target
+    with torch.no_grad():
+        target = render_frames(pv, src + torch.tensor([1.5, 0.0, -1.0], device=dev()), dirs, 512, 1e-4, sampler="trilinear")
+    s = src.clone().requires_grad_(True)
+    d = dirs.clone().requires_grad_(True)
+    loss = render_mse_loss(pv, s, d, target, 512, 1e-4)
+    loss.backward()
+    ref_loss = torch.nn.functional.mse_loss(frames, target)
+    np.testing.assert_allclose(loss.item(), ref_loss.item(), rtol=1e-4)
+    assert torch.isfinite(s.grad).all() and torch.isfinite(d.grad).all()
+    l0 = render_mse_loss(pv, src, dirs, frames, 512, 1e-4)
+    assert l0.item() < 1e-12
+    # directional derivative along the gradient (sum over poses) vs a central finite difference of the loss
+    gs = s.grad / s.grad.norm()
+    eps = 2e-2
+    lp = render_mse_loss(pv, src + eps * gs, dirs, target, 512, 1e-4).item()
+    lm = render_mse_loss(pv, src - eps * gs, dirs, target, 512, 1e-4).item()
+    fd, an = (lp - lm) / (2 * eps), (s.grad * gs).sum().item()
+    assert abs(fd - an) <= 0.1 * abs(an) + 1e-12, (fd, an)
+
+
+def test_full_size_stress_geometry_config5():
+    """BASELINE config 5 geometry (512^3 volume, 512 rays x 2048 samples: four 512-column passes), a few poses."""
+    from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
+    from diffus_b200.phantoms import layered_phantom, pose_sweep
+    vol = layered_phantom(512, seed=0).to(dev())
+    src, dirs = pose_sweep(6, 512, 512, seed=2)
+    src, dirs = src.to(dev()), dirs.to(dev())
+    pv = PreparedVolume(vol)
+    f = render_frames(pv, src, dirs, 2048, 1e-4, sampler="trilinear")
+    assert f.shape == (6, 512, 2048) and torch.isfinite(f).all()
+    assert torch.equal(render_frames(vol, src[2:3], dirs[2:3, 100:140], 2048, 1e-4, sampler="trilinear")[0], f[2, 100:140])
+    # truncation invariance across pass boundaries: a 1300-sample render equals the first 1300 columns
+    assert torch.equal(render_frames(pv, src, dirs, 1300, 1e-4, sampler="trilinear"), f[:, :, :1300])
+    target = f * 0.9
+    s = src.clone().requires_grad_(True)
+    loss, fr = render_mse_loss(pv, s, dirs, target, 2048, 1e-4, return_frame=True)
+    loss.backward()
+    torch.testing.assert_close(fr, f, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(loss.item(), torch.nn.functional.mse_loss(f, target).item(), rtol=1e-4)
+    assert torch.isfinite(s.grad).all() and s.grad.abs().max() > 0
+
+
 def test_no_cpu_fallback():
     from diffus_b200 import render_frames
     from diffus_b200._lib import DiffusError
