@@ -292,8 +292,18 @@ def cpu_scene(n_rays):
     return vol, s, d, target.float()
 
 
+def bounded_cpu_rays(n_rays):
+    """The dense per-depth solves keep ~2 GB of autograd state per ray at 512 samples: stay under a quarter of free RAM."""
+    try:
+        import psutil
+        return max(1, min(n_rays, int(psutil.virtual_memory().available / 2**30 / 4 / 2)))
+    except Exception:
+        return min(n_rays, 4)
+
+
 def cpu_baseline(n_rays):
     """Reference algorithm (oracle port: one dense solve per depth + torch autograd) on a bounded sample."""
+    n_rays = bounded_cpu_rays(n_rays)
     vol, s, d, target = cpu_scene(n_rays)
     t = time.perf_counter()
     cpu_sample_step(vol, s, d, target)
@@ -321,6 +331,7 @@ def run_reference(args):
         sys.stdout.flush()
         return
     K, W = args.steps, args.warmup
+    args.cpu_rays = bounded_cpu_rays(args.cpu_rays)
     vol, s, d, target = cpu_scene(args.cpu_rays)
     for _ in range(min(W, 1)):
         cpu_sample_step(vol, s, d, target)
