@@ -75,13 +75,21 @@ template <class G_, int LOSS>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
                                              float& loss_acc, int lane, const float* z_lane = nullptr,
-                                             unsigned skip_mask = 0u, float* rbar1 = nullptr) {
+                                             unsigned skip_mask = 0u, float* rbar1 = nullptr,
+                                             const M2* known_total = nullptr, const M2* known_prefix = nullptr) {
     constexpr int CHUNK = G_::CHUNK;
     const int base = lane * (CHUNK + 1);
-    M2 T = m2_identity();
+    // chunk product and exclusive prefix: reuse them when the caller already ran this sweep (prefix pass)
+    M2 T, P;
+    if (known_total) {
+        T = *known_total;
+        P = *known_prefix;
+    } else {
+        T = m2_identity();
 #pragma unroll
-    for (int i = 0; i < CHUNK; ++i) T = m2_mul_interface(T, r[i]);
-    M2 P = warp_exclusive_prefix(T, carry, lane);
+        for (int i = 0; i < CHUNK; ++i) T = m2_mul_interface(T, r[i]);
+        P = warp_exclusive_prefix(T, carry, lane);
+    }
     M2 Pck[CHUNK / 2];             // true prefix BEFORE column 2j of the chunk (checkpoint every 2 columns)
     M2 G = m2_identity();          // local inclusive prefix
     M2 B = M2{0.f, 0.f, 0.f, 0.f};
@@ -380,18 +388,17 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             carry[0] = M2{c4.x, c4.y, c4.z, c4.w};
         }
         float r[G::CHUNK];
+        M2 T0 = m2_identity(), E0 = m2_identity();       // sub-segment 0's chunk products and prefixes, kept for its reverse scan
+        static_assert(BWD_SUB == 2, "the prefix pass keeps one sub-segment's products in registers");
+        const bool have0 = nsub > 1;
+        if (have0) {
+            chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, 0);
 #pragma unroll
-        for (int h = 0; h + 1 < BWD_SUB; ++h) {
-            if (h + 1 < nsub) {
-                chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, h * G::SEG);
-                M2 T = m2_identity();
-#pragma unroll
-                for (int i = 0; i < G::CHUNK; ++i) T = m2_mul_interface(T, r[i]);
-                M2 E = warp_exclusive_prefix(T, carry[h], lane);
-                carry[h + 1] = m2_shfl(m2_mul(E, T), 31);
-            } else {
-                carry[h + 1] = carry[h];
-            }
+            for (int i = 0; i < G::CHUNK; ++i) T0 = m2_mul_interface(T0, r[i]);
+            E0 = warp_exclusive_prefix(T0, carry[0], lane);
+            carry[1] = m2_shfl(m2_mul(E0, T0), 31);
+        } else {
+            carry[1] = carry[0];
         }
         // reverse scan, last sub-segment first
 #pragma unroll
@@ -406,7 +413,8 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                 vin = backward_chunk<G, LOSS>(r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col),
                                               fout ? fout + c0 + lane_col : nullptr, p.grad_scale, ncol - lane_col,
                                               loss_acc, lane, zbuf + G::pad(lane_col), skip,
-                                              (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr);
+                                              (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr,
+                                              (h == 0 && have0) ? &T0 : nullptr, &E0);
             }
         }
         __syncwarp();
