@@ -145,3 +145,23 @@ def test_preprocessing_and_impedance_volume(golden_impvol):
     params = [torch.tensor(g[k]) for k in ("param_model_0_weight", "param_model_0_bias", "param_model_2_weight",
                                            "param_model_2_bias", "param_model_4_weight", "param_model_4_bias")]
     np.testing.assert_allclose(port.compute_impedance_volume(vol, params).numpy(), g["Z"], rtol=1e-5, atol=1.0)
+
+
+def test_reference_known_answers_for_the_sign_convention():
+    """The only numbers the reference's own notebooks pin for this path.
+
+    notebooks/[DEMO] Intro to the theory behind propagation.ipynb cell 12: propagate_boundary(g=10, d=10, Z1=1, Z2=2)
+    prints r=0.3333, tLR=1.3333, tRL=0.6667 and returns (16.6667, 10.0): r = (Z2-Z1)/(Z1+Z2), tLR = 1+r, tRL = 1-r.
+    """
+    r = port.reflection_coeff(torch.tensor([1.0]), torch.tensor([2.0]))
+    np.testing.assert_allclose([r.item(), (1 + r).item(), (1 - r).item()], [0.3333, 1.3333, 0.6667], atol=5e-5)
+    g = d = torch.tensor([10.0])
+    new_g, new_d = (1 + r) * g + r * d, (1 - r) * d + r * g
+    np.testing.assert_allclose([new_g.item(), new_d.item()], [16.6667, 10.0], atol=5e-5)
+    # the same convention is what the layered system of src/renderer.py:380-405 encodes: one interface, d0 = r
+    np.testing.assert_allclose(port.surface_return_dense(r.reshape(1, 1))[0].numpy(), [0.0, r.item()], atol=1e-7)
+    # forward_physics.md:52-88 works Z=(1,2,1.5) with the PHYSICAL convention and does not pin the code;
+    # the code's own answer for it (measured on the reference, SURVEY appendix B) is echo [0, 0.3333, 0.2121]
+    Z = torch.tensor([[1.0, 2.0, 1.5]], dtype=torch.float64)
+    e = port.echo_closed_form(port.reflection_coeff(Z[:, :-1], Z[:, 1:]))
+    np.testing.assert_allclose(e[0].numpy(), [0.0, 1 / 3, 0.21212121], atol=1e-7)
