@@ -224,6 +224,27 @@ def splat_cases(ref):
     np.savez_compressed(os.path.join(OUT, "splat.npz"), **out)
 
 
+def brain_phantom2d_cases(ref):
+    """generate_brain_phantom_2d of notebooks/[DEMO] Modeling Choices.ipynb cell 5 (air 400, bone 7.8e6: |r| up to 0.9995)."""
+    R = ref.renderer
+    rows, cols = 20, 10
+    brain, tumor, csf, bone, air = 1.60e6, 1.68e6, 1.50e6, 7.80e6, 0.0004e6
+    ph = torch.full((rows, cols), air)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, rows), torch.linspace(-1, 1, cols), indexing="ij")
+    brain_mask = (xx ** 2 / 0.8 ** 2 + yy ** 2 / 0.95 ** 2) <= 1.0
+    ph[brain_mask] = brain
+    csf_mask = (xx ** 2 / 0.88 ** 2 + yy ** 2 / 1.05 ** 2) <= 1.0
+    ph[csf_mask & (~brain_mask)] = csf
+    ph[(abs(xx) < 0.2) & (abs(yy) < 0.3) & brain_mask] = tumor
+    last = torch.where(brain_mask.any(dim=1))[0][-1]
+    ph[last, brain_mask[last]] = bone
+    r = R.UltrasoundRenderer.compute_reflection_coeff(ph[:, 1:], ph[:, :-1])
+    with RL.quiet():
+        e32, _ = R.compute_echo_traces(r)
+        e64, _ = R.compute_echo_traces(r.double())
+    np.savez_compressed(os.path.join(OUT, "echo_brain_phantom2d.npz"), Z=_np(ph), r=_np(r), echo32=_np(e32), echo64=_np(e64))
+
+
 def impedance_volume_cases(ref):
     I, U = ref.impedance, ref.utils
     sys.path.insert(0, ROOT)
@@ -249,7 +270,7 @@ def main():
         raise SystemExit("reference tree not found at " + RL.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
-    for fn in (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases, impedance_volume_cases):
+    for fn in (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases, impedance_volume_cases, brain_phantom2d_cases):
         if only and fn.__name__ not in only:
             continue
         fn(ref)

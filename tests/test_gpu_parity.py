@@ -151,6 +151,10 @@ def test_echo_traces_golden(golden_echo):
         r = torch.tensor(g[f"{name}_r"], device=dev(), dtype=torch.float32)
         echo, _ = compute_echo_traces(r)
         assert_frame_close(echo.cpu().numpy(), g[f"{name}_echo64"], name)
+    from conftest import load_golden
+    b = load_golden("echo_brain_phantom2d.npz")                   # the notebook's air / bone phantom, |r| up to 0.9995
+    echo, _ = compute_echo_traces(torch.tensor(b["r"], device=dev()))
+    assert_frame_close(echo.cpu().numpy(), b["echo64"], "brain phantom 2d")
 
 
 @pytest.mark.parametrize("B,N", [(3, 1), (5, 31), (4, 512), (2, 513), (3, 1200), (2, 2047)])

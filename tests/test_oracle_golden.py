@@ -165,3 +165,14 @@ def test_reference_known_answers_for_the_sign_convention():
     Z = torch.tensor([[1.0, 2.0, 1.5]], dtype=torch.float64)
     e = port.echo_closed_form(port.reflection_coeff(Z[:, :-1], Z[:, 1:]))
     np.testing.assert_allclose(e[0].numpy(), [0.0, 1 / 3, 0.21212121], atol=1e-7)
+
+
+def test_notebook_brain_phantom_2d():
+    """generate_brain_phantom_2d (Modeling Choices cell 5): air / bone interfaces, |r| up to 0.9995."""
+    from conftest import load_golden
+    g = load_golden("echo_brain_phantom2d.npz")
+    ph = torch.tensor(g["Z"])
+    r = port.reflection_coeff(ph[:, 1:], ph[:, :-1])
+    np.testing.assert_array_equal(r.numpy(), g["r"])
+    np.testing.assert_array_equal(port.echo_dense_solve(r).numpy(), g["echo32"])
+    np.testing.assert_allclose(port.echo_closed_form(r.double()).numpy(), g["echo64"], atol=1e-13)
