@@ -143,46 +143,60 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) mlp_bwd_kernel(const float* __
             h1t[lane * TILE_LD + i] = fmaxf(fmaf(w1i, xv, b1i), 0.f);
         }
         __syncwarp();
-        // phase B: lane = unit j of layer 2
-        for (int v = 0; v < 32; ++v) {
-            float gv = gs[warp][v];
-            const float4* row = (const float4*)(h1t + v * TILE_LD);
-            float s = b2;
+        // phase B: lane = unit j of layer 2.  Four voxels per iteration with split accumulators: the dot
+        // products are 32 dependent FMAs each, so without this the FMA pipe idles on its own latency.
+        for (int v = 0; v < 32; v += 4) {
+            float sa[4], sb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { sa[u] = b2; sb[u] = 0.f; }
 #pragma unroll
             for (int i4 = 0; i4 < H / 4; ++i4) {
-                float4 q = row[i4];
-                s = fmaf(w2_row[4 * i4], q.x, s);
-                s = fmaf(w2_row[4 * i4 + 1], q.y, s);
-                s = fmaf(w2_row[4 * i4 + 2], q.z, s);
-                s = fmaf(w2_row[4 * i4 + 3], q.w, s);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float4 q = ((const float4*)(h1t + (v + u) * TILE_LD))[i4];
+                    sa[u] = fmaf(w2_row[4 * i4], q.x, sa[u]);
+                    sb[u] = fmaf(w2_row[4 * i4 + 1], q.y, sb[u]);
+                    sa[u] = fmaf(w2_row[4 * i4 + 2], q.z, sa[u]);
+                    sb[u] = fmaf(w2_row[4 * i4 + 3], q.w, sb[u]);
+                }
             }
-            float h2 = fmaxf(s, 0.f);
-            float dh2 = (s > 0.f) ? gv * w3 : 0.f;
-            g_w3 = fmaf(gv, h2, g_w3);
-            g_b2 += dh2;
-            d2t[v * TILE_LD + lane] = dh2;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float s = sa[u] + sb[u];
+                float gv = gs[warp][v + u];
+                float h2 = fmaxf(s, 0.f);
+                float dh2 = (s > 0.f) ? gv * w3 : 0.f;
+                g_w3 = fmaf(gv, h2, g_w3);
+                g_b2 += dh2;
+                d2t[(v + u) * TILE_LD + lane] = dh2;
+            }
         }
         __syncwarp();
-        // phase C: lane = unit i of layer 1
-        for (int v = 0; v < 32; ++v) {
-            float h1v = h1t[v * TILE_LD + lane];
-            const float4* row = (const float4*)(d2t + v * TILE_LD);
-            float dh1 = 0.f;
+        // phase C: lane = unit i of layer 1 (two voxels per iteration for the same reason)
+        for (int v = 0; v < 32; v += 2) {
+            float h1a = h1t[v * TILE_LD + lane], h1b = h1t[(v + 1) * TILE_LD + lane];
+            const float4* rowa = (const float4*)(d2t + v * TILE_LD);
+            const float4* rowb = (const float4*)(d2t + (v + 1) * TILE_LD);
+            float da0 = 0.f, da1 = 0.f, db0 = 0.f, db1 = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < H / 4; ++j4) {
-                float4 q = row[j4];
-                g_w2[4 * j4] = fmaf(q.x, h1v, g_w2[4 * j4]);
-                g_w2[4 * j4 + 1] = fmaf(q.y, h1v, g_w2[4 * j4 + 1]);
-                g_w2[4 * j4 + 2] = fmaf(q.z, h1v, g_w2[4 * j4 + 2]);
-                g_w2[4 * j4 + 3] = fmaf(q.w, h1v, g_w2[4 * j4 + 3]);
-                dh1 = fmaf(q.x, w2_col[4 * j4], dh1);
-                dh1 = fmaf(q.y, w2_col[4 * j4 + 1], dh1);
-                dh1 = fmaf(q.z, w2_col[4 * j4 + 2], dh1);
-                dh1 = fmaf(q.w, w2_col[4 * j4 + 3], dh1);
+                float4 qa = rowa[j4], qb = rowb[j4];
+                g_w2[4 * j4] = fmaf(qb.x, h1b, fmaf(qa.x, h1a, g_w2[4 * j4]));
+                g_w2[4 * j4 + 1] = fmaf(qb.y, h1b, fmaf(qa.y, h1a, g_w2[4 * j4 + 1]));
+                g_w2[4 * j4 + 2] = fmaf(qb.z, h1b, fmaf(qa.z, h1a, g_w2[4 * j4 + 2]));
+                g_w2[4 * j4 + 3] = fmaf(qb.w, h1b, fmaf(qa.w, h1a, g_w2[4 * j4 + 3]));
+                da0 = fmaf(qa.x, w2_col[4 * j4], da0);
+                da1 = fmaf(qa.y, w2_col[4 * j4 + 1], da1);
+                da0 = fmaf(qa.z, w2_col[4 * j4 + 2], da0);
+                da1 = fmaf(qa.w, w2_col[4 * j4 + 3], da1);
+                db0 = fmaf(qb.x, w2_col[4 * j4], db0);
+                db1 = fmaf(qb.y, w2_col[4 * j4 + 1], db1);
+                db0 = fmaf(qb.z, w2_col[4 * j4 + 2], db0);
+                db1 = fmaf(qb.w, w2_col[4 * j4 + 3], db1);
             }
-            dh1 = (h1v > 0.f) ? dh1 : 0.f;
-            g_b1 += dh1;
-            g_w1 = fmaf(dh1, xs[warp][v], g_w1);
+            float dh1a = (h1a > 0.f) ? da0 + da1 : 0.f, dh1b = (h1b > 0.f) ? db0 + db1 : 0.f;
+            g_b1 += dh1a + dh1b;
+            g_w1 = fmaf(dh1b, xs[warp][v + 1], fmaf(dh1a, xs[warp][v], g_w1));
         }
         __syncwarp();
     }
