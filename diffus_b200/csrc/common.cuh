@@ -11,10 +11,10 @@
 // the echo line equals what the reference obtains from one dense linear solve per
 // truncation depth (src/renderer.py:367-457); see oracle/port.py::echo_closed_form.
 //
-// A warp owns a ray and walks it in segments of SEG = 512 columns: a gather phase with
+// A warp owns a ray and walks it in passes of 512 columns: a gather phase with
 // lane = consecutive sample (coalesced stores, few cache lines per load instruction)
-// parks impedances in shared memory, a chunk phase with lane = 16 consecutive columns does
-// the sequential 2x2 products plus ONE warp-shuffle scan per segment, and a tile phase
+// parks impedances in shared memory, a chunk phase with lane = CH consecutive columns does
+// the sequential 2x2 products plus one warp-shuffle scan per 32*CH columns, and a tile phase
 // writes the result back with lane = consecutive column.
 #pragma once
 #include <cuda_runtime.h>
@@ -29,7 +29,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // Geometry of one warp pass: 32 lanes x CH consecutive columns per lane.  The forward uses
 // CH = 16 (one warp scan per 512 columns); the backward keeps per-column prefixes in
-// registers for its reverse sweep and uses CH = 8 to stay at 5+ CTAs per SM without spills.
+// registers for its reverse sweep and uses CH = 8 to fit 128 registers (4 CTAs per SM) without spills.
 template <int CH>
 struct Geo {
     static constexpr int CHUNK = CH;

@@ -33,15 +33,13 @@ __device__ __forceinline__ M2 warp_exclusive_prefix(const M2& chunk_total, const
 
 // Forward chunk phase for one segment.  `r[i]` must hold the coefficient of column
 // c0 + lane*CH + i (0 for columns that do not exist).  Writes echo (NaN -> 0) to obuf and
-// returns the updated carry (prefix through the last column of the segment); `mid` gets
-// the prefix before the segment's middle column (lane 16's exclusive prefix).
+// returns the updated carry (prefix through the last column of the segment).
 template <class G>
-__device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, float* obuf, int lane, M2& mid) {
+__device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, float* obuf, int lane) {
     M2 T = m2_identity();
 #pragma unroll
     for (int i = 0; i < G::CHUNK; ++i) T = m2_mul_interface(T, r[i]);
     M2 P = warp_exclusive_prefix(T, carry, lane);
-    mid = m2_shfl(P, 16);
 #pragma unroll
     for (int i = 0; i < G::CHUNK; ++i) {
         P = m2_mul_interface(P, r[i]);
@@ -264,8 +262,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
         // chunk phase: lane = 16 consecutive columns
         float r[G::CHUNK];
         chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r);
-        M2 mid;
-        carry = forward_chunk<G>(r, carry, obuf, lane, mid);
+        carry = forward_chunk<G>(r, carry, obuf, lane);
         if (p.seg_prefix && lane == 0 && c0 + G::SEG < p.Sout) store_prefix(p, ray, c0 + G::SEG, carry);
         __syncwarp();
         // tile phase: attenuate and write, lane = consecutive column
@@ -493,8 +490,7 @@ __global__ void __launch_bounds__(128) echo_fwd_kernel(const float* __restrict__
         float r[G::CHUNK];
 #pragma unroll
         for (int i = 0; i < G::CHUNK; ++i) r[i] = rbuf[G::pad(lane * G::CHUNK + i)];
-        M2 mid;
-        carry = forward_chunk<G>(r, carry, obuf, lane, mid);
+        carry = forward_chunk<G>(r, carry, obuf, lane);
         __syncwarp();
         for (int idx = lane; idx < ncol; idx += 32) out[c0 + idx] = obuf[G::pad(idx)];
         __syncwarp();
