@@ -79,11 +79,10 @@ def main():
             ms = timed(lambda: ops.render_mse_impl(vol, None, [256, 256, 256], s1, d1, tgt, 512, 0, 1e-4, 1, False, False,
                                                    True, False), args.iters)
             report("2: same, raw op call (no autograd bookkeeping)", ms, 65536, 1, 36)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = ops.render_mse_impl(vol, None, [256, 256, 256], s1, d1, tgt, 512, 0, 1e-4, 1, False, False, True, False)
-            ms = timed(g.replay, args.iters)
-            report("2: same, captured in a CUDA graph (device time of one pose-recovery step)", ms, 65536, 1, 36)
+            from diffus_b200.graphs import GraphedPoseStep
+            gstep = GraphedPoseStep(vol, tgt, 128, 512, 1e-4)
+            ms = timed(lambda: gstep(s1, d1), args.iters)
+            report("2: same as a GraphedPoseStep (CUDA graph replay incl. copying the new pose in)", ms, 65536, 1, 36)
     if "3f" in want:
         vol = PreparedVolume(intensity_to_impedance(mri_phantom(256, "t1")).to(dev))
         s, d = pose_sweep(1024, 128, 256, seed=1)

@@ -691,6 +691,25 @@ def test_full_size_stress_geometry_config5():
     assert torch.isfinite(s.grad).all() and s.grad.abs().max() > 0
 
 
+def test_graphed_pose_step_matches_eager():
+    from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
+    from diffus_b200.graphs import GraphedPoseStep
+    from diffus_b200.phantoms import layered_phantom, pose_sweep
+    vol = layered_phantom(48, seed=2).to(dev())
+    src, dirs = pose_sweep(3, 16, 48, seed=1)
+    src, dirs = src.to(dev()), dirs.to(dev())
+    with torch.no_grad():
+        target = render_frames(vol, src + 0.8, dirs, 96, 1e-3, sampler="trilinear")
+    step = GraphedPoseStep(PreparedVolume(vol), target, 16, 96, 1e-3)
+    for shift in (0.0, 0.3, -0.5):                       # replay with new poses
+        s = (src + shift).clone().requires_grad_(True)
+        d = dirs.clone().requires_grad_(True)
+        loss = render_mse_loss(PreparedVolume(vol), s, d, target, 96, 1e-3)
+        loss.backward()
+        gl, gs, gd = step(src + shift, dirs)
+        assert torch.equal(gl, loss.detach()) and torch.equal(gs, s.grad) and torch.equal(gd, d.grad)
+
+
 def test_no_cpu_fallback():
     from diffus_b200 import render_frames
     from diffus_b200._lib import DiffusError
