@@ -30,9 +30,10 @@ constexpr unsigned FULL = 0xffffffffu;
 // Geometry of one warp pass: 32 lanes x CH consecutive columns per lane.  The forward uses
 // CH = 16 (one warp scan per 512 columns); the backward keeps per-column prefixes in
 // registers for its reverse sweep and uses CH = 8 to fit 128 registers (4 CTAs per SM) without spills.
-template <int CH>
+template <int CH, int CK = 2>
 struct Geo {
     static constexpr int CHUNK = CH;
+    static constexpr int CKPT = CK;      // backward: columns between saved prefixes
     static constexpr int SEG = 32 * CH;
     // padded shared-memory slot: rows of CH+1 floats make the lane*CH+i pattern conflict free
     __device__ __forceinline__ static int pad(int i) { return i + i / CH; }
@@ -40,7 +41,7 @@ struct Geo {
     static constexpr int OBUF = SEG + SEG / CH + 3;             // slots 0..SEG-1
 };
 using FwdGeo = Geo<16>;
-using BwdGeo = Geo<8>;
+using BwdGeo = Geo<8, 2>;
 // The forward saves its transfer-matrix carry at every PREFIX_STRIDE columns; the backward
 // gathers PREFIX_STRIDE columns at a time and walks them as BWD_SUB sub-segments of BwdGeo::SEG.
 constexpr int PREFIX_STRIDE = FwdGeo::SEG;

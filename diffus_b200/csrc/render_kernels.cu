@@ -88,12 +88,13 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         for (int i = 0; i < CHUNK; ++i) T = m2_mul_interface(T, r[i]);
         P = warp_exclusive_prefix(T, carry, lane);
     }
-    M2 Pck[CHUNK / 2];             // true prefix BEFORE column 2j of the chunk (checkpoint every 2 columns)
+    constexpr int CK = G_::CKPT;   // a checkpoint every CK columns, the prefixes in between are recomputed
+    M2 Pck[CHUNK / CK];            // true prefix BEFORE column CK*j of the chunk
     M2 G = m2_identity();          // local inclusive prefix
     M2 B = M2{0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
-        if ((i & 1) == 0) Pck[i >> 1] = P;
+        if (i % CK == 0) Pck[i / CK] = P;
         P = m2_mul_interface(P, r[i]);
         G = m2_mul_interface(G, r[i]);
         float inv = fast_rcp(P.d);
@@ -134,8 +135,9 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     float z_hi = z_lane ? z_lane[G_::pad(CHUNK)] : 0.f;   // sample of the chunk's last column
 #pragma unroll
     for (int i = CHUNK - 1; i >= 0; --i) {
-        M2 Q = Pck[i >> 1];                            // prefix before column i
-        if (i & 1) Q = m2_mul_interface(Q, r[i - 1]);
+        M2 Q = Pck[i / CK];                            // prefix before column i
+#pragma unroll
+        for (int m = 0; m < i % CK; ++m) Q = m2_mul_interface(Q, r[i - i % CK + m]);
         M2 Pc = m2_mul_interface(Q, r[i]);
         float inv = fast_rcp(Pc.d);
         float e = echo_of(Pc.b, inv);
@@ -386,16 +388,17 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
         }
         float r[G::CHUNK];
         M2 T0 = m2_identity(), E0 = m2_identity();       // sub-segment 0's chunk products and prefixes, kept for its reverse scan
-        static_assert(BWD_SUB == 2, "the prefix pass keeps one sub-segment's products in registers");
-        const bool have0 = nsub > 1;
-        if (have0) {
+        static_assert(BWD_SUB <= 2, "the prefix pass keeps one sub-segment's products in registers");
+        const bool have0 = BWD_SUB == 2 && nsub > 1;
+        if (BWD_SUB == 1) {
+        } else if (have0) {
             chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, 0);
 #pragma unroll
             for (int i = 0; i < G::CHUNK; ++i) T0 = m2_mul_interface(T0, r[i]);
             E0 = warp_exclusive_prefix(T0, carry[0], lane);
-            carry[1] = m2_shfl(m2_mul(E0, T0), 31);
+            carry[BWD_SUB - 1] = m2_shfl(m2_mul(E0, T0), 31);
         } else {
-            carry[1] = carry[0];
+            carry[BWD_SUB - 1] = carry[0];
         }
         // reverse scan, last sub-segment first
 #pragma unroll
