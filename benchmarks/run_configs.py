@@ -42,10 +42,22 @@ def main():
     from diffus_b200.training import TrainingVolume, mlp_render_mse_loss
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    dev = torch.device("cuda:0")
+    import torch.distributed as dist
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                          # torchrun: only config 4 has a collective (the weight-gradient all-reduce)
+        dist.init_process_group("nccl", device_id=dev)
     want = args.configs.split(",")
 
     def report(name, ms, samples, frames, bytes_per_sample, extra=None):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, samples, frames = t.item(), samples * world, frames * world
+            name = f"[{world} GPUs, poses sharded, max over ranks] " + name
+            if rank != 0:
+                return
         gs = samples / (ms * 1e-3) / 1e9
         line = {"config": name, "ms": ms, "gsamples_per_s": gs, "frames_per_s": frames / (ms * 1e-3),
                 "bytes_per_sample": bytes_per_sample, "hbm_frac": gs * bytes_per_sample / peak}
@@ -99,8 +111,9 @@ def main():
             model.model[4].weight.mul_(0.3)
         mri = (mri_phantom(256, "t2") / 1000.0).to(dev)
         P = 4096
-        s, d = pose_sweep(P, 128, 256, seed=2)
+        s, d = pose_sweep(P, 128, 256, seed=2 + rank)
         s, d = s.to(dev), d.to(dev)
+        from diffus_b200 import distributed as D
         with torch.no_grad():
             tgt = render_frames(PreparedVolume(model.impedance_volume(mri, None, 1e6, 400.0) * 1.01), s, d, 512, 1e-4,
                                 sampler="trilinear")
@@ -110,6 +123,7 @@ def main():
         def step(sampler="trilinear"):
             model.zero_grad(set_to_none=True)
             mlp_render_mse_loss(model, tv, s, d, tgt, 512, 1e-4, out_scale=1e6, sampler=sampler).backward()
+            D.allreduce_module_grads(model, average=True)          # one 4.6 KB flat all-reduce (no-op on 1 GPU)
         ms_near = timed(lambda: step("nearest"), max(3, args.iters // 4))
         report("4: MLP(256^3) -> 4096 frames -> MSE -> d/dweights, NEAREST sampler (the reference's own training form)",
                ms_near, P * 65536, P, 12)
@@ -147,3 +161,6 @@ def main():
 
 if __name__ == "__main__":
     main()
+    import torch.distributed as _d
+    if _d.is_initialized():
+        _d.destroy_process_group()
