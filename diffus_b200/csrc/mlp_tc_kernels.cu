@@ -118,10 +118,12 @@ __global__ void __launch_bounds__(TILE_M) mlp_fwd_tc_kernel(const float* __restr
         float* row_lo = a_lo + (tid >> 3) * (A_SBO / 4) + (tid & 7) * 4;
 #pragma unroll
         for (int kc = 0; kc < HID / 4; ++kc) {
+            const float4 w4 = ((const float4*)w1)[kc], c4 = ((const float4*)b1)[kc];     // broadcast 16-byte reads
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
             float h[4], hi[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                h[j] = fmaxf(fmaf(w1[4 * kc + j], xv, b1[4 * kc + j]), 0.f);
+                h[j] = fmaxf(fmaf(wv[j], xv, cv[j]), 0.f);
                 hi[j] = tf32_hi(h[j]);
             }
             *(float4*)(row_hi + kc * (A_LBO / 4)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
@@ -165,9 +167,16 @@ __global__ void __launch_bounds__(TILE_M) mlp_fwd_tc_kernel(const float* __restr
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         // layer 3 on the CUDA cores
-        float acc3 = b3;
+        float acc3a = b3, acc3b = 0.f;
 #pragma unroll
-        for (int j = 0; j < HID; ++j) acc3 = fmaf(w3[j], fmaxf(__uint_as_float(v[j]) + b2[j], 0.f), acc3);
+        for (int j4 = 0; j4 < HID / 4; ++j4) {
+            const float4 c4 = ((const float4*)b2)[j4], w4 = ((const float4*)w3)[j4];
+            acc3a = fmaf(w4.x, fmaxf(__uint_as_float(v[4 * j4]) + c4.x, 0.f), acc3a);
+            acc3b = fmaf(w4.y, fmaxf(__uint_as_float(v[4 * j4 + 1]) + c4.y, 0.f), acc3b);
+            acc3a = fmaf(w4.z, fmaxf(__uint_as_float(v[4 * j4 + 2]) + c4.z, 0.f), acc3a);
+            acc3b = fmaf(w4.w, fmaxf(__uint_as_float(v[4 * j4 + 3]) + c4.w, 0.f), acc3b);
+        }
+        const float acc3 = acc3a + acc3b;
         if (idx < n) out[idx] = (mask && !mask[idx]) ? fill : out_scale * acc3;
         // the next tile overwrites the operand tiles and the accumulator
         asm volatile("tcgen05.fence::before_thread_sync;\n");
