@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
 #pragma unroll 4
         for (int t = 0; t < ntile; ++t) {
             int idx = t * 32 + lane;
-            if (idx < ncol) out[c0 + idx] = __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]);
+            if (idx < ncol) __stcs(out + c0 + idx, __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]));   // streaming store: frames are write-once
         }
         if (lane == 0) zbuf[G::pad(0)] = zbuf[G::pad(G::SEG)];   // sample c0+SEG-1 becomes the next segment's left neighbour
         __syncwarp();
