@@ -123,6 +123,7 @@ def build_scene(device, n_poses, seed):
 def run_ours(args):
     import torch.distributed as dist
     from diffus_b200 import PreparedVolume, ops, render_frames, render_mse_loss
+    from diffus_b200.graphs import GraphedPoseStep
     from diffus_b200._lib import SAMPLER_TRILINEAR
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,14 +162,24 @@ def run_ours(args):
     out_dir = torch.empty((P, N_RAYS, 3), dtype=torch.float32).pin_memory()
     out_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
+    # a pose sweep repeats the same shapes every step: the user-facing call for that is the CUDA-graph
+    # wrapper of the fused step (diffus_b200.graphs.GraphedPoseStep); eager autograd costs ~0.15 ms more
+    gstep = GraphedPoseStep(vol, target, N_RAYS, N_SAMPLES, ALPHA) if args.e2e == "graph" else None
+
     def step_e2e():
-        s = src_pin.to(dev, non_blocking=True).requires_grad_(True)
-        d = dir_pin.to(dev, non_blocking=True).requires_grad_(True)
-        loss = render_mse_loss(vol, s, d, target, N_SAMPLES, ALPHA, 0, sampler="trilinear")
-        loss.backward()
-        out_loss.copy_(loss.detach(), non_blocking=True)
-        out_src.copy_(s.grad, non_blocking=True)
-        out_dir.copy_(d.grad, non_blocking=True)
+        if gstep is not None:
+            loss, gs, gd = gstep(src_pin, dir_pin)              # H2D of the poses into the graph's static inputs
+            out_loss.copy_(loss, non_blocking=True)
+            out_src.copy_(gs, non_blocking=True)
+            out_dir.copy_(gd, non_blocking=True)
+        else:
+            s = src_pin.to(dev, non_blocking=True).requires_grad_(True)
+            d = dir_pin.to(dev, non_blocking=True).requires_grad_(True)
+            loss = render_mse_loss(vol, s, d, target, N_SAMPLES, ALPHA, 0, sampler="trilinear")
+            loss.backward()
+            out_loss.copy_(loss.detach(), non_blocking=True)
+            out_src.copy_(s.grad, non_blocking=True)
+            out_dir.copy_(d.grad, non_blocking=True)
         torch.cuda.current_stream().synchronize()        # the caller needs the numbers on the host
         return out_loss
 
@@ -248,8 +259,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(src_pin.numel() * 4 + dir_pin.numel() * 4),
                     "d2h_bytes_per_step": int(out_src.numel() * 4 + out_dir.numel() * 4 + 4),
                     "ms_per_step": e2e_ms_total / K,
-                    "note": "public API render_mse_loss + loss.backward(); poses from pinned host memory each step, loss "
-                            "and pose gradients copied back to pinned host memory; volume and target frames resident"},
+                    "api": "GraphedPoseStep (CUDA-graph replay of the fused step)" if args.e2e == "graph"
+                           else "render_mse_loss + loss.backward() (eager autograd)",
+                    "note": "public API call per step; poses from pinned host memory each step, loss and pose gradients "
+                            "copied back to pinned host memory, stream synchronised every step; volume and target "
+                            "frames resident"},
             "gpu_launches": launches,
             "kernels_ms": {"fused_step(render_bwd_kernel+reduce_rays+reduce_sum)": step_ms},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -370,6 +384,7 @@ def main():
     ap.add_argument("--layout", default="brick", choices=["linear", "brick"])
     ap.add_argument("--cpu-rays", type=int, default=16, help="rays in the bounded CPU sample (~2 GB and ~0.5 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e", default="graph", choices=["graph", "eager"], help="public API used by the end-to-end loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
