@@ -105,9 +105,10 @@ def ncu_traffic(P, layout):
     """DRAM bytes per launch of the fused kernel from the committed ncu capture, if it is the same workload."""
     try:
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            t = json.load(f)["render_bwd_kernel_fused_mse"]
-        if (t["poses"], t["rays"], t["samples"], t["layout"]) == (P, N_RAYS, N_SAMPLES, layout):
-            return t["bytes_per_launch"]
+            entries = json.load(f)["render_bwd_kernel_fused_mse"]
+        for t in (entries if isinstance(entries, list) else [entries]):
+            if (t["poses"], t["rays"], t["samples"], t["layout"]) == (P, N_RAYS, N_SAMPLES, layout):
+                return t["bytes_per_launch"]
     except Exception:
         pass
     return None
@@ -135,7 +136,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     P = args.poses
     vol_h, src_h, dir_h = build_scene(dev, P, seed=1000 + rank)       # every rank: its own pose shard
-    vol = PreparedVolume(vol_h.to(dev)) if args.layout == "brick" else vol_h.to(dev)
+    vol = PreparedVolume(vol_h.to(dev), args.layout) if args.layout != "linear" else vol_h.to(dev)
     src_pin, dir_pin = src_h.pin_memory(), dir_h.pin_memory()
     src_d, dir_d = src_h.to(dev), dir_h.to(dev)
     with torch.no_grad():
@@ -381,7 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=1024, help="poses per GPU per step")
-    ap.add_argument("--layout", default="brick", choices=["linear", "brick"])
+    ap.add_argument("--layout", default="brick", choices=["linear", "brick", "quad"])
     ap.add_argument("--cpu-rays", type=int, default=16, help="rays in the bounded CPU sample (~2 GB and ~0.5 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e", default="graph", choices=["graph", "eager"], help="public API used by the end-to-end loop")

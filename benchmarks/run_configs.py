@@ -36,6 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3f,4,5")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--layout", default="auto", choices=["auto", "brick", "quad"], help="packed layout of the pose-sweep volumes")
     args = ap.parse_args()
     from diffus_b200 import ImpedanceEstimator, PreparedVolume, UltrasoundRenderer, render_frames, render_mse_loss
     from diffus_b200.phantoms import config1_pose, intensity_to_impedance, layered_phantom, mri_phantom, pose_sweep
@@ -96,13 +97,13 @@ def main():
             ms = timed(lambda: gstep(s1, d1), args.iters)
             report("2: same as a GraphedPoseStep (CUDA graph replay incl. copying the new pose in)", ms, 65536, 1, 36)
     if "3f" in want:
-        vol = PreparedVolume(intensity_to_impedance(mri_phantom(256, "t1")).to(dev))
+        vol = PreparedVolume(intensity_to_impedance(mri_phantom(256, "t1")).to(dev), args.layout)
         s, d = pose_sweep(1024, 128, 256, seed=1)
         s, d = s.to(dev), d.to(dev)
         for sampler, b in (("trilinear", 36), ("nearest", 8)):
             with torch.no_grad():
                 ms = timed(lambda: render_frames(vol, s, d, 512, 1e-4, sampler=sampler), args.iters)
-            report(f"3: pose sweep forward only, 1024 poses, {sampler}", ms, 1024 * 65536, 1024, b)
+            report(f"3: pose sweep forward only, 1024 poses, {sampler}, {vol.layout} layout", ms, 1024 * 65536, 1024, b)
     if "4" in want:
         torch.manual_seed(0)
         model = ImpedanceEstimator(1).to(dev)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libdiffus_b200.so")
 ABI_VERSION = 1
 
 SAMPLER_NEAREST, SAMPLER_TRILINEAR = 0, 1
-LAYOUT_LINEAR, LAYOUT_BRICK = 0, 1
+LAYOUT_LINEAR, LAYOUT_BRICK, LAYOUT_QUAD = 0, 1, 2
 POSE_F32, POSE_F64 = 0, 1
 MLP_NPARAMS = 1153
 
@@ -89,6 +89,8 @@ SIGNATURES = {
     "diffus_brick_elems": (_i64, [_P(_i32 * 3)]),
     "diffus_volume_to_bricks": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
     "diffus_bricks_to_volume": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
+    "diffus_quad_elems": (_i64, [_P(_i32 * 3)]),
+    "diffus_volume_to_quads": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
 }
 
 _lib = None

@@ -14,7 +14,8 @@ int32_t check_volume(const DiffusVolume& v) {
     if (v.dim[0] < 1 || v.dim[1] < 1 || v.dim[2] < 1) return DIFFUS_E_SHAPE;
     // 32-bit element offsets (also in the padded brick layout)
     if (((int64_t)v.dim[0] + 3) * ((int64_t)v.dim[1] + 3) * ((int64_t)v.dim[2] + 1) >= ((int64_t)1 << 31)) return DIFFUS_E_UNSUPPORTED;
-    if (v.layout != DIFFUS_LAYOUT_LINEAR && v.layout != DIFFUS_LAYOUT_BRICK) return DIFFUS_E_ENUM;
+    if (v.layout != DIFFUS_LAYOUT_LINEAR && v.layout != DIFFUS_LAYOUT_BRICK && v.layout != DIFFUS_LAYOUT_QUAD) return DIFFUS_E_ENUM;
+    if (v.layout == DIFFUS_LAYOUT_QUAD && ((uintptr_t)v.data & 15)) return DIFFUS_E_UNSUPPORTED;   // float4 loads
     return DIFFUS_OK;
 }
 
@@ -41,13 +42,19 @@ RenderParams pack(const DiffusRenderArgs* a) {
     p.vol.D = a->volume.dim[0];
     p.vol.H = a->volume.dim[1];
     p.vol.W = a->volume.dim[2];
+    const uint32_t nbj = (p.vol.H + BRICK_J - 1) / BRICK_J, nbk = (p.vol.W + BRICK_K - 1) / BRICK_K;
     if (a->volume.layout == DIFFUS_LAYOUT_BRICK) {
-        uint32_t nbj = (p.vol.H + BRICK_J - 1) / BRICK_J, nbk = (p.vol.W + BRICK_K - 1) / BRICK_K;
-        p.vol.sy = nbk * 32;
-        p.vol.sx = nbj * nbk * 32;
+        p.vol.gsy = p.vol.sy = nbk * 32;
+        p.vol.gsx = p.vol.sx = nbj * nbk * 32;
+    } else if (a->volume.layout == DIFFUS_LAYOUT_QUAD) {
+        const uint32_t nqj = (p.vol.H + QUAD_B - 1) / QUAD_B, nqk = (p.vol.W + QUAD_B - 1) / QUAD_B;
+        p.vol.sy = nqk * 8;                 // float4 units
+        p.vol.sx = nqj * nqk * 8;
+        p.vol.gsy = nbk * 32;               // gradients of a QUAD volume go to a BRICK buffer
+        p.vol.gsx = nbj * nbk * 32;
     } else {
-        p.vol.sy = (uint32_t)p.vol.W;
-        p.vol.sx = (uint32_t)p.vol.H * (uint32_t)p.vol.W;
+        p.vol.gsy = p.vol.sy = (uint32_t)p.vol.W;
+        p.vol.gsx = p.vol.sx = (uint32_t)p.vol.H * (uint32_t)p.vol.W;
     }
     p.sources = a->sources;
     p.directions = a->directions;
@@ -379,6 +386,19 @@ int32_t diffus_bricks_to_volume(const float* bricks, const int32_t dim[3], float
     if (!linear || !dim || !bricks) return DIFFUS_E_NULL;
     if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
     return cuda_rc(launch_from_bricks(bricks, dim, linear, (cudaStream_t)stream));
+}
+
+int64_t diffus_quad_elems(const int32_t dim[3]) {
+    if (!dim) return 0;
+    int64_t nqi = (dim[0] + QUAD_B - 1) / QUAD_B, nqj = (dim[1] + QUAD_B - 1) / QUAD_B, nqk = (dim[2] + QUAD_B - 1) / QUAD_B;
+    return nqi * nqj * nqk * 8 * 4;
+}
+
+int32_t diffus_volume_to_quads(const float* linear, const int32_t dim[3], float* quads, void* stream) {
+    if (!linear || !dim || !quads) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
+    if ((uintptr_t)quads & 15) return DIFFUS_E_UNSUPPORTED;
+    return cuda_rc(launch_to_quads(linear, dim, quads, (cudaStream_t)stream));
 }
 
 }  // extern "C"

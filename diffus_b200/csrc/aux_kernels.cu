@@ -92,14 +92,14 @@ __global__ void median_backward_kernel(const RenderParams p, const int32_t* __re
             float p0 = rs.coord(0, kk), p1 = rs.coord(1, kk), p2 = rs.coord(2, kk);
             if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
                 int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
-                atomicAdd(p.grad_volume + voxel_offset<LAYOUT>(p.vol, i, j, l), zb);
+                atomicAdd(p.grad_volume + grad_offset<LAYOUT>(p.vol, i, j, l), zb);
             } else {
                 TriCell c;
-                tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
-                tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
-                tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+                tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0]);
+                tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1]);
+                tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2]);
                 uint32_t off[8];
-                tri_offsets<LAYOUT>(p.vol, c, off);
+                tri_offsets<GradLayout<LAYOUT>::value>(p.vol, c, off);
                 for (int q = 0; q < 8; ++q) {
                     float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
                     if (w != 0.f) atomicAdd(p.grad_volume + off[q], w * zb);
@@ -211,20 +211,18 @@ __global__ void trace_values_bwd_kernel(const RenderParams p, const float* __res
         if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
             if (VOL_GRAD && g != 0.f) {
                 int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
-                atomicAdd(p.grad_volume + voxel_offset<LAYOUT>(p.vol, i, j, l), g);
+                atomicAdd(p.grad_volume + grad_offset<LAYOUT>(p.vol, i, j, l), g);
             }
         } else {
             TriCell c;
-            tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
-            tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
-            tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+            tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0]);
+            tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1]);
+            tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2]);
             uint32_t off[8];
-            tri_offsets<LAYOUT>(p.vol, c, off);
+            tri_offsets<GradLayout<LAYOUT>::value>(p.vol, c, off);
             if (POSE_GRAD) {
-                float z[8], dzv[3];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) z[q] = __ldg(p.vol.data + off[q]);
-                tri_combine<true>(z, c, dzv);
+                float dzv[3];
+                sample_volume<SAMPLER, LAYOUT, true>(p.vol, p0, p1, p2, dzv);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) { acc_s[a] += g * dzv[a]; acc_d[a] += (float)k * g * dzv[a]; }
             }
@@ -351,6 +349,38 @@ cudaError_t launch_from_bricks(const float* bricks, const int32_t dim[3], float*
     int64_t n = (int64_t)nbi * nbj * nbk * 32;
     unsigned grid = (unsigned)min((int64_t)148 * 32, (n + 255) / 256);
     brick_copy_kernel<false><<<grid, 256, 0, st>>>(bricks, linear, dim[0], dim[1], dim[2], nbi, nbj, nbk);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// LINEAR -> QUAD: element (i, j, k) = (Z[i,j,k], Z[i,j+1,k], Z[i,j,k+1], Z[i,j+1,k+1]) with +1 clamped at the faces
+// (the i1 = min(i0 + 1, n - 1) rule of the sampler); 2x2x2 elements per 128-byte line, the i-pair in one sector.
+// ---------------------------------------------------------------------------------------
+__global__ void quad_copy_kernel(const float* __restrict__ src, float4* __restrict__ dst, int D, int H, int W, int nqi,
+                                 int nqj, int nqk) {
+    const int64_t n = (int64_t)nqi * nqj * nqk * 8;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int e = (int)(t & 7);
+        int64_t b = t >> 3;
+        int bk = (int)(b % nqk);
+        int bj = (int)((b / nqk) % nqj);
+        int bi = (int)(b / ((int64_t)nqk * nqj));
+        int i = bi * QUAD_B + (e & 1), k = bk * QUAD_B + ((e >> 1) & 1), j = bj * QUAD_B + ((e >> 2) & 1);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < D && j < H && k < W) {
+            const int j1 = min(j + 1, H - 1), k1 = min(k + 1, W - 1);
+            const float* slab = src + (int64_t)i * H * W;
+            q = make_float4(slab[(int64_t)j * W + k], slab[(int64_t)j1 * W + k], slab[(int64_t)j * W + k1], slab[(int64_t)j1 * W + k1]);
+        }
+        dst[t] = q;
+    }
+}
+
+cudaError_t launch_to_quads(const float* linear, const int32_t dim[3], float* quads, cudaStream_t st) {
+    int nqi = (dim[0] + QUAD_B - 1) / QUAD_B, nqj = (dim[1] + QUAD_B - 1) / QUAD_B, nqk = (dim[2] + QUAD_B - 1) / QUAD_B;
+    int64_t n = (int64_t)nqi * nqj * nqk * 8;
+    unsigned grid = (unsigned)min((int64_t)148 * 32, (n + 255) / 256);
+    quad_copy_kernel<<<grid, 256, 0, st>>>(linear, (float4*)quads, dim[0], dim[1], dim[2], nqi, nqj, nqk);
     return cudaGetLastError();
 }
 

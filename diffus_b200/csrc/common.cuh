@@ -47,40 +47,45 @@ using BwdGeo = Geo<8, 2>;
 constexpr int PREFIX_STRIDE = FwdGeo::SEG;
 constexpr int BWD_SUB = PREFIX_STRIDE / BwdGeo::SEG;
 
-struct M2 {          // [[a, b], [c, d]]
-    float a, b, c, d;
+// 2x2 transfer matrix [[a, b], [c, d]] held as its two COLUMNS, (a, c) and (b, d), each in one 64-bit
+// register pair: every product below is then a handful of packed FP32 operations (sm_100 `fma.rn.f32x2`
+// -> SASS FFMA2 / FMUL2 / FADD2, which take a scalar broadcast operand and negation for free).  A packed
+// op rounds each half exactly like its scalar counterpart, so the roundings spelled out here (one multiply
+// + one fused multiply-add per entry) are what every kernel walking the same ray reproduces bit for bit.
+struct M2 {
+    float2 c0, c1;       // c0 = (a, c), c1 = (b, d)
+    __device__ __forceinline__ float a() const { return c0.x; }
+    __device__ __forceinline__ float b() const { return c1.x; }
+    __device__ __forceinline__ float c() const { return c0.y; }
+    __device__ __forceinline__ float d() const { return c1.y; }
 };
-__device__ __forceinline__ M2 m2_identity() { return M2{1.f, 0.f, 0.f, 1.f}; }
-// The products below spell out their roundings (one multiply + one fused multiply-add per
-// entry) so that every kernel that walks the same ray produces bit-identical prefixes,
-// whatever the compiler would have contracted on its own.
-__device__ __forceinline__ float mul_add2(float a, float b, float c, float d) {   // a*b + c*d
-    return __fmaf_rn(a, b, __fmul_rn(c, d));
-}
+__device__ __forceinline__ float2 bcast(float s) { return make_float2(s, s); }
+__device__ __forceinline__ M2 m2_make(float a, float b, float c, float d) { return M2{make_float2(a, c), make_float2(b, d)}; }
+__device__ __forceinline__ M2 m2_identity() { return m2_make(1.f, 0.f, 0.f, 1.f); }
+__device__ __forceinline__ M2 m2_zero() { return m2_make(0.f, 0.f, 0.f, 0.f); }
+// x * y: entry = fma(x_row[0], y_col[0], x_row[1] * y_col[1])
 __device__ __forceinline__ M2 m2_mul(const M2& x, const M2& y) {
-    return M2{mul_add2(x.a, y.a, x.b, y.c), mul_add2(x.a, y.b, x.b, y.d), mul_add2(x.c, y.a, x.d, y.c), mul_add2(x.c, y.b, x.d, y.d)};
+    return M2{__ffma2_rn(x.c0, bcast(y.c0.x), __fmul2_rn(x.c1, bcast(y.c0.y))),
+              __ffma2_rn(x.c0, bcast(y.c1.x), __fmul2_rn(x.c1, bcast(y.c1.y)))};
 }
 // P * M(r),  M(r) = [[1 - 2 r^2, r], [-r, 1]]
 __device__ __forceinline__ M2 m2_mul_interface(const M2& p, float r) {
     float q = __fmaf_rn(-2.f * r, r, 1.f);
-    return M2{__fmaf_rn(p.a, q, -__fmul_rn(p.b, r)), __fmaf_rn(p.a, r, p.b), __fmaf_rn(p.c, q, -__fmul_rn(p.d, r)), __fmaf_rn(p.c, r, p.d)};
+    return M2{__ffma2_rn(p.c0, bcast(q), __fmul2_rn(p.c1, bcast(-r))), __ffma2_rn(p.c0, bcast(r), p.c1)};
 }
 // X * M(r)^T
 __device__ __forceinline__ M2 m2_mul_interface_t(const M2& x, float r) {
     float q = __fmaf_rn(-2.f * r, r, 1.f);
-    return M2{mul_add2(x.a, q, x.b, r), __fmaf_rn(-x.a, r, x.b), mul_add2(x.c, q, x.d, r), __fmaf_rn(-x.c, r, x.d)};
+    return M2{__ffma2_rn(x.c0, bcast(q), __fmul2_rn(x.c1, bcast(r))), __ffma2_rn(x.c0, bcast(-r), x.c1)};
 }
-__device__ __forceinline__ M2 m2_transpose(const M2& x) { return M2{x.a, x.c, x.b, x.d}; }
-__device__ __forceinline__ M2 m2_add(const M2& x, const M2& y) { return M2{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
-__device__ __forceinline__ M2 m2_shfl_up(const M2& x, int d) {
-    return M2{__shfl_up_sync(FULL, x.a, d), __shfl_up_sync(FULL, x.b, d), __shfl_up_sync(FULL, x.c, d), __shfl_up_sync(FULL, x.d, d)};
-}
-__device__ __forceinline__ M2 m2_shfl_down(const M2& x, int d) {
-    return M2{__shfl_down_sync(FULL, x.a, d), __shfl_down_sync(FULL, x.b, d), __shfl_down_sync(FULL, x.c, d), __shfl_down_sync(FULL, x.d, d)};
-}
-__device__ __forceinline__ M2 m2_shfl(const M2& x, int src) {
-    return M2{__shfl_sync(FULL, x.a, src), __shfl_sync(FULL, x.b, src), __shfl_sync(FULL, x.c, src), __shfl_sync(FULL, x.d, src)};
-}
+__device__ __forceinline__ M2 m2_transpose(const M2& x) { return m2_make(x.a(), x.c(), x.b(), x.d()); }
+__device__ __forceinline__ M2 m2_add(const M2& x, const M2& y) { return M2{__fadd2_rn(x.c0, y.c0), __fadd2_rn(x.c1, y.c1)}; }
+__device__ __forceinline__ float2 shfl_up2(float2 v, int d) { return make_float2(__shfl_up_sync(FULL, v.x, d), __shfl_up_sync(FULL, v.y, d)); }
+__device__ __forceinline__ float2 shfl_down2(float2 v, int d) { return make_float2(__shfl_down_sync(FULL, v.x, d), __shfl_down_sync(FULL, v.y, d)); }
+__device__ __forceinline__ float2 shfl2(float2 v, int src) { return make_float2(__shfl_sync(FULL, v.x, src), __shfl_sync(FULL, v.y, src)); }
+__device__ __forceinline__ M2 m2_shfl_up(const M2& x, int d) { return M2{shfl_up2(x.c0, d), shfl_up2(x.c1, d)}; }
+__device__ __forceinline__ M2 m2_shfl_down(const M2& x, int d) { return M2{shfl_down2(x.c0, d), shfl_down2(x.c1, d)}; }
+__device__ __forceinline__ M2 m2_shfl(const M2& x, int src) { return M2{shfl2(x.c0, src), shfl2(x.c1, src)}; }
 
 // nan_to_num(nan=0) of src/renderer.py:408 (+-inf -> +-FLT_MAX like torch's default)
 __device__ __forceinline__ float nan_to_num(float e) {
@@ -99,30 +104,59 @@ __device__ __forceinline__ float warp_sum(float v) {
 // eight corners of a trilinear cell cost six per-axis terms and a handful of adds instead
 // of eight full index computations (integer address math was 47 % of the forward's
 // instructions in the first profile, profiles/r1_first_ncu.md).
+//
+// Layouts (include/diffus_b200.h):
+//   LINEAR  the torch tensor as is
+//   BRICK   4x4x2 voxels per 128-byte line, one float per voxel
+//   QUAD    one float4 per voxel holding the voxel and its +j, +k, +j+k neighbours (clamped at the faces),
+//           2x2x2 voxels per 128-byte line with the i-pair sharing a 32-byte sector.  A trilinear cell is
+//           two 16-byte loads (i0 and i1) instead of eight 4-byte ones: a quarter of the load instructions
+//           and L1 tag look-ups for four times the footprint.  Read-only: gradients w.r.t. a QUAD volume
+//           are scattered into a BRICK buffer (gsx / gsy below).
 // ---------------------------------------------------------------------------------------
 struct VolumeView {
     const float* data;
     int D, H, W;          // extents along point components 0, 1, 2
-    uint32_t sx, sy;      // LINEAR: H*W, W     BRICK: bricks-per-slab*32, bricks-per-row*32
+    uint32_t sx, sy;      // LINEAR: H*W, W     BRICK: bricks-per-slab*32, bricks-per-row*32    QUAD: same in float4 units (*8)
+    uint32_t gsx, gsy;    // strides of the gradient volume: = sx, sy for LINEAR / BRICK, the BRICK strides for QUAD
 };
 
 constexpr int BRICK_I = 4, BRICK_J = 4, BRICK_K = 2;   // 32 floats = one 128-byte line
+constexpr int QUAD_B = 2;                              // 2x2x2 float4 = one 128-byte line
+
+// layout of the gradient volume that belongs to a gathered layout
+template <int LAYOUT>
+struct GradLayout { static constexpr int value = LAYOUT == DIFFUS_LAYOUT_QUAD ? DIFFUS_LAYOUT_BRICK : LAYOUT; };
 
 template <int LAYOUT>
-__device__ __forceinline__ uint32_t axis_x(const VolumeView& v, int i) {
-    return LAYOUT == DIFFUS_LAYOUT_LINEAR ? (uint32_t)i * v.sx : (uint32_t)(i >> 2) * v.sx + ((uint32_t)(i & 3) << 3);
+__device__ __forceinline__ uint32_t axis_x(uint32_t sx, int i) {
+    if (LAYOUT == DIFFUS_LAYOUT_LINEAR) return (uint32_t)i * sx;
+    if (LAYOUT == DIFFUS_LAYOUT_BRICK) return (uint32_t)(i >> 2) * sx + ((uint32_t)(i & 3) << 3);
+    return (uint32_t)(i >> 1) * sx + (uint32_t)(i & 1);
 }
 template <int LAYOUT>
-__device__ __forceinline__ uint32_t axis_y(const VolumeView& v, int j) {
-    return LAYOUT == DIFFUS_LAYOUT_LINEAR ? (uint32_t)j * v.sy : (uint32_t)(j >> 2) * v.sy + ((uint32_t)(j & 3) << 1);
+__device__ __forceinline__ uint32_t axis_y(uint32_t sy, int j) {
+    if (LAYOUT == DIFFUS_LAYOUT_LINEAR) return (uint32_t)j * sy;
+    if (LAYOUT == DIFFUS_LAYOUT_BRICK) return (uint32_t)(j >> 2) * sy + ((uint32_t)(j & 3) << 1);
+    return (uint32_t)(j >> 1) * sy + ((uint32_t)(j & 1) << 2);
 }
 template <int LAYOUT>
-__device__ __forceinline__ uint32_t axis_z(const VolumeView& v, int k) {
-    return LAYOUT == DIFFUS_LAYOUT_LINEAR ? (uint32_t)k : ((uint32_t)(k >> 1) << 5) + (uint32_t)(k & 1);
+__device__ __forceinline__ uint32_t axis_z(int k) {
+    if (LAYOUT == DIFFUS_LAYOUT_LINEAR) return (uint32_t)k;
+    if (LAYOUT == DIFFUS_LAYOUT_BRICK) return ((uint32_t)(k >> 1) << 5) + (uint32_t)(k & 1);
+    return ((uint32_t)(k >> 1) << 3) + ((uint32_t)(k & 1) << 1);
 }
+// element offset in the gathered layout (float units for LINEAR / BRICK, float4 units for QUAD)
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t voxel_offset(const VolumeView& v, int i, int j, int k) {
-    return axis_x<LAYOUT>(v, i) + axis_y<LAYOUT>(v, j) + axis_z<LAYOUT>(v, k);
+    return axis_x<LAYOUT>(v.sx, i) + axis_y<LAYOUT>(v.sy, j) + axis_z<LAYOUT>(k);
+}
+
+// element offset in the gradient volume that belongs to a LAYOUT volume
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t grad_offset(const VolumeView& v, int i, int j, int k) {
+    constexpr int GL = GradLayout<LAYOUT>::value;
+    return axis_x<GL>(v.gsx, i) + axis_y<GL>(v.gsy, j) + axis_z<GL>(k);
 }
 
 // a / b without the IEEE slow path (<= 2 ulp): the reference's own float32 run is ~1e-5 of
@@ -188,83 +222,97 @@ __device__ __forceinline__ int nearest_index(float p, int n) {
 
 struct TriCell {       // clamp-then-floor cell of a trilinear sample, grid_sample border semantics
     int i0[3], i1[3];
-    float f[3];
-    bool inside[3];    // derivative w.r.t. the coordinate is non-zero only strictly inside
+    float f[3];        // fraction in [0, 1); -0.0f marks a coordinate at or beyond a face (see tri_axis)
 };
 
-__device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float& f, bool& inside) {
+// The derivative w.r.t. a coordinate is non-zero only strictly inside the volume.  A coordinate at or beyond a
+// face clamps to the face and its fraction is exactly 0, so "outside" travels for free in the sign bit of f:
+// -0.0f interpolates exactly like +0.0f and costs no register or predicate per sample.
+__device__ __forceinline__ bool tri_inside(float f) { return (__float_as_uint(f) >> 31) == 0u; }
+
+__device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float& f) {
     float hi = (float)(n - 1);
-    inside = (p > 0.f) && (p < hi);
+    bool inside = (p > 0.f) && (p < hi);
     float pc = fminf(fmaxf(p, 0.f), hi);
     float fl = floorf(pc);
-    f = pc - fl;
+    f = inside ? pc - fl : -0.f;
     i0 = (int)fl;
     i1 = min(i0 + 1, n - 1);
 }
 
-template <int LAYOUT>
+// offsets of the eight corners in the layout of the GRADIENT volume (also the gathered one for LINEAR / BRICK)
+template <int GLAYOUT>
 __device__ __forceinline__ void tri_offsets(const VolumeView& v, const TriCell& c, uint32_t off[8]) {
-    uint32_t x0 = axis_x<LAYOUT>(v, c.i0[0]), x1 = axis_x<LAYOUT>(v, c.i1[0]);
-    uint32_t y0 = axis_y<LAYOUT>(v, c.i0[1]), y1 = axis_y<LAYOUT>(v, c.i1[1]);
-    uint32_t z0 = axis_z<LAYOUT>(v, c.i0[2]), z1 = axis_z<LAYOUT>(v, c.i1[2]);
+    uint32_t x0 = axis_x<GLAYOUT>(v.gsx, c.i0[0]), x1 = axis_x<GLAYOUT>(v.gsx, c.i1[0]);
+    uint32_t y0 = axis_y<GLAYOUT>(v.gsy, c.i0[1]), y1 = axis_y<GLAYOUT>(v.gsy, c.i1[1]);
+    uint32_t z0 = axis_z<GLAYOUT>(c.i0[2]), z1 = axis_z<GLAYOUT>(c.i1[2]);
     uint32_t a00 = x0 + y0, a01 = x0 + y1, a10 = x1 + y0, a11 = x1 + y1;
     off[0] = a00 + z0; off[1] = a00 + z1; off[2] = a01 + z0; off[3] = a01 + z1;
     off[4] = a10 + z0; off[5] = a10 + z1; off[6] = a11 + z0; off[7] = a11 + z1;
 }
 
-// value (and optionally the spatial gradient) of the border-clamped trilinear interpolant
+// Value (and optionally the spatial gradient) of the border-clamped trilinear interpolant from the two faces
+// of the cell: q0 = face i0, q1 = face i1, each (j0k0, j1k0, j0k1, j1k1) -- exactly a QUAD element.
+// Interpolation is a + f (b - a) along i (4 wide), then k (2 wide), then j, in packed FP32; the derivative
+// along an axis is the difference of the two faces across it, interpolated along the other two.
 template <bool GRAD>
-__device__ __forceinline__ float tri_combine(const float z[8], const TriCell& c, float g[3]) {
-    float fx = c.f[0], fy = c.f[1], fz = c.f[2];
-    float gx = 1.f - fx, gy = 1.f - fy, gz = 1.f - fz;
-    float c00 = z[0] * gz + z[1] * fz;   // (i0, j0)
-    float c01 = z[2] * gz + z[3] * fz;   // (i0, j1)
-    float c10 = z[4] * gz + z[5] * fz;   // (i1, j0)
-    float c11 = z[6] * gz + z[7] * fz;   // (i1, j1)
-    float c0 = c00 * gy + c01 * fy;
-    float c1 = c10 * gy + c11 * fy;
+__device__ __forceinline__ float tri_combine(const float4& q0, const float4& q1, const float f[3], float g[3]) {
+    const float2 a0 = make_float2(q0.x, q0.y), a1 = make_float2(q0.z, q0.w);      // face i0: k0 pair, k1 pair
+    const float2 d0 = __fadd2_rn(make_float2(q1.x, q1.y), make_float2(-a0.x, -a0.y));
+    const float2 d1 = __fadd2_rn(make_float2(q1.z, q1.w), make_float2(-a1.x, -a1.y));
+    const float2 fx = bcast(f[0]), fz = bcast(f[2]);
+    const float2 l0 = __ffma2_rn(d0, fx, a0), l1 = __ffma2_rn(d1, fx, a1);        // along i: (j0, j1) at k0 and at k1
+    const float2 ek = __fadd2_rn(l1, make_float2(-l0.x, -l0.y));                  // d / d k at j0, j1
+    const float2 m = __ffma2_rn(ek, fz, l0);                                      // along k: value at j0, j1
+    const float dj = m.y - m.x;
     if (GRAD) {
-        g[0] = c.inside[0] ? (c1 - c0) : 0.f;
-        g[1] = c.inside[1] ? ((c01 - c00) * gx + (c11 - c10) * fx) : 0.f;
-        float d00 = z[1] - z[0], d01 = z[3] - z[2], d10 = z[5] - z[4], d11 = z[7] - z[6];
-        g[2] = c.inside[2] ? ((d00 * gy + d01 * fy) * gx + (d10 * gy + d11 * fy) * fx) : 0.f;
+        const float2 di = __ffma2_rn(__fadd2_rn(d1, make_float2(-d0.x, -d0.y)), fz, d0);   // d / d i at j0, j1
+        g[0] = tri_inside(f[0]) ? __fmaf_rn(di.y - di.x, f[1], di.x) : 0.f;
+        g[1] = tri_inside(f[1]) ? dj : 0.f;
+        g[2] = tri_inside(f[2]) ? __fmaf_rn(ek.y - ek.x, f[1], ek.x) : 0.f;
     }
-    return c0 * gx + c1 * fx;
+    return __fmaf_rn(dj, f[1], m.x);
 }
 
 // A sample split into "issue the loads" and "combine", so a gather loop can keep the next
-// tile's eight loads in flight while it combines the current one (software pipelining).
+// tile's loads in flight while it combines the current one (software pipelining).
 template <int SAMPLER, int LAYOUT>
 struct Fetch {
-    float z[SAMPLER == DIFFUS_SAMPLER_NEAREST ? 1 : 8];
+    float4 q0, q1;     // nearest: q0.x only
     float f[3];
-    bool inside[3];
 
     __device__ __forceinline__ void issue(const VolumeView& v, float p0, float p1, float p2) {
         if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
             int i = nearest_index(p0, v.D), j = nearest_index(p1, v.H), k = nearest_index(p2, v.W);
-            z[0] = __ldg(v.data + voxel_offset<LAYOUT>(v, i, j, k));
+            const uint32_t off = voxel_offset<LAYOUT>(v, i, j, k);
+            q0.x = __ldg(v.data + (LAYOUT == DIFFUS_LAYOUT_QUAD ? (size_t)off * 4 : (size_t)off));
         } else {
             TriCell c;
-            tri_axis(p0, v.D, c.i0[0], c.i1[0], f[0], inside[0]);
-            tri_axis(p1, v.H, c.i0[1], c.i1[1], f[1], inside[1]);
-            tri_axis(p2, v.W, c.i0[2], c.i1[2], f[2], inside[2]);
-            uint32_t off[8];
-            tri_offsets<LAYOUT>(v, c, off);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) z[q] = __ldg(v.data + off[q]);
+            tri_axis(p0, v.D, c.i0[0], c.i1[0], f[0]);
+            tri_axis(p1, v.H, c.i0[1], c.i1[1], f[1]);
+            tri_axis(p2, v.W, c.i0[2], c.i1[2], f[2]);
+            if (LAYOUT == DIFFUS_LAYOUT_QUAD) {
+                const uint32_t base = axis_y<LAYOUT>(v.sy, c.i0[1]) + axis_z<LAYOUT>(c.i0[2]);
+                const float4* q = (const float4*)v.data;
+                q0 = __ldg(q + (base + axis_x<LAYOUT>(v.sx, c.i0[0])));
+                q1 = __ldg(q + (base + axis_x<LAYOUT>(v.sx, c.i1[0])));
+            } else {
+                uint32_t x0 = axis_x<LAYOUT>(v.sx, c.i0[0]), x1 = axis_x<LAYOUT>(v.sx, c.i1[0]);
+                uint32_t y0 = axis_y<LAYOUT>(v.sy, c.i0[1]), y1 = axis_y<LAYOUT>(v.sy, c.i1[1]);
+                uint32_t z0 = axis_z<LAYOUT>(c.i0[2]), z1 = axis_z<LAYOUT>(c.i1[2]);
+                uint32_t a00 = x0 + y0, a01 = x0 + y1, a10 = x1 + y0, a11 = x1 + y1;
+                q0 = make_float4(__ldg(v.data + (a00 + z0)), __ldg(v.data + (a01 + z0)), __ldg(v.data + (a00 + z1)), __ldg(v.data + (a01 + z1)));
+                q1 = make_float4(__ldg(v.data + (a10 + z0)), __ldg(v.data + (a11 + z0)), __ldg(v.data + (a10 + z1)), __ldg(v.data + (a11 + z1)));
+            }
         }
     }
     template <bool GRAD>
     __device__ __forceinline__ float finish(float g[3]) const {
         if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
             if (GRAD) { g[0] = g[1] = g[2] = 0.f; }
-            return z[0];
+            return q0.x;
         } else {
-            TriCell c;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { c.f[a] = f[a]; c.inside[a] = inside[a]; }
-            return tri_combine<GRAD>(z, c, g);
+            return tri_combine<GRAD>(q0, q1, f, g);
         }
     }
 };

@@ -15,6 +15,13 @@ namespace diffus {
         constexpr bool P64_ = (Pv);                                        \
         __VA_ARGS__;                                                       \
     }
+// -DDIFFUS_DEV_MINIMAL: instantiate only the benchmark's kernels (trilinear, brick, float32 pose) -- a build-time
+// shortcut for looking at one kernel's SASS, never used for the shipped library.
+#ifdef DIFFUS_DEV_MINIMAL
+#define DIFFUS_DISPATCH(...)                                                                    \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)     \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_QUAD, false, __VA_ARGS__)
+#else
 #define DIFFUS_DISPATCH(...)                                                                   \
     DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, false, __VA_ARGS__)     \
     DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, true, __VA_ARGS__)      \
@@ -23,7 +30,12 @@ namespace diffus {
     DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)      \
     DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)       \
     DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)    \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)     \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_QUAD, false, __VA_ARGS__)       \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_QUAD, true, __VA_ARGS__)        \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_QUAD, false, __VA_ARGS__)     \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_QUAD, true, __VA_ARGS__)
+#endif
 
 // render_kernels.cu
 cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st);
@@ -51,6 +63,7 @@ cudaError_t launch_cone_directions(const double* median, int64_t n_poses, int64_
                                    float* out, cudaStream_t st);
 cudaError_t launch_to_bricks(const float* linear, const int32_t dim[3], float* bricks, cudaStream_t st);
 cudaError_t launch_from_bricks(const float* bricks, const int32_t dim[3], float* linear, cudaStream_t st);
+cudaError_t launch_to_quads(const float* linear, const int32_t dim[3], float* quads, cudaStream_t st);
 
 // splat_kernels.cu
 int64_t splat_workspace_bytes(int H, int W);

@@ -43,7 +43,7 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
 #pragma unroll
     for (int i = 0; i < G::CHUNK; ++i) {
         P = m2_mul_interface(P, r[i]);
-        obuf[lane * (G::CHUNK + 1) + i] = nan_to_num(echo_of(P.b, fast_rcp(P.d)));
+        obuf[lane * (G::CHUNK + 1) + i] = nan_to_num(echo_of(P.b(), fast_rcp(P.d())));
     }
     return m2_shfl(P, 31);
 }
@@ -91,14 +91,14 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     constexpr int CK = G_::CKPT;   // a checkpoint every CK columns, the prefixes in between are recomputed
     M2 Pck[CHUNK / CK];            // true prefix BEFORE column CK*j of the chunk
     M2 G = m2_identity();          // local inclusive prefix
-    M2 B = M2{0.f, 0.f, 0.f, 0.f};
+    M2 B = m2_zero();
 #pragma unroll
     for (int i = 0; i < CHUNK; ++i) {
         if (i % CK == 0) Pck[i / CK] = P;
         P = m2_mul_interface(P, r[i]);
         G = m2_mul_interface(G, r[i]);
-        float inv = fast_rcp(P.d);
-        float e = echo_of(P.b, inv);
+        float inv = fast_rcp(P.d());
+        float e = echo_of(P.b(), inv);
         bool finite = fabsf(e) <= FLT_MAX;             // nan_to_num passes no gradient at NaN/inf
         float ge;
         const float att = att_lane ? att_lane[i] : 1.f;
@@ -115,8 +115,9 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         }
         if (!finite || i >= ncol_lane) ge = 0.f;           // columns that do not exist: the table beyond Sout is not filled
         gbuf[base + i] = ge;
-        float da = ge * inv, db = -ge * e * inv;       // D = [[0, da], [0, db]]
-        B.a += da * G.b; B.b += da * G.d; B.c += db * G.b; B.d += db * G.d;
+        const float2 dcol = make_float2(ge * inv, -ge * e * inv);   // D = [[0, da], [0, db]];  B += D G^T
+        B.c0 = __ffma2_rn(dcol, bcast(G.b()), B.c0);
+        B.c1 = __ffma2_rn(dcol, bcast(G.d()), B.c1);
     }
     // suffix scan of the affine maps X -> X * A + B, A = T^T
     M2 As = m2_transpose(T), Bs = B;
@@ -138,16 +139,16 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         M2 Q = Pck[i / CK];                            // prefix before column i
 #pragma unroll
         for (int m = 0; m < i % CK; ++m) Q = m2_mul_interface(Q, r[i - i % CK + m]);
-        M2 Pc = m2_mul_interface(Q, r[i]);
-        float inv = fast_rcp(Pc.d);
-        float e = echo_of(Pc.b, inv);
+        const float2 pc1 = __ffma2_rn(Q.c0, bcast(r[i]), Q.c1);      // (b, d) of the prefix through column i
+        float inv = fast_rcp(pc1.y);
+        float e = echo_of(pc1.x, inv);
         float ge = gbuf[base + i];
         M2 Pbar = V;
-        Pbar.b += ge * inv;
-        Pbar.d -= ge * e * inv;
-        float ma = Q.a * Pbar.a + Q.c * Pbar.c;
-        float mb = Q.a * Pbar.b + Q.c * Pbar.d;
-        float mc = Q.b * Pbar.a + Q.d * Pbar.c;
+        Pbar.c1 = __fadd2_rn(Pbar.c1, make_float2(ge * inv, -ge * e * inv));
+        const float2 t0 = __fmul2_rn(Q.c0, Pbar.c0), t1 = __fmul2_rn(Q.c0, Pbar.c1), t2 = __fmul2_rn(Q.c1, Pbar.c0);
+        float ma = t0.x + t0.y;          // Mbar = Q^T Pbar
+        float mb = t1.x + t1.y;
+        float mc = t2.x + t2.y;
         float rbar = -4.f * r[i] * ma + mb - mc;
         rbar = (rbar == rbar) ? rbar : 0.f;
         if (z_lane) {
@@ -221,11 +222,11 @@ constexpr int FWD_SMEM_PER_WARP = FwdGeo::ZBUF + FwdGeo::OBUF;
 __device__ __forceinline__ void store_prefix(const RenderParams& p, int64_t ray, int col, const M2& m) {
     // prefix before column `col` (a positive multiple of PREFIX_STRIDE below Sout)
     float4* sp = (float4*)(p.seg_prefix + (ray * p.nprefix + (col / PREFIX_STRIDE - 1)) * 4);
-    *sp = make_float4(m.a, m.b, m.c, m.d);
+    *sp = make_float4(m.a(), m.b(), m.c(), m.d());
 }
 
 template <int SAMPLER, int LAYOUT, bool POSE64>
-__global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(128, 6) render_fwd_kernel(const RenderParams p) {
     using G = FwdGeo;
     extern __shared__ float smem[];
     float* att = smem;
@@ -249,15 +250,25 @@ __global__ void __launch_bounds__(128) render_fwd_kernel(const RenderParams p) {
         const int ncol = min(G::SEG, p.Sout - c0);
         // gather phase: lane = consecutive sample
         const int ntile = (ncol + 31) >> 5;
-        constexpr int GATHER_UNROLL = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 4;
-#pragma unroll GATHER_UNROLL
-        for (int t = 0; t < ntile; ++t) {
-            int idx = t * 32 + lane;
-            if (idx < ncol) {
-                int k = p.start + c0 + idx;
-                float g[3];
-                float z = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
-                zbuf[G::pad(idx + 1)] = z;
+        // batches of tiles: every load of a batch is issued before the first one is combined
+        constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 2;
+        for (int t0 = 0; t0 < ntile; t0 += GB) {
+            Fetch<SAMPLER, LAYOUT> fe[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                int idx = (t0 + u) * 32 + lane;
+                if (idx < ncol) {
+                    int k = p.start + c0 + idx;
+                    fe[u].issue(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                int idx = (t0 + u) * 32 + lane;
+                if (idx < ncol) {
+                    float g[3];
+                    zbuf[G::pad(idx + 1)] = fe[u].template finish<false>(g);
+                }
             }
         }
         __syncwarp();
@@ -295,14 +306,14 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
     float p0 = rs.coord(0, k), p1 = rs.coord(1, k), p2 = rs.coord(2, k);
     if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
         int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), kk = nearest_index(p2, p.vol.W);
-        atomicAdd(p.grad_volume + voxel_offset<LAYOUT>(p.vol, i, j, kk), zbar);
+        atomicAdd(p.grad_volume + grad_offset<LAYOUT>(p.vol, i, j, kk), zbar);
     } else {
         TriCell c;
-        tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0], c.inside[0]);
-        tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1], c.inside[1]);
-        tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2], c.inside[2]);
+        tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0]);
+        tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1]);
+        tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2]);
         uint32_t off[8];
-        tri_offsets<LAYOUT>(p.vol, c, off);
+        tri_offsets<GradLayout<LAYOUT>::value>(p.vol, c, off);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
@@ -311,7 +322,10 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
     }
 }
 
-template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS>
+// ONE_PASS: the ray fits one 512-column pass (every BASELINE config but the 2048-sample stress case).  The pass
+// loop disappears, so the accumulators and the adjoint carried between passes are not live during the gather:
+// that is what lets the gather batch four tiles of loads at 128 registers without spills.
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS>
 __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p) {
     using G = BwdGeo;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
@@ -331,10 +345,10 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     const float* gin = (LOSS == LOSS_MSE ? p.target : p.grad_frame) + ray * (int64_t)p.Sout;
     float* fout = (LOSS == LOSS_MSE && p.frame) ? p.frame + ray * (int64_t)p.Sout : nullptr;
     if (lane == 0) zbuf[0] = 0.f;
-    const int nss = (p.Sout + SS - 1) / SS;
+    const int nss = ONE_PASS ? 1 : (p.Sout + SS - 1) / SS;
     const uint64_t stream_policy = l2_evict_first_policy();
 
-    M2 vin = M2{0.f, 0.f, 0.f, 0.f};
+    M2 vin = m2_zero();
     float carry_w = 0.f, carry_z = 0.f;      // first column of the later pass: its weight w and its impedance
     float acc_s[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
     float loss_acc = 0.f;
@@ -357,17 +371,30 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             // gather phase: one pass over the volume for these columns.  (A cp.async ring for the
             // gathers themselves was measured slower than plain loads: LDGSTS issues at a quarter of
             // the LDG rate and adds eight shared-memory reads per sample)
-            // The nearest sampler has one load per sample and almost no L1 reuse: keep 8 tiles in flight.
-            constexpr int GATHER_UNROLL = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 2;
-#pragma unroll GATHER_UNROLL
-            for (int t = 0; t < nt; ++t) {
-                int idx = t * 32 + lane;
-                if (idx < ncol) {
-                    int k = p.start + c0 + idx;
-                    float g[3];
-                    float z = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
-                    zbuf[G::pad(idx + 1)] = z;
-                    if (POSE_GRAD) { dz[idx] = g[0]; dz[SS + idx] = g[1]; dz[2 * SS + idx] = g[2]; }
+            // Tiles go in batches: all loads of a batch are issued before the first is combined, so a warp
+            // keeps GB tiles of gathers in flight (the loads miss L1 about half the time and, for the
+            // QUAD copy that does not fit L2, DRAM a third of the time: memory-level parallelism per warp
+            // is what hides that at 16 warps per SM).
+            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2);
+            for (int t0 = 0; t0 < nt; t0 += GB) {
+                Fetch<SAMPLER, LAYOUT> fe[GB];
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    int idx = (t0 + u) * 32 + lane;
+                    if (idx < ncol) {
+                        int k = p.start + c0 + idx;
+                        fe[u].issue(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    int idx = (t0 + u) * 32 + lane;
+                    if (idx < ncol) {
+                        float g[3];
+                        float z = fe[u].template finish<POSE_GRAD>(g);
+                        zbuf[G::pad(idx + 1)] = z;
+                        if (POSE_GRAD) { dz[idx] = g[0]; dz[SS + idx] = g[1]; dz[2 * SS + idx] = g[2]; }
+                    }
                 }
             }
             __pipeline_wait_prior(0);
@@ -384,7 +411,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
         carry[0] = m2_identity();
         if (s > 0) {
             float4 c4 = __ldg((const float4*)(p.seg_prefix + (ray * p.nprefix + (s - 1)) * 4));
-            carry[0] = M2{c4.x, c4.y, c4.z, c4.w};
+            carry[0] = m2_make(c4.x, c4.y, c4.z, c4.w);
         }
         float r[G::CHUNK];
         M2 T0 = m2_identity(), E0 = m2_identity();       // sub-segment 0's chunk products and prefixes, kept for its reverse scan
@@ -518,7 +545,7 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     M2 carry = m2_identity();
     for (int s = 0; s < nseg; ++s) {
         const int c0 = s * G::SEG, ncol = min(G::SEG, Sout - c0);
-        if (lane == 0) { prefix[4 * s] = carry.a; prefix[4 * s + 1] = carry.b; prefix[4 * s + 2] = carry.c; prefix[4 * s + 3] = carry.d; }
+        if (lane == 0) { prefix[4 * s] = carry.a(); prefix[4 * s + 1] = carry.b(); prefix[4 * s + 2] = carry.c(); prefix[4 * s + 3] = carry.d(); }
         if (s + 1 == nseg) break;
         for (int idx = lane; idx < G::SEG; idx += 32) {
             int c = c0 + idx;
@@ -533,7 +560,7 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
         __syncwarp();
     }
     __syncwarp();
-    M2 vin = M2{0.f, 0.f, 0.f, 0.f};
+    M2 vin = m2_zero();
     float unused = 0.f;
     for (int s = nseg - 1; s >= 0; --s) {
         const int c0 = s * G::SEG, ncol = min(G::SEG, Sout - c0);
@@ -547,7 +574,7 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
         float r[G::CHUNK];
 #pragma unroll
         for (int i = 0; i < G::CHUNK; ++i) r[i] = rbuf[G::pad(lane * G::CHUNK + i)];
-        M2 cs = M2{prefix[4 * s], prefix[4 * s + 1], prefix[4 * s + 2], prefix[4 * s + 3]};
+        M2 cs = m2_make(prefix[4 * s], prefix[4 * s + 1], prefix[4 * s + 2], prefix[4 * s + 3]);
         vin = backward_chunk<G, LOSS_GRAD>(r, cs, vin, gbuf, nullptr, nullptr, 0.f, ncol - lane * G::CHUNK, unused, lane);
         __syncwarp();
         for (int idx = lane; idx < ncol; idx += 32) {
@@ -637,7 +664,15 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
     constexpr bool TRI = S_ == DIFFUS_SAMPLER_TRILINEAR;
 #define DIFFUS_BWD_GO(PG, VG)                                                   \
     {                                                                           \
-        auto k = render_bwd_kernel<S_, L_, P64_, PG, VG, LOSS>;                 \
+        /* the one-pass specialisation exists for float32 poses only (build time) */ \
+        if (!P64_ && p.Sout <= PREFIX_STRIDE) {                                 \
+            auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true>;      \
+            cudaError_t e = ensure_smem(k, smem);                               \
+            if (e != cudaSuccess) return e;                                     \
+            k<<<grid, threads, smem, st>>>(p);                                  \
+            return cudaGetLastError();                                          \
+        }                                                                       \
+        auto k = render_bwd_kernel<S_, L_, P64_, PG, VG, LOSS, false>;          \
         cudaError_t e = ensure_smem(k, smem);                                   \
         if (e != cudaSuccess) return e;                                         \
         k<<<grid, threads, smem, st>>>(p);                                      \

@@ -12,7 +12,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (LAYOUT_BRICK, LAYOUT_LINEAR, MLP_NPARAMS, POSE_F32, POSE_F64, SAMPLER_NEAREST,
+from ._lib import (LAYOUT_BRICK, LAYOUT_LINEAR, LAYOUT_QUAD, MLP_NPARAMS, POSE_F32, POSE_F64, SAMPLER_NEAREST,
                    SAMPLER_TRILINEAR, DiffusRenderArgs, DiffusRenderBwdArgs)
 
 SEG = 512  # PREFIX_STRIDE of csrc/common.cuh: the forward saves a 2x2 prefix every SEG columns
@@ -56,13 +56,30 @@ def _nseg(sout: int) -> int:
     return (sout + SEG - 1) // SEG
 
 
+def _packed_layout(bricks: Optional[torch.Tensor]) -> int:
+    """Layout of the packed copy handed to the ops as ``bricks``: none -> LINEAR, 1-D -> BRICK, (n, 4) -> QUAD."""
+    if bricks is None or bricks.numel() == 0:
+        return LAYOUT_LINEAR
+    return LAYOUT_QUAD if bricks.dim() == 2 else LAYOUT_BRICK
+
+
+def _grad_volume_shape(bricks: Optional[torch.Tensor], dims) -> Tuple[int, ...]:
+    """The gradient has the gathered layout (LINEAR / BRICK); a QUAD volume scatters into a BRICK buffer."""
+    layout = _packed_layout(bricks)
+    if layout == LAYOUT_LINEAR:
+        return tuple(dims)
+    if layout == LAYOUT_BRICK:
+        return (bricks.numel(),)
+    return (_lib.load().diffus_brick_elems(C.byref((C.c_int32 * 3)(*dims))),)
+
+
 def _fill_render_args(a: DiffusRenderArgs, volume, bricks, dims, sources, directions, n_samples, start, alpha,
                       sampler, product_f32):
-    use_bricks = bricks is not None and bricks.numel() > 0
-    data = bricks if use_bricks else volume
+    layout = _packed_layout(bricks)
+    data = volume if layout == LAYOUT_LINEAR else bricks
     a.volume.data = data.data_ptr()
     a.volume.dim[0], a.volume.dim[1], a.volume.dim[2] = dims
-    a.volume.layout = LAYOUT_BRICK if use_bricks else LAYOUT_LINEAR
+    a.volume.layout = layout
     a.sources = sources.data_ptr()
     a.directions = directions.data_ptr()
     a.pose_dtype = POSE_F64 if sources.dtype == torch.float64 else POSE_F32
@@ -149,7 +166,7 @@ def render_bwd_impl(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Opti
         grad_frame = grad_frame.contiguous().float()
         need_pose = need_pose and sampler == SAMPLER_TRILINEAR
         use_bricks = bricks is not None and bricks.numel() > 0
-        gshape = (bricks.numel(),) if use_bricks else tuple(dims)          # the gradient has the gathered layout
+        gshape = _grad_volume_shape(bricks, dims)
         gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else \
             torch.empty((0,), dtype=torch.float32, device=dev)
         gsrc = torch.empty((P, 3) if need_pose else (0,), dtype=torch.float32, device=dev)
@@ -290,7 +307,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         frame = torch.empty((P, R, sout), dtype=torch.float32, device=dev) if want_frame else empty()
         use_bricks = bricks is not None and bricks.numel() > 0
-        gshape = (bricks.numel(),) if use_bricks else tuple(dims)          # the gradient has the gathered layout
+        gshape = _grad_volume_shape(bricks, dims)
         gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else empty()
         gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else empty()
@@ -426,7 +443,7 @@ def trace_values_bwd(grad_values, volume, bricks, dims, sources, directions, n_s
         need_pose = need_pose and sampler == SAMPLER_TRILINEAR
         use_bricks = bricks is not None and bricks.numel() > 0
         g = grad_values.contiguous().float()
-        gvol = torch.zeros((bricks.numel(),) if use_bricks else tuple(dims), dtype=torch.float32, device=dev) \
+        gvol = torch.zeros(_grad_volume_shape(bricks, dims), dtype=torch.float32, device=dev) \
             if need_volume else None
         gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else None
         gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else None
@@ -555,6 +572,20 @@ def to_bricks(volume: torch.Tensor) -> torch.Tensor:
         out = torch.empty((lib.diffus_brick_elems(C.byref(dim)),), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_volume_to_bricks(v.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
                    "diffus_volume_to_bricks")
+        _count(1)
+    return out
+
+
+def to_quads(volume: torch.Tensor) -> torch.Tensor:
+    """LINEAR (D,H,W) float32 -> (n, 4) quad buffer: each voxel with its +p1, +p2, +p1+p2 neighbours (2x2x2 per 128 B)."""
+    dev = _require_cuda(volume)
+    lib = _lib.load()
+    v = volume.detach().contiguous().float()
+    dim = (C.c_int32 * 3)(*v.shape)
+    with torch.cuda.device(dev):
+        out = torch.empty((lib.diffus_quad_elems(C.byref(dim)) // 4, 4), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_volume_to_quads(v.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
+                   "diffus_volume_to_quads")
         _count(1)
     return out
 

@@ -52,24 +52,34 @@ def _canon_pose(source: torch.Tensor, directions: torch.Tensor, device) -> Tuple
 
 
 class PreparedVolume:
-    """A volume plus its device-side brick copy (4x4x2-voxel 128-byte bricks).
+    """A volume plus a device-side packed copy laid out for the gathers.
 
-    Gathers along a ray touch ~3x fewer cache lines per load instruction in the brick
-    layout; building it costs one pass over the volume, so it pays for pose sweeps, not for
-    a single frame.  Gradients still flow to ``volume`` (the LINEAR tensor).
+    ``layout='brick'``: 4x4x2-voxel 128-byte bricks, one float per voxel -- a ray's gathers touch ~3x fewer
+    cache lines per load instruction than in the torch layout.  ``layout='quad'``: one float4 per voxel holding
+    the voxel and its three +p1 / +p2 neighbours, so a trilinear cell is two 16-byte loads instead of eight
+    4-byte ones (4x the memory; faster only while the copy stays L2-resident).  ``'auto'`` picks ``'quad'`` up
+    to 40 MiB of packed data (about 136^3 voxels) and ``'brick'`` above.  Building the copy costs one pass over the volume, so it pays for
+    pose sweeps, not for a single frame.  Gradients still flow to ``volume`` (the LINEAR tensor).
     """
 
-    def __init__(self, volume: torch.Tensor):
+    QUAD_AUTO_MAX_BYTES = 40 << 20      # measured: once the float4 copy outgrows L2 (256^3 = 256 MiB) its random DRAM sectors lose to the L2-resident bricks
+
+    def __init__(self, volume: torch.Tensor, layout: str = "auto"):
         if volume.dim() != 3:
             raise ValueError("volume must be (D,H,W)")
+        if layout not in ("auto", "brick", "quad"):
+            raise ValueError("layout must be 'auto', 'brick' or 'quad'")
+        if layout == "auto":
+            layout = "quad" if volume.numel() * 16 <= self.QUAD_AUTO_MAX_BYTES else "brick"
+        self.layout = layout
         self.volume = volume if volume.dtype == torch.float32 else volume.float()
         self.volume = self.volume.contiguous()
         self.shape = tuple(volume.shape)
         self.refresh()
 
     def refresh(self) -> "PreparedVolume":
-        """Rebuild the brick copy (done automatically when the volume tensor was modified in place)."""
-        self._bricks = ops.to_bricks(self.volume)
+        """Rebuild the packed copy (done automatically when the volume tensor was modified in place)."""
+        self._bricks = ops.to_quads(self.volume) if self.layout == "quad" else ops.to_bricks(self.volume)
         self._version = self.volume._version
         return self
 

@@ -46,6 +46,9 @@ extern "C" {
 /* volume layout in HBM */
 #define DIFFUS_LAYOUT_LINEAR 0 /* C-contiguous [p0][p1][p2], exactly the torch tensor        */
 #define DIFFUS_LAYOUT_BRICK 1  /* 4x4x2-voxel bricks of 128 B made by diffus_volume_to_bricks */
+#define DIFFUS_LAYOUT_QUAD 2   /* one float4 per voxel = the voxel and its +p1, +p2, +p1+p2 neighbours (clamped at
+                                  the faces), 2x2x2 voxels per 128 B, made by diffus_volume_to_quads: a trilinear
+                                  cell is two 16-byte loads.  4x the footprint; read-only (see grad_volume)        */
 
 /* dtype tags for the probe pose (the reference's `points` dtype follows torch promotion,
    src/renderer.py:124, and is cast to float32 at :751) */
@@ -98,7 +101,8 @@ typedef struct DiffusRenderBwdArgs {
                                    fwd.seg_prefix = the buffer the forward filled (required
                                    when S-start > 512)                                        */
     const float* grad_frame;    /* (P,R,S-start)                                             */
-    float* grad_volume;         /* same layout as fwd.volume (LINEAR (D,H,W), or diffus_brick_elems()
+    float* grad_volume;         /* QUAD volumes: a BRICK buffer.  Otherwise the
+                                   same layout as fwd.volume (LINEAR (D,H,W), or diffus_brick_elems()
                                    floats for BRICK), ACCUMULATED into (caller zero-fills)    */
     float* grad_sources;        /* (P,3) overwritten; trilinear only                         */
     float* grad_directions;     /* (P,R,3) overwritten; trilinear only (per pose, also when
@@ -216,6 +220,9 @@ int32_t diffus_masked_zscore(const float* volume, const uint8_t* mask, int64_t n
 int64_t diffus_brick_elems(const int32_t dim[3]);
 int32_t diffus_volume_to_bricks(const float* linear, const int32_t dim[3], float* bricks, void* stream);
 int32_t diffus_bricks_to_volume(const float* bricks, const int32_t dim[3], float* linear, void* stream);
+/* LINEAR -> QUAD copy; the quad buffer holds diffus_quad_elems(dim) FLOATS (4 per padded voxel, 16-byte aligned). */
+int64_t diffus_quad_elems(const int32_t dim[3]);
+int32_t diffus_volume_to_quads(const float* linear, const int32_t dim[3], float* quads, void* stream);
 
 #ifdef __cplusplus
 }

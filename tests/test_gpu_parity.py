@@ -89,7 +89,8 @@ def test_simulate_rays_is_differentiable_like_the_reference(sampler):
 
 
 @pytest.mark.parametrize("name", NEAREST_CASES)
-def test_brick_layout_matches_linear(golden_frames, name):
+def test_packed_layouts_match_linear(golden_frames, name):
+    """BRICK and QUAD copies hold the same voxels and the kernels do the same arithmetic on them: bit-equal frames."""
     from diffus_b200 import PreparedVolume, render_frames
     g = golden_frames
     vol = torch.tensor(g[f"{name}_volume"], device=dev())
@@ -98,8 +99,9 @@ def test_brick_layout_matches_linear(golden_frames, name):
     S, alpha = int(g[f"{name}_S"]), float(g[f"{name}_alpha"])
     for sampler in ("nearest", "trilinear"):
         a = render_frames(vol, src, dirs, S, alpha, _start(g, name), sampler=sampler)
-        b = render_frames(PreparedVolume(vol), src, dirs, S, alpha, _start(g, name), sampler=sampler)
-        assert torch.equal(a, b), f"{name} {sampler}: brick layout changes the result"
+        for layout in ("brick", "quad"):
+            b = render_frames(PreparedVolume(vol, layout), src, dirs, S, alpha, _start(g, name), sampler=sampler)
+            assert torch.equal(a, b), f"{name} {sampler}: {layout} layout changes the result"
 
 
 @pytest.mark.parametrize("name", ["t0", "t1", "t2"])
@@ -219,7 +221,7 @@ def test_batched_poses_vs_oracle(sampler, S, start):
 
 
 @pytest.mark.parametrize("sampler", ["nearest", "trilinear"])
-@pytest.mark.parametrize("S,start,prepared", [(96, 0, False), (700, 0, True), (1300, 11, False)])
+@pytest.mark.parametrize("S,start,prepared", [(96, 0, None), (700, 0, "quad"), (1300, 11, None), (513, 3, "brick"), (300, 0, "quad")])
 def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
     """render_mse_loss (one fused kernel) == mse_loss(render_frames) through autograd == fp64 oracle."""
     from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
@@ -241,7 +243,7 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
         v = vol.to(dev()).requires_grad_(True)
         s = sources.to(dev()).requires_grad_(True)
         d = dirs.to(dev()).requires_grad_(True)
-        vv = PreparedVolume(v) if prepared else v
+        vv = PreparedVolume(v, prepared) if prepared else v
         if fused:
             loss, frame = render_mse_loss(vv, s, d, target, S, alpha, start, sampler=sampler, return_frame=True)
         else:
@@ -312,7 +314,8 @@ def test_randomised_configurations_vs_oracle(seed):
     S = rnd.choice([2, 3, 17, 32, 33, 64, 100, 255, 256, 257, 511, 512, 513, 700, 1024, 1100])
     start = rnd.choice([0, 0, 0, 1, S // 3, max(S - 2, 0)]) if S > 3 else 0
     sampler = rnd.choice(["nearest", "trilinear"])
-    prepared = rnd.random() < 0.5
+    u = rnd.random()
+    prepared = None if u >= 0.5 else ("brick" if u < 0.2 else "quad")
     shared = rnd.random() < 0.3
     pose64 = rnd.random() < 0.25
     alpha = rnd.choice([0.0, 1e-4, 1e-2, 0.5])
@@ -336,7 +339,7 @@ def test_randomised_configurations_vs_oracle(seed):
         v = vol.to(dev()).requires_grad_(True)
         s = src.to(pdt).to(dev()).requires_grad_(True)
         dd = d.to(pdt).to(dev()).requires_grad_(True)
-        vv = PreparedVolume(v) if prepared else v
+        vv = PreparedVolume(v, prepared) if prepared else v
         if fused:
             loss, f = render_mse_loss(vv, s, dd, tgt.to(dev()), S, alpha, start, sampler=sampler, return_frame=True)
         else:
