@@ -35,10 +35,12 @@ struct Geo {
     static constexpr int CHUNK = CH;
     static constexpr int CKPT = CK;      // backward: columns between saved prefixes
     static constexpr int SEG = 32 * CH;
-    // padded shared-memory slot: rows of CH+1 floats make the lane*CH+i pattern conflict free
-    __device__ __forceinline__ static int pad(int i) { return i + i / CH; }
-    static constexpr int ZBUF = SEG + 1 + (SEG + 1) / CH + 3;   // slots 0..SEG (slot 0 = sample c0-1)
-    static constexpr int OBUF = SEG + SEG / CH + 3;             // slots 0..SEG-1
+    // Padded shared-memory slot: one spare word per 32 columns.  Both access patterns are then conflict free:
+    // lane = consecutive column (offset constant over the 32 lanes) and lane = CH consecutive columns
+    // (slot CH*l + i sits in bank CH*(l mod 32/CH) + i + l/(32/CH): all 32 distinct).
+    __device__ __forceinline__ static int pad(int i) { return i + (i >> 5); }
+    static constexpr int ZBUF = (SEG + 2) + (SEG + 2) / 32 + 3;   // slots 0..SEG+1 (slot s = sample c0+s-1)
+    static constexpr int OBUF = (SEG + 1) + (SEG + 1) / 32 + 3;   // slots 0..SEG
 };
 using FwdGeo = Geo<16>;
 using BwdGeo = Geo<8, 2>;

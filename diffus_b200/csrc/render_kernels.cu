@@ -43,7 +43,7 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
 #pragma unroll
     for (int i = 0; i < G::CHUNK; ++i) {
         P = m2_mul_interface(P, r[i]);
-        obuf[lane * (G::CHUNK + 1) + i] = nan_to_num(echo_of(P.b(), fast_rcp(P.d())));
+        obuf[G::pad(lane * G::CHUNK) + i] = nan_to_num(echo_of(P.b(), fast_rcp(P.d())));   // i < CHUNK stays inside one 32-column block
     }
     return m2_shfl(P, 31);
 }
@@ -54,29 +54,42 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
 //               diff = frame - target, ebar = grad_scale * diff * att, accumulates diff^2
 //               and (optionally) stores the frame
 constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
+constexpr int BWD_DZ_STRIDE = FwdGeo::OBUF;   // floats between the per-axis rows of the spatial-gradient buffer
+
+// What the render kernels add to the plain echo backward: the impedances around the lane's columns, so that the
+// reverse sweep goes all the way to d loss / d Z per column and (pose gradient) to the lane's share of
+// d loss / d source and d loss / d direction -- no separate pass over the columns afterwards.
+struct ZTail {
+    const float* zbuf;     // padded; slot s = impedance of the sample before pass-column s
+    const float* dz;       // padded rows (BWD_DZ floats per axis): spatial gradient of Z per pass-column
+    int lane_col;          // first pass-column of this lane's chunk
+    float kbase;           // sample index of that column
+    unsigned skip_mask;    // bit i: column i has no direct Z dependence (column 0, or the median-replaced one)
+    float* rbar1;          // if not null, lane 0 stores rbar of its column 1 there (the median's gradient)
+    float w_after;         // weight w of the column after the segment's last one (later segment / pass), 0 if none
+    float w_first;         // out: w of the segment's first column (all lanes)
+    float acc_s[3], acc_d[3];
+};
 
 // Backward chunk phase for one segment.
 //   r[i]        coefficient of column c0 + lane*CH + i (0 where the column does not exist)
-//   gbuf        see above; on return gbuf holds d loss / d r per column
+//   gbuf        see above; on return gbuf holds d loss / d r per column (ZMODE: d loss / d Z when STORE_ZBAR)
 //   att_lane    attenuation of this lane's columns (padded table), or null for 1
 //   frame_lane  where this lane's columns of the frame go (global), or null
-//   z_lane      impedances around this lane's columns (slot j = sample before column j), or null.
-//               When given, gbuf receives w_c = 2 rbar_c / (Z_{c-1} + Z_c)^2 instead of rbar_c, so
-//               that d loss / d Z_c = w_c Z_{c-1} - w_{c+1} Z_{c+1} in the tile phase; `skip_mask`
-//               bit i set = column i has no direct Z dependence (column 0, or the median-replaced one)
-//   rbar1       if not null, lane 0 stores rbar of its column 1 there (the median's gradient)
+//   zt          ZMODE only.  With w_c = 2 rbar_c / (Z_{c-1} + Z_c)^2 (0 for skipped / missing columns),
+//               d loss / d Z_c = w_c Z_{c-1} - w_{c+1} Z_{c+1}; the lane's last column takes w_{c+1} from the
+//               next lane (one shuffle after the sweep)
 //   carry       forward prefix P through the column before the segment
 //   vin         adjoint flowing into the segment's last column from later segments
 //   ncol_lane   number of existing columns in this lane's chunk (may be <= 0 or > CHUNK)
 // returns the adjoint flowing out of the segment's first column (into the previous segment)
-template <class G_, int LOSS>
+template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
-                                             float& loss_acc, int lane, const float* z_lane = nullptr,
-                                             unsigned skip_mask = 0u, float* rbar1 = nullptr,
+                                             float& loss_acc, int lane, ZTail* zt = nullptr,
                                              const M2* known_total = nullptr, const M2* known_prefix = nullptr) {
     constexpr int CHUNK = G_::CHUNK;
-    const int base = lane * (CHUNK + 1);
+    const int base = G_::pad(lane * CHUNK);        // columns lane*CHUNK .. +CHUNK-1 share a 32-column block
     // chunk product and exclusive prefix: reuse them when the caller already ran this sweep (prefix pass)
     M2 T, P;
     if (known_total) {
@@ -133,7 +146,32 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     M2 An = m2_shfl_down(As, 1), Bn = m2_shfl_down(Bs, 1);
     M2 V = (lane == 31) ? vin : m2_add(m2_mul(vin, An), Bn);
     M2 vout = m2_add(m2_mul(vin, As), Bs);             // valid on lane 0
-    float z_hi = z_lane ? z_lane[G_::pad(CHUNK)] : 0.f;   // sample of the chunk's last column
+    // ZMODE state: impedances of the samples at columns c+1, c (slot s = sample of column s-1) and the last weight
+    const float* zl = nullptr;
+    const float* dzl = nullptr;
+    float z_hh = 0.f, z_hi = 0.f, w_prev = 0.f, part_last = 0.f, z_after = 0.f;
+    if (ZMODE) {
+        zl = zt->zbuf + G_::pad(zt->lane_col);          // slots lane_col .. lane_col+CHUNK-1: one 32-column block
+        if (POSE_GRAD) dzl = zt->dz + G_::pad(zt->lane_col);
+        z_hi = zt->zbuf[G_::pad(zt->lane_col + CHUNK)];
+        z_hh = zt->zbuf[G_::pad(zt->lane_col + CHUNK + 1)];
+        z_after = z_hh;
+    }
+    // one column's d loss / d Z: stored for the volume scatter and / or folded into the pose accumulators
+    auto emit = [&](int i, float zbar) {
+        if (!(zbar == zbar) || i >= ncol_lane) zbar = 0.f;
+        if (STORE_ZBAR) gbuf[base + i] = zbar;
+        if (POSE_GRAD) {
+            const float kf = zt->kbase + (float)i;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float ga = zbar * dzl[a * BWD_DZ_STRIDE + i];
+                if (i >= ncol_lane) ga = 0.f;             // no sample there: the buffer holds nothing
+                zt->acc_s[a] += ga;
+                zt->acc_d[a] = __fmaf_rn(kf, ga, zt->acc_d[a]);
+            }
+        }
+    };
 #pragma unroll
     for (int i = CHUNK - 1; i >= 0; --i) {
         M2 Q = Pck[i / CK];                            // prefix before column i
@@ -151,18 +189,27 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         float mc = t2.x + t2.y;
         float rbar = -4.f * r[i] * ma + mb - mc;
         rbar = (rbar == rbar) ? rbar : 0.f;
-        if (z_lane) {
-            if (rbar1 && i == 1 && lane == 0) *rbar1 = rbar;
-            float z_lo = z_lane[i];
+        if (ZMODE) {
+            if (zt->rbar1 && i == 1 && lane == 0) *zt->rbar1 = rbar;
+            float z_lo = zl[i];
             float sum = z_lo + z_hi;
             float w = 2.f * rbar * fast_rcp(sum * sum);
-            if (i >= ncol_lane || ((skip_mask >> i) & 1u)) w = 0.f;
-            gbuf[base + i] = w;
+            if (i >= ncol_lane || ((zt->skip_mask >> i) & 1u)) w = 0.f;
+            if (i == CHUNK - 1) part_last = w * z_lo;                  // its w_{c+1} lives in the next lane
+            else emit(i, w * z_lo - w_prev * z_hh);
+            z_hh = z_hi;
             z_hi = z_lo;
+            w_prev = w;
         } else {
             gbuf[base + i] = rbar;
         }
         V = m2_mul_interface_t(Pbar, r[i]);
+    }
+    if (ZMODE) {
+        float w_next = __shfl_down_sync(FULL, w_prev, 1);
+        if (lane == 31) w_next = zt->w_after;
+        emit(CHUNK - 1, part_last - w_next * z_after);
+        zt->w_first = __shfl_sync(FULL, w_prev, 0);
     }
     return m2_shfl(vout, 0);
 }
@@ -202,10 +249,11 @@ template <class G>
 __device__ __forceinline__ void chunk_reflections(const float* zbuf, int c0, int ncol, const float* median, float med,
                                                   int lane, float r[G::CHUNK], int col_off = 0) {
     const int cl = col_off + lane * G::CHUNK;
-    float zp = zbuf[G::pad(cl)];
+    const int zb = G::pad(cl);                   // slots cl .. cl+CHUNK-1 share a 32-column block
+    float zp = zbuf[zb];
 #pragma unroll
     for (int i = 0; i < G::CHUNK; ++i) {
-        float zc = zbuf[G::pad(cl + i + 1)];
+        float zc = i + 1 < G::CHUNK ? zbuf[zb + i + 1] : zbuf[G::pad(cl + G::CHUNK)];
         int c = c0 + cl + i;
         float ri = reflection(zp, zc);
         if (c == 1 && median) ri = med;
@@ -293,9 +341,10 @@ __global__ void __launch_bounds__(128, 6) render_fwd_kernel(const RenderParams p
 // backward render (optionally fused with the forward and an MSE loss)
 // ---------------------------------------------------------------------------------------
 // buffers for PREFIX_STRIDE columns in the backward's padding (rows of CHUNK+1 floats)
-constexpr int BWD_ZBUF = PREFIX_STRIDE + 1 + (PREFIX_STRIDE + 1) / BwdGeo::CHUNK + 3;
-constexpr int BWD_OBUF = PREFIX_STRIDE + PREFIX_STRIDE / BwdGeo::CHUNK + 3;
-constexpr int BWD_SMEM_PER_WARP = BWD_ZBUF + BWD_OBUF + 3 * PREFIX_STRIDE;
+constexpr int BWD_ZBUF = FwdGeo::ZBUF;          // PREFIX_STRIDE + 2 slots, padded
+constexpr int BWD_OBUF = FwdGeo::OBUF;
+constexpr int BWD_DZ = BWD_DZ_STRIDE;           // one padded row per axis
+constexpr int BWD_SMEM_PER_WARP = BWD_ZBUF + BWD_OBUF + 3 * BWD_DZ;
 
 // d loss / d volume accumulates with red.global.add.f32 (index_put_(accumulate=True) semantics) into a
 // gradient volume that has the SAME layout as the volume being gathered: in the brick layout the 32 lanes
@@ -337,7 +386,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     if (ray >= p.total_rays) return;
     float* zbuf = smem + p.att_slots_padded + warp * BWD_SMEM_PER_WARP;
     float* gbuf = zbuf + BWD_ZBUF;           // target / upstream gradient in, d loss / d r out
-    float* dz = gbuf + BWD_OBUF;             // [3][SS] spatial gradient of Z at each sample
+    float* dz = gbuf + BWD_OBUF;             // [3][BWD_DZ] spatial gradient of Z at each sample (padded rows)
     const int64_t pose = ray / p.n_rays;
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
@@ -350,7 +399,12 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
 
     M2 vin = m2_zero();
     float carry_w = 0.f, carry_z = 0.f;      // first column of the later pass: its weight w and its impedance
-    float acc_s[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
+    ZTail zt;
+    zt.zbuf = zbuf;
+    zt.dz = dz;
+    zt.rbar1 = nullptr;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) zt.acc_s[a] = zt.acc_d[a] = 0.f;
     float loss_acc = 0.f;
 
     for (int s = nss - 1; s >= 0; --s) {
@@ -372,9 +426,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             // gathers themselves was measured slower than plain loads: LDGSTS issues at a quarter of
             // the LDG rate and adds eight shared-memory reads per sample)
             // Tiles go in batches: all loads of a batch are issued before the first is combined, so a warp
-            // keeps GB tiles of gathers in flight (the loads miss L1 about half the time and, for the
-            // QUAD copy that does not fit L2, DRAM a third of the time: memory-level parallelism per warp
-            // is what hides that at 16 warps per SM).
+            // keeps GB tiles of gathers in flight.
             constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2);
             for (int t0 = 0; t0 < nt; t0 += GB) {
                 Fetch<SAMPLER, LAYOUT> fe[GB];
@@ -393,16 +445,22 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                         float g[3];
                         float z = fe[u].template finish<POSE_GRAD>(g);
                         zbuf[G::pad(idx + 1)] = z;
-                        if (POSE_GRAD) { dz[idx] = g[0]; dz[SS + idx] = g[1]; dz[2 * SS + idx] = g[2]; }
+                        if (POSE_GRAD) {
+                            const int di = G::pad(idx);
+                            dz[di] = g[0]; dz[BWD_DZ + di] = g[1]; dz[2 * BWD_DZ + di] = g[2];
+                        }
                     }
                 }
             }
             __pipeline_wait_prior(0);
         }
-        if (s > 0 && lane == 0) {            // left neighbour of the pass's first column
-            int k = p.start + c0 - 1;
-            float g[3];
-            zbuf[G::pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
+        if (lane == 0) {
+            if (s > 0) {                     // left neighbour of the pass's first column
+                int k = p.start + c0 - 1;
+                float g[3];
+                zbuf[G::pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
+            }
+            zbuf[G::pad(ncol + 1)] = carry_z;    // the sample after the pass's last column lives in the later pass
         }
         __syncwarp();
 
@@ -427,7 +485,8 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
         } else {
             carry[BWD_SUB - 1] = carry[0];
         }
-        // reverse scan, last sub-segment first
+        // reverse scan, last sub-segment first; it ends in d loss / d Z per column and the pose accumulators
+        zt.w_after = (c0 + ncol < p.Sout) ? carry_w : 0.f;
 #pragma unroll
         for (int h = BWD_SUB - 1; h >= 0; --h) {
             if (h < nsub) {
@@ -435,52 +494,37 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                 chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, off);
                 const int lane_col = off + lane * G::CHUNK;
                 // columns without a direct impedance dependence: column 0 and the median-replaced column 1
-                unsigned skip = 0u;
-                if (c0 + lane_col == 0) skip = p.median ? 3u : 1u;
-                vin = backward_chunk<G, LOSS>(r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col),
-                                              fout ? fout + c0 + lane_col : nullptr, p.grad_scale, ncol - lane_col,
-                                              loss_acc, lane, zbuf + G::pad(lane_col), skip,
-                                              (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr,
-                                              (h == 0 && have0) ? &T0 : nullptr, &E0);
+                zt.skip_mask = 0u;
+                if (c0 + lane_col == 0) zt.skip_mask = p.median ? 3u : 1u;
+                zt.lane_col = lane_col;
+                zt.kbase = (float)(p.start + c0 + lane_col);
+                zt.rbar1 = (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr;
+                vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD>(
+                    r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fout ? fout + c0 + lane_col : nullptr,
+                    p.grad_scale, ncol - lane_col, loss_acc, lane, &zt, (h == 0 && have0) ? &T0 : nullptr, &E0);
+                zt.w_after = zt.w_first;
             }
         }
+        carry_w = zt.w_first;
+        carry_z = zbuf[G::pad(1)];
         __syncwarp();
 
-        // tile phase: d loss / d Z_c = w_c Z_{c-1} - w_{c+1} Z_{c+1}, then pose partials and the volume scatter.
-        // The column after the last one lives in the later pass: park its weight and impedance in the spare slots.
-        const float next_carry_w = gbuf[G::pad(0)], next_carry_z = zbuf[G::pad(1)];
-        __syncwarp();
-        if (lane == 0) {
-            gbuf[G::pad(ncol)] = (c0 + ncol < p.Sout) ? carry_w : 0.f;
-            zbuf[G::pad(ncol + 1)] = carry_z;
-        }
-        __syncwarp();
-        for (int t = 0; t < ntile; ++t) {
-            int idx = t * 32 + lane;
-            if (idx < ncol) {
-                float zbar = gbuf[G::pad(idx)] * zbuf[G::pad(idx)] - gbuf[G::pad(idx + 1)] * zbuf[G::pad(idx + 2)];
-                if (!(zbar == zbar)) zbar = 0.f;
-                int k = p.start + c0 + idx;
-                if (POSE_GRAD) {
-                    float kf = (float)k;
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        float ga = zbar * dz[a * SS + idx];
-                        acc_s[a] += ga;
-                        acc_d[a] += kf * ga;
-                    }
+        // tile phase, only for the volume gradient: scatter d loss / d Z_c with lane = consecutive sample
+        if (VOL_GRAD) {
+            for (int t = 0; t < ntile; ++t) {
+                int idx = t * 32 + lane;
+                if (idx < ncol) {
+                    float zbar = gbuf[G::pad(idx)];
+                    if (zbar != 0.f) scatter_volume_grad<SAMPLER, LAYOUT, POSE64>(p, rs, p.start + c0 + idx, zbar);
                 }
-                if (VOL_GRAD && zbar != 0.f) scatter_volume_grad<SAMPLER, LAYOUT, POSE64>(p, rs, k, zbar);
             }
+            __syncwarp();
         }
-        carry_w = next_carry_w;
-        carry_z = next_carry_z;
-        __syncwarp();
     }
     if (POSE_GRAD) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            float ss = warp_sum(acc_s[a]), dd = warp_sum(acc_d[a]);
+            float ss = warp_sum(zt.acc_s[a]), dd = warp_sum(zt.acc_d[a]);
             if (lane == 0) {
                 p.grad_src_partial[ray * 3 + a] = ss;
                 p.grad_dir[ray * 3 + a] = dd;
