@@ -401,4 +401,13 @@ int32_t diffus_volume_to_quads(const float* linear, const int32_t dim[3], float*
     return cuda_rc(launch_to_quads(linear, dim, quads, (cudaStream_t)stream));
 }
 
+int32_t diffus_gather_probe(const float* buf, int64_t n_floats, int32_t reads_per_thread, int64_t n_threads, uint32_t seed,
+                            float* sink, void* stream) {
+    if (!buf || !sink) return DIFFUS_E_NULL;
+    if (n_floats < 8 || n_floats / 8 >= ((int64_t)1 << 32) || reads_per_thread < 8 || reads_per_thread % 8 || n_threads < 256 ||
+        n_threads % 256 || n_threads / 256 >= ((int64_t)1 << 31))
+        return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_gather_probe(buf, n_floats, reads_per_thread, n_threads, seed, sink, (cudaStream_t)stream));
+}
+
 }  // extern "C"

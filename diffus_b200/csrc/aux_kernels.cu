@@ -384,4 +384,29 @@ cudaError_t launch_to_quads(const float* linear, const int32_t dim[3], float* qu
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// roofline probe: random 32-byte-sector reads (measurement aid, include/diffus_b200.h)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_probe_kernel(const float* __restrict__ buf, uint32_t n_sectors, int reads,
+                                                           uint32_t seed, float* __restrict__ sink) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t h = (tid + 1u) * 2654435761u ^ seed;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < reads; r += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {                    // eight independent loads in flight per thread
+            h ^= h << 13; h ^= h >> 17; h ^= h << 5;     // xorshift32
+            const uint32_t sector = (uint32_t)(((uint64_t)h * n_sectors) >> 32);
+            acc[u] += __ldg(buf + (size_t)sector * 8 + (h & 7u));
+        }
+    }
+    sink[tid] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+
+cudaError_t launch_gather_probe(const float* buf, int64_t n_floats, int reads, int64_t n_threads, uint32_t seed, float* sink,
+                                cudaStream_t st) {
+    gather_probe_kernel<<<(unsigned)(n_threads / 256), 256, 0, st>>>(buf, (uint32_t)(n_floats / 8), reads, seed, sink);
+    return cudaGetLastError();
+}
+
 }  // namespace diffus

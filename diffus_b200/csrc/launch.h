@@ -64,6 +64,8 @@ cudaError_t launch_cone_directions(const double* median, int64_t n_poses, int64_
 cudaError_t launch_to_bricks(const float* linear, const int32_t dim[3], float* bricks, cudaStream_t st);
 cudaError_t launch_from_bricks(const float* bricks, const int32_t dim[3], float* linear, cudaStream_t st);
 cudaError_t launch_to_quads(const float* linear, const int32_t dim[3], float* quads, cudaStream_t st);
+cudaError_t launch_gather_probe(const float* buf, int64_t n_floats, int reads, int64_t n_threads, uint32_t seed, float* sink,
+                                cudaStream_t st);
 
 // splat_kernels.cu
 int64_t splat_workspace_bytes(int H, int W);

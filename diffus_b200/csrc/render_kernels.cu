@@ -68,7 +68,7 @@ struct ZTail {
     float* rbar1;          // if not null, lane 0 stores rbar of its column 1 there (the median's gradient)
     float w_after;         // weight w of the column after the segment's last one (later segment / pass), 0 if none
     float w_first;         // out: w of the segment's first column (all lanes)
-    float acc_s[3], acc_d[3];
+    float2 acc[3];         // per axis: (d loss / d source, d loss / d direction) partial sums of this lane
 };
 
 // Backward chunk phase for one segment.
@@ -161,15 +161,11 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     auto emit = [&](int i, float zbar) {
         if (!(zbar == zbar) || i >= ncol_lane) zbar = 0.f;
         if (STORE_ZBAR) gbuf[base + i] = zbar;
-        if (POSE_GRAD) {
-            const float kf = zt->kbase + (float)i;
+        if (POSE_GRAD) {                                  // (d/dsource, d/ddirection) += zbar dZ/dp (1, k), one packed FMA per axis
+            const float2 one_k = make_float2(1.f, zt->kbase + (float)i);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                float ga = zbar * dzl[a * BWD_DZ_STRIDE + i];
-                if (i >= ncol_lane) ga = 0.f;             // no sample there: the buffer holds nothing
-                zt->acc_s[a] += ga;
-                zt->acc_d[a] = __fmaf_rn(kf, ga, zt->acc_d[a]);
-            }
+            for (int a = 0; a < 3; ++a)                   // the gather zero-fills dz where the pass has no sample
+                zt->acc[a] = __ffma2_rn(bcast(zbar * dzl[a * BWD_DZ_STRIDE + i]), one_k, zt->acc[a]);
         }
     };
 #pragma unroll
@@ -404,7 +400,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     zt.dz = dz;
     zt.rbar1 = nullptr;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) zt.acc_s[a] = zt.acc_d[a] = 0.f;
+    for (int a = 0; a < 3; ++a) zt.acc[a] = make_float2(0.f, 0.f);
     float loss_acc = 0.f;
 
     for (int s = nss - 1; s >= 0; --s) {
@@ -449,6 +445,9 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
                             const int di = G::pad(idx);
                             dz[di] = g[0]; dz[BWD_DZ + di] = g[1]; dz[2 * BWD_DZ + di] = g[2];
                         }
+                    } else if (POSE_GRAD) {               // no sample: the reverse sweep multiplies these by zbar = 0
+                        const int di = G::pad(idx);
+                        dz[di] = 0.f; dz[BWD_DZ + di] = 0.f; dz[2 * BWD_DZ + di] = 0.f;
                     }
                 }
             }
@@ -524,7 +523,7 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
     if (POSE_GRAD) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            float ss = warp_sum(zt.acc_s[a]), dd = warp_sum(zt.acc_d[a]);
+            float ss = warp_sum(zt.acc[a].x), dd = warp_sum(zt.acc[a].y);
             if (lane == 0) {
                 p.grad_src_partial[ray * 3 + a] = ss;
                 p.grad_dir[ray * 3 + a] = dd;

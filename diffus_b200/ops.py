@@ -562,6 +562,40 @@ def cone_directions(median: torch.Tensor, opening_angle: float, n_rays: int) -> 
     return out
 
 
+def gather_probe(buffer_mib: int = 64, reads_per_thread: int = 64, n_threads: int = 148 * 8 * 256, repeats: int = 5,
+                 device: Optional[torch.device] = None) -> dict:
+    """Roofline probe: random 32-byte-sector reads over a ``buffer_mib`` MiB buffer, timed with CUDA events.
+
+    64 MiB (a 256^3 float32 volume) stays in L2 and gives the L2 -> SM random-sector rate the gather-bound march
+    competes with; a buffer well above L2 (126 MB) gives the HBM random-sector rate.  Returns sectors/s and GB/s
+    (32 bytes per sector).
+    """
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        n = buffer_mib * (1 << 20) // 4
+        buf = torch.ones((n,), dtype=torch.float32, device=dev)
+        sink = torch.empty((n_threads,), dtype=torch.float32, device=dev)
+
+        def launch(seed):
+            _lib.check(lib.diffus_gather_probe(buf.data_ptr(), n, reads_per_thread, n_threads, seed, sink.data_ptr(),
+                                               _stream(dev)), "diffus_gather_probe")
+        for w in range(3):
+            launch(w)                                     # warm-up: the buffer settles in L2 if it fits
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(repeats):
+            launch(100 + r)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / repeats
+        if abs(float(sink[0]) - reads_per_thread) > 0.5:
+            raise _lib.DiffusError("gather probe returned a wrong sum")
+    sectors = n_threads * reads_per_thread
+    return {"buffer_mib": buffer_mib, "sectors_per_launch": sectors, "ms": ms, "sectors_per_s": sectors / (ms * 1e-3),
+            "gb_per_s": sectors * 32 / (ms * 1e-3) / 1e9}
+
+
 def to_bricks(volume: torch.Tensor) -> torch.Tensor:
     """LINEAR (D,H,W) float32 -> 1-D brick buffer (4x4x2 voxels per 128-byte line)."""
     dev = _require_cuda(volume)

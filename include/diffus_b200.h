@@ -224,6 +224,13 @@ int32_t diffus_bricks_to_volume(const float* bricks, const int32_t dim[3], float
 int64_t diffus_quad_elems(const int32_t dim[3]);
 int32_t diffus_volume_to_quads(const float* linear, const int32_t dim[3], float* quads, void* stream);
 
+/* Measurement aid for the roofline, not part of the render path: every thread issues
+ * `reads_per_thread` independent 4-byte loads at pseudo-random 32-byte-sector-aligned positions of buf (n_floats
+ * floats) and stores their sum in sink[thread].  Over a 64 MiB buffer this is the L2 -> SM random-sector rate the
+ * gather-bound march competes with; over a buffer larger than L2 it is the HBM random-sector rate. */
+int32_t diffus_gather_probe(const float* buf, int64_t n_floats, int32_t reads_per_thread, int64_t n_threads,
+                            uint32_t seed, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
