@@ -106,11 +106,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("DIFFUS_B200_LIB", LIB_PATH)     # development aid: point at another build of the same ABI
+    if not os.path.exists(path):
         raise DiffusError(
-            f"{LIB_PATH} not found: the CUDA library has not been built. "
+            f"{path} not found: the CUDA library has not been built. "
             "Run `python -m diffus_b200.build` (or `__graft_entry__.build()`); there is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)            # AttributeError if the symbol is missing
         fn.restype = res

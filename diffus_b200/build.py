@@ -37,11 +37,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("DIFFUS_DEV_MINIMAL") == "1":      # kernel-development shortcut (csrc/launch.h): benchmark kernels only
+        flags.append("-DDIFFUS_DEV_MINIMAL")
     os.makedirs(BUILD, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

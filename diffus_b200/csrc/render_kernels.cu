@@ -270,7 +270,7 @@ __device__ __forceinline__ void store_prefix(const RenderParams& p, int64_t ray,
 }
 
 template <int SAMPLER, int LAYOUT, bool POSE64>
-__global__ void __launch_bounds__(128, 6) render_fwd_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p) {
     using G = FwdGeo;
     extern __shared__ float smem[];
     float* att = smem;
@@ -294,8 +294,10 @@ __global__ void __launch_bounds__(128, 6) render_fwd_kernel(const RenderParams p
         const int ncol = min(G::SEG, p.Sout - c0);
         // gather phase: lane = consecutive sample
         const int ntile = (ncol + 31) >> 5;
-        // batches of tiles: every load of a batch is issued before the first one is combined
-        constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 2;
+        // batches of tiles: every load of a batch is issued before the first one is combined.  One tile per batch for
+        // the trilinear sampler: measured, 28 resident warps (7 CTAs at 72 registers) hide the gather latency better than
+        // deeper batches at fewer warps (0.460 vs 0.470 ms per 1024 poses)
+        constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 1;
         for (int t0 = 0; t0 < ntile; t0 += GB) {
             Fetch<SAMPLER, LAYOUT> fe[GB];
 #pragma unroll
@@ -368,10 +370,10 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
 }
 
 // ONE_PASS: the ray fits one 512-column pass (every BASELINE config but the 2048-sample stress case).  The pass
-// loop disappears, so the accumulators and the adjoint carried between passes are not live during the gather:
-// that is what lets the gather batch four tiles of loads at 128 registers without spills.
+// loop disappears, so the accumulators and the adjoint carried between passes are not live during the gather; the
+// pose-only kernels then fit 96 registers and run 5 CTAs (20 warps) per SM: 0.817 -> 0.753 ms per 1024 poses.
 template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS>
-__global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_bwd_kernel(const RenderParams p) {
     using G = BwdGeo;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
     extern __shared__ float smem[];
@@ -423,7 +425,9 @@ __global__ void __launch_bounds__(128, 4) render_bwd_kernel(const RenderParams p
             // the LDG rate and adds eight shared-memory reads per sample)
             // Tiles go in batches: all loads of a batch are issued before the first is combined, so a warp
             // keeps GB tiles of gathers in flight.
-            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2);
+            // Measured on the one-pass pose kernel (96 registers, 5 CTAs = 20 warps per SM): batches of 1 / 2 / 4 tiles
+            // run 0.753 / 0.779 / 0.785 ms per 1024 poses -- the fifth CTA hides the latency, deeper batches only spill.
+            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : ((ONE_PASS && !VOL_GRAD) ? 1 : 2));
             for (int t0 = 0; t0 < nt; t0 += GB) {
                 Fetch<SAMPLER, LAYOUT> fe[GB];
 #pragma unroll
@@ -729,6 +733,9 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
 #undef DIFFUS_BWD_GO
 }
 
+// One CTA per four rays, NOT a persistent grid: a grid sized to the resident CTAs with every warp striding over the
+// rays was measured 16 % slower (0.871 vs 0.753 ms).  CTAs that start together stay in step -- all gathering (L1-bound)
+// or all sweeping (issue-bound) at once -- while the hardware's staggered CTA launches keep the two phases overlapped.
 cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, bool vol_grad,
                               cudaStream_t st) {
     int wpb = warps_per_block(p.total_rays);
