@@ -11,7 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libdiffus_b200.so")
-SOURCES = ["api.cu", "render_kernels.cu", "aux_kernels.cu", "mlp_kernels.cu", "mlp_tc_kernels.cu", "splat_kernels.cu", "preprocess_kernels.cu"]
+# (source, extra flags, object): render_kernels.cu is compiled once per volume layout (its 100+ kernel instantiations
+# are most of the build time) plus once for the dispatching entry points and the echo-only kernels
+SOURCES = [("render_kernels.cu", ["-DDIFFUS_LAYOUT_SLICE=1"], "render_kernels_brick.o"),
+           ("render_kernels.cu", ["-DDIFFUS_LAYOUT_SLICE=0"], "render_kernels_linear.o"),
+           ("render_kernels.cu", ["-DDIFFUS_LAYOUT_SLICE=2"], "render_kernels_quad.o"),
+           ("aux_kernels.cu", [], "aux_kernels.o"), ("render_kernels.cu", [], "render_kernels.o"),
+           ("api.cu", [], "api.o"), ("mlp_kernels.cu", [], "mlp_kernels.o"), ("mlp_tc_kernels.cu", [], "mlp_tc_kernels.o"),
+           ("splat_kernels.cu", [], "splat_kernels.o"), ("preprocess_kernels.cu", [], "preprocess_kernels.o")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--threads", "2"]
 
@@ -42,9 +49,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         flags.append("-DDIFFUS_DEV_MINIMAL")
     os.makedirs(BUILD, exist_ok=True)
 
-    def compile_one(src):
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(item):
+        src, extra, objname = item
+        obj = os.path.join(BUILD, objname)
+        cmd = [nvcc, *flags, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as f:
             f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -54,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -15,32 +15,47 @@ namespace diffus {
         constexpr bool P64_ = (Pv);                                        \
         __VA_ARGS__;                                                       \
     }
-// -DDIFFUS_DEV_MINIMAL: instantiate only the benchmark's kernels (trilinear, brick, float32 pose) -- a build-time
-// shortcut for looking at one kernel's SASS, never used for the shipped library.
+// The cases of one layout.  -DDIFFUS_DEV_MINIMAL instantiates only the benchmark's kernels (trilinear, float32 pose,
+// brick / quad) -- a build-time shortcut for looking at one kernel's SASS, never used for the shipped library.
+// -DDIFFUS_LAYOUT_SLICE=n keeps one layout only: render_kernels.cu is compiled once per layout, in parallel (build.py).
 #ifdef DIFFUS_DEV_MINIMAL
-#define DIFFUS_DISPATCH(...)                                                                    \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)     \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_QUAD, false, __VA_ARGS__)
+#define DIFFUS_LAYOUT_CASES(Lv, ...) DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, Lv, false, __VA_ARGS__)
 #else
-#define DIFFUS_DISPATCH(...)                                                                   \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, false, __VA_ARGS__)     \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_LINEAR, true, __VA_ARGS__)      \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, false, __VA_ARGS__)   \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_LINEAR, true, __VA_ARGS__)    \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)      \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)       \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, false, __VA_ARGS__)    \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_BRICK, true, __VA_ARGS__)     \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_QUAD, false, __VA_ARGS__)       \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, DIFFUS_LAYOUT_QUAD, true, __VA_ARGS__)        \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_QUAD, false, __VA_ARGS__)     \
-    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, DIFFUS_LAYOUT_QUAD, true, __VA_ARGS__)
+#define DIFFUS_LAYOUT_CASES(Lv, ...)                                        \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, Lv, false, __VA_ARGS__)    \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_NEAREST, Lv, true, __VA_ARGS__)     \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, Lv, false, __VA_ARGS__)  \
+    DIFFUS_DISPATCH_CASE(DIFFUS_SAMPLER_TRILINEAR, Lv, true, __VA_ARGS__)
 #endif
+#if (!defined(DIFFUS_LAYOUT_SLICE) || DIFFUS_LAYOUT_SLICE == 0) && !defined(DIFFUS_DEV_MINIMAL)
+#define DIFFUS_DISPATCH_L0(...) DIFFUS_LAYOUT_CASES(DIFFUS_LAYOUT_LINEAR, __VA_ARGS__)
+#else
+#define DIFFUS_DISPATCH_L0(...)
+#endif
+#if !defined(DIFFUS_LAYOUT_SLICE) || DIFFUS_LAYOUT_SLICE == 1
+#define DIFFUS_DISPATCH_L1(...) DIFFUS_LAYOUT_CASES(DIFFUS_LAYOUT_BRICK, __VA_ARGS__)
+#else
+#define DIFFUS_DISPATCH_L1(...)
+#endif
+#if !defined(DIFFUS_LAYOUT_SLICE) || DIFFUS_LAYOUT_SLICE == 2
+#define DIFFUS_DISPATCH_L2(...) DIFFUS_LAYOUT_CASES(DIFFUS_LAYOUT_QUAD, __VA_ARGS__)
+#else
+#define DIFFUS_DISPATCH_L2(...)
+#endif
+#define DIFFUS_DISPATCH(...) DIFFUS_DISPATCH_L0(__VA_ARGS__) DIFFUS_DISPATCH_L1(__VA_ARGS__) DIFFUS_DISPATCH_L2(__VA_ARGS__)
 
 // render_kernels.cu
 cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st);
 cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad,
                               bool vol_grad, cudaStream_t st);
+// the same for one layout each: three translation units built from render_kernels.cu with -DDIFFUS_LAYOUT_SLICE=n
+#define DIFFUS_DECLARE_SLICE(n)                                                                                        \
+    cudaError_t launch_render_fwd_layout##n(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st); \
+    cudaError_t launch_render_bwd_layout##n(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, \
+                                            bool vol_grad, cudaStream_t st);
+DIFFUS_DECLARE_SLICE(0)
+DIFFUS_DECLARE_SLICE(1)
+DIFFUS_DECLARE_SLICE(2)
 int64_t reduce_sum_workspace_bytes();
 cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, void* workspace, cudaStream_t st);
 cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* echo, cudaStream_t st);

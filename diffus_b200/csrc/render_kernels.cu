@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
     }
 }
 
+#ifndef DIFFUS_LAYOUT_SLICE
 // ---------------------------------------------------------------------------------------
 // echo-only kernels: compute_echo_traces on explicit coefficients (src/renderer.py:439-457)
 // refl (B, N) -> echo (B, N+1); column c >= 1 uses refl[c-1]
@@ -676,6 +677,8 @@ cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, floa
     return cudaGetLastError();
 }
 
+#endif  // !DIFFUS_LAYOUT_SLICE
+
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
@@ -696,7 +699,13 @@ static cudaError_t ensure_smem(K kernel, size_t smem) {
     return cudaSuccess;
 }
 
-cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st) {
+#ifdef DIFFUS_LAYOUT_SLICE
+#define DIFFUS_CAT2(a, b) a##b
+#define DIFFUS_CAT(a, b) DIFFUS_CAT2(a, b)
+#define DIFFUS_FWD_NAME DIFFUS_CAT(launch_render_fwd_layout, DIFFUS_LAYOUT_SLICE)
+#define DIFFUS_BWD_NAME DIFFUS_CAT(launch_render_bwd_layout, DIFFUS_LAYOUT_SLICE)
+
+cudaError_t DIFFUS_FWD_NAME(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st) {
     int wpb = warps_per_block(p.total_rays);
     size_t smem = ((size_t)p.att_slots + (size_t)wpb * FWD_SMEM_PER_WARP) * sizeof(float);
     unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
@@ -736,14 +745,35 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
 // One CTA per four rays, NOT a persistent grid: a grid sized to the resident CTAs with every warp striding over the
 // rays was measured 16 % slower (0.871 vs 0.753 ms).  CTAs that start together stay in step -- all gathering (L1-bound)
 // or all sweeping (issue-bound) at once -- while the hardware's staggered CTA launches keep the two phases overlapped.
-cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, bool vol_grad,
-                              cudaStream_t st) {
+cudaError_t DIFFUS_BWD_NAME(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, bool vol_grad,
+                            cudaStream_t st) {
     int wpb = warps_per_block(p.total_rays);
     size_t smem = ((size_t)p.att_slots_padded + (size_t)wpb * BWD_SMEM_PER_WARP) * sizeof(float);
     unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
     const bool mse = p.target != nullptr;
     DIFFUS_DISPATCH(if (mse) return launch_bwd_g<S_, L_, P64_, LOSS_MSE>(p, pose_grad, vol_grad, grid, wpb * 32, smem, st);
                     return launch_bwd_g<S_, L_, P64_, LOSS_GRAD>(p, pose_grad, vol_grad, grid, wpb * 32, smem, st))
+    return cudaErrorInvalidValue;
+}
+
+#else  // !DIFFUS_LAYOUT_SLICE: the dispatching entry points and the echo-only launchers
+
+cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st) {
+    switch (layout) {
+        case DIFFUS_LAYOUT_LINEAR: return launch_render_fwd_layout0(p, sampler, layout, pose64, st);
+        case DIFFUS_LAYOUT_BRICK: return launch_render_fwd_layout1(p, sampler, layout, pose64, st);
+        case DIFFUS_LAYOUT_QUAD: return launch_render_fwd_layout2(p, sampler, layout, pose64, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, bool vol_grad,
+                              cudaStream_t st) {
+    switch (layout) {
+        case DIFFUS_LAYOUT_LINEAR: return launch_render_bwd_layout0(p, sampler, layout, pose64, pose_grad, vol_grad, st);
+        case DIFFUS_LAYOUT_BRICK: return launch_render_bwd_layout1(p, sampler, layout, pose64, pose_grad, vol_grad, st);
+        case DIFFUS_LAYOUT_QUAD: return launch_render_bwd_layout2(p, sampler, layout, pose64, pose_grad, vol_grad, st);
+    }
     return cudaErrorInvalidValue;
 }
 
@@ -764,5 +794,6 @@ cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n
     echo_bwd_kernel<<<(unsigned)((n_rays + wpb - 1) / wpb), wpb * 32, smem, st>>>(refl, grad_echo, n_rays, N, grad_refl);
     return cudaGetLastError();
 }
+#endif  // DIFFUS_LAYOUT_SLICE
 
 }  // namespace diffus
