@@ -322,13 +322,22 @@ int32_t diffus_mlp_forward(const float* params, const float* x, const uint8_t* m
 
 int64_t diffus_mlp_bwd_workspace_bytes(int64_t n) { return n < 1 ? 0 : mlp_bwd_workspace_bytes(n); }
 
+int32_t diffus_mlp_backward_ex(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                               float out_scale, float* grad_params, void* workspace, int64_t workspace_bytes, int32_t path,
+                               void* stream) {
+    if (!params || !x || !grad_out || !grad_params) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    if (path < DIFFUS_MLP_PATH_AUTO || path > DIFFUS_MLP_PATH_TENSOR) return DIFFUS_E_ENUM;
+    if (!workspace || workspace_bytes < mlp_bwd_workspace_bytes(n)) return DIFFUS_E_WORKSPACE;
+    const bool tensor = path == DIFFUS_MLP_PATH_TENSOR || (path == DIFFUS_MLP_PATH_AUTO && n >= 16384);
+    return cuda_rc(launch_mlp_bwd(params, x, mask, grad_out, n, out_scale, grad_params, workspace, tensor, (cudaStream_t)stream));
+}
+
 int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
                             float out_scale, float* grad_params, void* workspace, int64_t workspace_bytes,
                             void* stream) {
-    if (!params || !x || !grad_out || !grad_params) return DIFFUS_E_NULL;
-    if (n < 1) return DIFFUS_E_SHAPE;
-    if (!workspace || workspace_bytes < mlp_bwd_workspace_bytes(n)) return DIFFUS_E_WORKSPACE;
-    return cuda_rc(launch_mlp_bwd(params, x, mask, grad_out, n, out_scale, grad_params, workspace, (cudaStream_t)stream));
+    return diffus_mlp_backward_ex(params, x, mask, grad_out, n, out_scale, grad_params, workspace, workspace_bytes,
+                                  DIFFUS_MLP_PATH_AUTO, stream);
 }
 
 int64_t diffus_splat_workspace_bytes(int32_t H, int32_t W) { return (H < 1 || W < 1) ? 0 : splat_workspace_bytes(H, W); }

@@ -744,8 +744,8 @@ def mlp_bwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Ten
         if n:
             wbytes = lib.diffus_mlp_bwd_workspace_bytes(n)
             ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
-            _lib.check(lib.diffus_mlp_backward(p.data_ptr(), xc.data_ptr(), _ptr(m), g.data_ptr(), n, out_scale,
-                                               gp.data_ptr(), ws.data_ptr(), wbytes, _stream(dev)),
+            _lib.check(lib.diffus_mlp_backward_ex(p.data_ptr(), xc.data_ptr(), _ptr(m), g.data_ptr(), n, out_scale,
+                                                  gp.data_ptr(), ws.data_ptr(), wbytes, _MLP_PATH, _stream(dev)),
                        "diffus_mlp_backward")
             _count(2)
     return gp

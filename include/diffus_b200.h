@@ -187,6 +187,12 @@ int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* 
                             const float* grad_out, int64_t n, float out_scale,
                             float* grad_params, void* workspace, int64_t workspace_bytes,
                             void* stream);
+/* Same with an explicit path (DIFFUS_MLP_PATH_*): on the tensor-core path the layer-2 recompute, d/dH1 and
+ * the dW2 / db2 reductions over voxels are 3xTF32 tcgen05.mma with TMEM accumulators. */
+int32_t diffus_mlp_backward_ex(const float* params, const float* x, const uint8_t* mask,
+                               const float* grad_out, int64_t n, float out_scale,
+                               float* grad_params, void* workspace, int64_t workspace_bytes,
+                               int32_t path, void* stream);
 
 /* Scan conversion: differentiable_splat (src/renderer.py:694-737).  c0,c1,c2 are the three coordinate
  * arrays (float32, n each -- the reference casts x, y, z to float32, :709-710), intensities n float32.

@@ -435,6 +435,33 @@ def test_mlp_tensor_core_path_matches_cuda_cores_and_oracle(n):
     np.testing.assert_allclose(tc2.cpu().numpy(), want2.numpy(), rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 300, 5000, 70001])
+def test_mlp_backward_tensor_core_path_matches_cuda_cores_and_oracle(n):
+    """Weight gradient with layer-2 recompute, d/dH1 and the dW2 / db2 reductions as 3xTF32 tcgen05.mma vs the
+    fp32 CUDA-core kernel vs fp64 autograd of the oracle."""
+    from diffus_b200 import ImpedanceEstimator, ops
+    from diffus_b200.impedance import pack_params
+    from oracle import port
+    torch.manual_seed(100 + n)
+    model = ImpedanceEstimator(1).double()
+    x = torch.randn(n) * 2.0
+    mask = torch.rand(n) > 0.2
+    gup = torch.randn(n)
+    if n > 1000:
+        gup[200:700] = 0.0                                  # whole tiles without an upstream gradient are skipped
+    out = port.mlp_forward(x.double().reshape(-1, 1), *model.parameters()).reshape(-1) * 3.0
+    (torch.where(mask, out, torch.zeros_like(out)) * gup.double()).sum().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).numpy()
+    params = pack_params(model.float()).detach().to(dev())
+    got = {}
+    for name, path in (("cc", ops.MLP_PATH_CUDA_CORES), ("tc", ops.MLP_PATH_TENSOR)):
+        with ops.mlp_path(path):
+            got[name] = ops.mlp_bwd_impl(params, x.to(dev()), mask.to(dev()), gup.to(dev()), 3.0).cpu().numpy()
+            again = ops.mlp_bwd_impl(params, x.to(dev()), mask.to(dev()), gup.to(dev()), 3.0).cpu().numpy()
+        np.testing.assert_array_equal(got[name], again)       # fixed-order reductions: run-to-run identical
+        assert_grad_close(got[name], want, f"mlp weight gradient ({name})")
+
+
 def test_mlp_volume_masked_and_large():
     from diffus_b200 import ImpedanceEstimator
     from oracle import port
