@@ -27,7 +27,11 @@ import sys
 import threading
 import time
 
-import torch
+# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed to its debug file -- stdout by default --
+# when the box sets NCCL_DEBUG) and any other NCCL log go to stderr.  Set before torch / NCCL read the environment.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
