@@ -745,3 +745,36 @@ def test_no_cpu_fallback():
     from diffus_b200._lib import DiffusError
     with pytest.raises(DiffusError):
         render_frames(torch.zeros(4, 4, 4), torch.zeros(1, 3), torch.zeros(2, 3), 8)
+
+
+def test_prepared_volume_layouts_and_auto_choice():
+    """'auto' takes the float4 QUAD copy only while it stays small against L2; every layout renders the same frame and
+    the gradient w.r.t. a QUAD volume (scattered into a BRICK buffer) equals the LINEAR one."""
+    from diffus_b200 import PreparedVolume, render_frames
+    from diffus_b200.phantoms import layered_phantom, pose_sweep
+    vol = layered_phantom(40, seed=3).to(dev())
+    assert PreparedVolume(vol).layout == "quad" and PreparedVolume(vol, "brick").layout == "brick"
+    big = torch.zeros((160, 160, 160), device=dev())
+    assert PreparedVolume(big).layout == "brick"                        # 62.5 MiB of float4 would not stay in L2
+    with pytest.raises(ValueError):
+        PreparedVolume(vol, "tiles")
+    src, dirs = pose_sweep(3, n_rays=6, n=40, seed=4)
+    src, dirs = src.to(dev()), dirs.to(dev())
+    grads = {}
+    for layout in (None, "brick", "quad"):
+        v = vol.clone().requires_grad_(True)
+        f = render_frames(PreparedVolume(v, layout) if layout else v, src, dirs, 90, 1e-3, 5, sampler="trilinear")
+        f.square().sum().backward()
+        grads[layout] = (f.detach(), v.grad)
+    for layout in ("brick", "quad"):
+        assert torch.equal(grads[layout][0], grads[None][0])
+        torch.testing.assert_close(grads[layout][1], grads[None][1], rtol=1e-5, atol=1e-12)     # atomics: order varies
+
+
+def test_gather_probe_reports_a_plausible_roof():
+    """The roofline probe of bench.py: random 32-byte sectors out of L2 are several times faster than out of HBM."""
+    from diffus_b200 import ops
+    l2 = ops.gather_probe(32, reads_per_thread=32, repeats=2)
+    hbm = ops.gather_probe(512, reads_per_thread=32, repeats=2)
+    assert l2["sectors_per_s"] > 2.0 * hbm["sectors_per_s"] > 0
+    assert 100 < hbm["gb_per_s"] < 8000 and l2["gb_per_s"] < 40000
