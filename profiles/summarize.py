@@ -3,6 +3,7 @@
 
     python profiles/summarize.py launches gpurun_out/launches.csv          > profiles/rNN_launches.md
     python profiles/summarize.py kernel   gpurun_out/prof.ncu-rep SAMPLES  > profiles/rNN_kernel.md
+    python profiles/summarize.py configs  profiles/rNN_config_results.jsonl > table for rNN_config_results.md
 
 `launches` reads the CSV of `ncu --metrics gpu__time_duration.sum`; `kernel` reads a `--set full` report
 through `ncu -i ... --page raw/source --csv` (no GPU needed) and prints the roofline-relevant counters, the
@@ -89,8 +90,28 @@ def kernel(rep, samples):
         print()
 
 
+def configs(path):
+    """Table of benchmarks/run_configs.py JSON lines."""
+    import json
+    print("| config | ms per call | Gsamples/s | frames/s | B/sample | HBM frac |\n|---|---:|---:|---:|---:|---:|")
+    for line in open(path):
+        line = line.strip()
+        if not line.startswith("{"):
+            continue
+        d = json.loads(line)
+        if "gsamples_per_s" in d:
+            print(f"| {d['config']} | {d['ms']:.4g} | {d['gsamples_per_s']:.3g} | {d['frames_per_s']:.4g} | {d['bytes_per_sample']} | {d['hbm_frac']:.3f} |")
+        else:
+            print(f"| {d['config']} | {d['ms']:.4g} | ({d['gvoxels_per_s']:.3g} Gvoxels/s, {d['tflops_layer2']:.3g} TFLOP/s layer 2) | | | |")
+        extra = {k: v for k, v in d.items() if k.startswith("mlp_")}
+        if extra:
+            print("\nInside that step: " + ", ".join(f"{k} = {v:.3g}" for k, v in extra.items()) + "\n")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "configs":
+        configs(sys.argv[2])
     else:
         kernel(sys.argv[2], float(sys.argv[3]))
