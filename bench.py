@@ -40,6 +40,7 @@ METRIC = "bmode_frames_per_s_fwd_bwd"
 UNIT = "frames/s"
 N_RAYS, N_SAMPLES, VOL_N = 128, 512, 256
 ALPHA = 1e-4
+OPENING_ANGLE = math.radians(60.0)     # pose_sweep's fan aperture
 BYTES_PER_SAMPLE_FWD = 36      # 8 trilinear gathers x 4 B + 4 B frame write
 BYTES_PER_SAMPLE_BWD = 36      # re-gather 8 x 4 B + read d loss/d frame 4 B (pose gradients only)
 BYTES_PER_SAMPLE_FUSED = 36    # fused step: 8 gathers x 4 B + 4 B target read (frames are not written)
@@ -131,17 +132,19 @@ def ncu_counter(P, layout, key):
     return None
 
 
-def build_scene(device, n_poses, seed):
+def build_scene(device, n_poses, seed, return_params=False):
     from diffus_b200.phantoms import intensity_to_impedance, mri_phantom, pose_sweep
     vol = intensity_to_impedance(mri_phantom(VOL_N, "t1", seed=0))
-    sources, dirs = pose_sweep(n_poses, N_RAYS, VOL_N, seed=seed)
+    sources, dirs, median, hint = pose_sweep(n_poses, N_RAYS, VOL_N, seed=seed, return_params=True)
+    if return_params:
+        return vol, sources, dirs, median, hint
     return vol, sources, dirs
 
 
 def run_ours(args):
     import torch.distributed as dist
     from diffus_b200 import PreparedVolume, ops, render_frames, render_mse_loss
-    from diffus_b200.graphs import GraphedPoseStep
+    from diffus_b200.graphs import GraphedFanPoseStep, GraphedPoseStep
     from diffus_b200._lib import SAMPLER_TRILINEAR
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -152,7 +155,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     P = args.poses
-    vol_h, src_h, dir_h = build_scene(dev, P, seed=1000 + rank)       # every rank: its own pose shard
+    vol_h, src_h, dir_h, med_h, hint_h = build_scene(dev, P, seed=1000 + rank, return_params=True)   # every rank: its own pose shard
     vol = PreparedVolume(vol_h.to(dev), args.layout) if args.layout != "linear" else vol_h.to(dev)
     src_pin, dir_pin = src_h.pin_memory(), dir_h.pin_memory()
     src_d, dir_d = src_h.to(dev), dir_h.to(dev)
@@ -180,12 +183,23 @@ def run_ours(args):
     out_dir = torch.empty((P, N_RAYS, 3), dtype=torch.float32).pin_memory()
     out_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
-    # a pose sweep repeats the same shapes every step: the user-facing call for that is the CUDA-graph
-    # wrapper of the fused step (diffus_b200.graphs.GraphedPoseStep); eager autograd costs ~0.15 ms more
-    gstep = GraphedPoseStep(vol, target, N_RAYS, N_SAMPLES, ALPHA) if args.e2e == "graph" else None
+    # A pose sweep repeats the same shapes every step: the user-facing call for that is a CUDA-graph wrapper of the
+    # fused step (diffus_b200.graphs); eager autograd costs ~0.15 ms more.  "fan" (default) drives the step with the
+    # pose PARAMETERS north_star names -- source, median direction, in-plane hint, aperture (9 floats per pose in, 9
+    # gradient floats + the loss out; the fans are built and their gradient folded back on the device) -- "graph" and
+    # "eager" pass explicit (P,R,3) direction tensors like the reference's plot_beam_frame.
+    gstep = fstep = None
+    poses_pin = torch.stack([src_h, med_h, hint_h]).contiguous().pin_memory()       # (3, P, 3): one H2D copy per step
+    out_pin = torch.empty((9 * P + 1,), dtype=torch.float32).pin_memory()            # gradients + loss: one D2H copy
+    if args.e2e == "graph":
+        gstep = GraphedPoseStep(vol, target, N_RAYS, N_SAMPLES, ALPHA)
+    elif args.e2e == "fan":
+        fstep = GraphedFanPoseStep(vol, target, N_RAYS, N_SAMPLES, OPENING_ANGLE, ALPHA)
 
     def step_e2e():
-        if gstep is not None:
+        if fstep is not None:
+            out_pin.copy_(fstep.packed(poses_pin), non_blocking=True)   # pose parameters in, gradients + loss out
+        elif gstep is not None:
             loss, gs, gd = gstep(src_pin, dir_pin)              # H2D of the poses into the graph's static inputs
             out_loss.copy_(loss, non_blocking=True)
             out_src.copy_(gs, non_blocking=True)
@@ -274,14 +288,18 @@ def run_ours(args):
                       "1024 poses (>> 126 MB L2, marked evict-first); the 64 MiB volume is meant to stay L2-resident",
             },
             "e2e": {"value": e2e_frames_per_s, "unit": UNIT,
-                    "h2d_bytes_per_step": int(src_pin.numel() * 4 + dir_pin.numel() * 4),
-                    "d2h_bytes_per_step": int(out_src.numel() * 4 + out_dir.numel() * 4 + 4),
+                    "h2d_bytes_per_step": int(poses_pin.numel() * 4) if args.e2e == "fan"
+                                          else int(src_pin.numel() * 4 + dir_pin.numel() * 4),
+                    "d2h_bytes_per_step": int(out_pin.numel() * 4) if args.e2e == "fan"
+                                          else int(out_src.numel() * 4 + out_dir.numel() * 4 + 4),
                     "ms_per_step": e2e_ms_total / K,
-                    "api": "GraphedPoseStep (CUDA-graph replay of the fused step)" if args.e2e == "graph"
-                           else "render_mse_loss + loss.backward() (eager autograd)",
-                    "note": "public API call per step; poses from pinned host memory each step, loss and pose gradients "
-                            "copied back to pinned host memory, stream synchronised every step; volume and target "
-                            "frames resident"},
+                    "api": {"fan": "GraphedFanPoseStep (CUDA-graph replay: fans from pose parameters -> fused step -> gradient "
+                                   "folded back onto the pose parameters)",
+                            "graph": "GraphedPoseStep (CUDA-graph replay of the fused step, explicit (P,R,3) directions)",
+                            "eager": "render_mse_loss + loss.backward() (eager autograd, explicit directions)"}[args.e2e],
+                    "note": "public API call per step; pose parameters (fan: source, median direction, in-plane hint; else "
+                            "source + explicit directions) from pinned host memory each step, loss and pose gradients copied "
+                            "back to pinned host memory, stream synchronised every step; volume and target frames resident"},
             "gpu_launches": launches,
             "kernels_ms": {"fused_step(render_bwd_kernel+reduce_rays+reduce_sum)": step_ms},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -293,6 +311,7 @@ def run_ours(args):
                          "frac_vs_two_pass_bytes": samples_per_step * 72 / (step_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,
             "loss": float(loss),
+            "loss_e2e": float(out_pin[-1]) if args.e2e == "fan" else float(out_loss),
         }
         # the L2 gather roof from our own microbenchmark (random 32-byte sectors over a 64 MiB buffer), and
         # the same over 512 MiB (HBM random sectors: what a volume copy that does not fit L2 would run at)
@@ -421,7 +440,7 @@ def main():
     ap.add_argument("--layout", default="brick", choices=["linear", "brick", "quad"])
     ap.add_argument("--cpu-rays", type=int, default=16, help="rays in the bounded CPU sample (~2 GB and ~0.5 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e", default="graph", choices=["graph", "eager"], help="public API used by the end-to-end loop")
+    ap.add_argument("--e2e", default="fan", choices=["fan", "graph", "eager"], help="public API used by the end-to-end loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -7,9 +7,10 @@ first op call loads ``libdiffus_b200.so`` and fails loudly if it has not been bu
 """
 from .cone import generate_cone_directions
 from .impedance import ImpedanceEstimator
+from .ops import fan_directions
 from .renderer import (PreparedVolume, UltrasoundRenderer, compute_echo_traces, compute_gaussian_pulse, gaussian_pulse, custom_nearest_sampler, differentiable_splat,
                        propagate_full_rays_batched, render_frames, render_mse_loss, rotate_around_apex)
 
 __all__ = ["UltrasoundRenderer", "render_frames", "render_mse_loss", "PreparedVolume", "compute_echo_traces", "compute_gaussian_pulse", "gaussian_pulse",
            "propagate_full_rays_batched", "custom_nearest_sampler", "differentiable_splat", "rotate_around_apex", "generate_cone_directions",
-           "ImpedanceEstimator"]
+           "fan_directions", "ImpedanceEstimator"]

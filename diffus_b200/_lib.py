@@ -90,6 +90,8 @@ SIGNATURES = {
     "diffus_brick_elems": (_i64, [_P(_i32 * 3)]),
     "diffus_volume_to_bricks": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
     "diffus_bricks_to_volume": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
+    "diffus_fan_directions": (_i32, [_vp, _vp, _i64, _i64, C.c_double, _vp, _vp]),
+    "diffus_fan_directions_backward": (_i32, [_vp, _vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _vp]),
     "diffus_gather_probe": (_i32, [_vp, _i64, _i32, _i64, C.c_uint32, _vp, _vp]),
     "diffus_quad_elems": (_i64, [_P(_i32 * 3)]),
     "diffus_volume_to_quads": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),

@@ -419,4 +419,19 @@ int32_t diffus_gather_probe(const float* buf, int64_t n_floats, int32_t reads_pe
     return cuda_rc(launch_gather_probe(buf, n_floats, reads_per_thread, n_threads, seed, sink, (cudaStream_t)stream));
 }
 
+int32_t diffus_fan_directions(const float* median, const float* hint, int64_t n_poses, int64_t n_rays, double opening_angle,
+                              float* out, void* stream) {
+    if (!median || !hint || !out) return DIFFUS_E_NULL;
+    if (n_poses < 1 || n_rays < 1 || n_poses >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_fan_directions(median, hint, n_poses, n_rays, opening_angle, out, (cudaStream_t)stream));
+}
+
+int32_t diffus_fan_directions_backward(const float* median, const float* hint, const float* grad_directions, int64_t n_poses,
+                                       int64_t n_rays, double opening_angle, float* grad_median, float* grad_hint, void* stream) {
+    if (!median || !hint || !grad_directions || !grad_median || !grad_hint) return DIFFUS_E_NULL;
+    if (n_poses < 1 || n_rays < 1 || n_poses >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_fan_directions_bwd(median, hint, grad_directions, n_poses, n_rays, opening_angle, grad_median, grad_hint,
+                                             (cudaStream_t)stream));
+}
+
 }  // extern "C"

@@ -409,4 +409,98 @@ cudaError_t launch_gather_probe(const float* buf, int64_t n_floats, int reads, i
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// fans in an arbitrary plane for a batch of poses, from pose PARAMETERS (north_star: "source position and
+// direction, cone aperture and ray count in"): ray i = cos(a_i) m^ + sin(a_i) u^, a = linspace(-angle/2, angle/2, R),
+// m^ = median / |median|, u^ = the normal hint made orthogonal to m^ and normalised -- generate_cone_directions
+// (src/cone.py:242-259) generalised from the z = 0 plane, float64 arithmetic and a float32 result like the reference.
+// The backward takes d loss / d directions (P,R,3) to d loss / d median and d loss / d hint.
+// ---------------------------------------------------------------------------------------
+struct FanFrame {
+    double m[3], u[3], nm, nu, hm;       // unit median, unit in-plane axis, |median|, |hint - (hint.m^) m^|, hint.m^
+};
+__device__ __forceinline__ FanFrame fan_frame(const float* median, const float* hint) {
+    FanFrame f;
+    double mx = median[0], my = median[1], mz = median[2], hx = hint[0], hy = hint[1], hz = hint[2];
+    f.nm = sqrt(mx * mx + my * my + mz * mz);
+    f.m[0] = mx / f.nm; f.m[1] = my / f.nm; f.m[2] = mz / f.nm;
+    f.hm = hx * f.m[0] + hy * f.m[1] + hz * f.m[2];
+    double ux = hx - f.hm * f.m[0], uy = hy - f.hm * f.m[1], uz = hz - f.hm * f.m[2];
+    f.nu = sqrt(ux * ux + uy * uy + uz * uz);
+    f.u[0] = ux / f.nu; f.u[1] = uy / f.nu; f.u[2] = uz / f.nu;
+    return f;
+}
+__device__ __forceinline__ double fan_angle(int64_t i, int64_t n_rays, double angle) {
+    const double lo = -angle / 2, hi = angle / 2;
+    if (n_rays <= 1) return lo;
+    return (i == n_rays - 1) ? hi : (double)i * ((hi - lo) / (double)(n_rays - 1)) + lo;
+}
+
+__global__ void fan_directions_kernel(const float* __restrict__ median, const float* __restrict__ hint, int64_t n_poses,
+                                      int64_t n_rays, double angle, float* __restrict__ out) {
+    const int64_t pose = blockIdx.x;
+    const FanFrame f = fan_frame(median + pose * 3, hint + pose * 3);
+    for (int64_t i = threadIdx.x; i < n_rays; i += blockDim.x) {
+        double sa, ca;
+        sincos(fan_angle(i, n_rays, angle), &sa, &ca);
+        float* o = out + (pose * n_rays + i) * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) o[a] = (float)(ca * f.m[a] + sa * f.u[a]);
+    }
+}
+
+__global__ void fan_directions_bwd_kernel(const float* __restrict__ median, const float* __restrict__ hint,
+                                          const float* __restrict__ grad_dirs, int64_t n_poses, int64_t n_rays, double angle,
+                                          float* __restrict__ grad_median, float* __restrict__ grad_hint) {
+    const int64_t pose = blockIdx.x;                       // one warp per pose
+    const int lane = threadIdx.x;
+    double gm[3] = {0, 0, 0}, gu[3] = {0, 0, 0};           // d loss / d m^ and d loss / d u^ (as independent vectors)
+    for (int64_t i = lane; i < n_rays; i += 32) {
+        double sa, ca;
+        sincos(fan_angle(i, n_rays, angle), &sa, &ca);
+        const float* g = grad_dirs + (pose * n_rays + i) * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { gm[a] += ca * (double)g[a]; gu[a] += sa * (double)g[a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            gm[a] += __shfl_xor_sync(FULL, gm[a], d);
+            gu[a] += __shfl_xor_sync(FULL, gu[a], d);
+        }
+    if (lane != 0) return;
+    const FanFrame f = fan_frame(median + pose * 3, hint + pose * 3);
+    // u^ = u / |u|
+    double gud = gu[0] * f.u[0] + gu[1] * f.u[1] + gu[2] * f.u[2], gv[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gv[a] = (gu[a] - gud * f.u[a]) / f.nu;              // d loss / d u
+    // u = h - (h.m^) m^
+    const double gvm = gv[0] * f.m[0] + gv[1] * f.m[1] + gv[2] * f.m[2];
+    double gmt[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double h = (double)hint[pose * 3 + a];
+        grad_hint[pose * 3 + a] = (float)(gv[a] - gvm * f.m[a]);
+        gmt[a] = gm[a] - f.hm * gv[a] - gvm * h;                                        // total d loss / d m^
+    }
+    // m^ = m / |m|
+    const double gmd = gmt[0] * f.m[0] + gmt[1] * f.m[1] + gmt[2] * f.m[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) grad_median[pose * 3 + a] = (float)((gmt[a] - gmd * f.m[a]) / f.nm);
+}
+
+cudaError_t launch_fan_directions(const float* median, const float* hint, int64_t n_poses, int64_t n_rays, double angle,
+                                  float* out, cudaStream_t st) {
+    fan_directions_kernel<<<(unsigned)n_poses, 128, 0, st>>>(median, hint, n_poses, n_rays, angle, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fan_directions_bwd(const float* median, const float* hint, const float* grad_dirs, int64_t n_poses,
+                                      int64_t n_rays, double angle, float* grad_median, float* grad_hint, cudaStream_t st) {
+    fan_directions_bwd_kernel<<<(unsigned)n_poses, 32, 0, st>>>(median, hint, grad_dirs, n_poses, n_rays, angle, grad_median,
+                                                                grad_hint);
+    return cudaGetLastError();
+}
+
 }  // namespace diffus

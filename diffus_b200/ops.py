@@ -562,6 +562,59 @@ def cone_directions(median: torch.Tensor, opening_angle: float, n_rays: int) -> 
     return out
 
 
+def fan_directions_fwd(median: torch.Tensor, hint: torch.Tensor, opening_angle: float, n_rays: int) -> torch.Tensor:
+    dev = _require_cuda(median, hint)
+    lib = _lib.load()
+    m, h = median.detach().float().contiguous(), hint.detach().float().contiguous()
+    if m.dim() != 2 or m.shape[1] != 3 or h.shape != m.shape:
+        raise _lib.DiffusError("median and hint must both be (P,3)")
+    P = m.shape[0]
+    with torch.cuda.device(dev):
+        out = torch.empty((P, n_rays, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_fan_directions(m.data_ptr(), h.data_ptr(), P, n_rays, float(opening_angle), out.data_ptr(),
+                                             _stream(dev)), "diffus_fan_directions")
+        _count(1)
+    return out
+
+
+def fan_directions_bwd(median: torch.Tensor, hint: torch.Tensor, grad_dirs: torch.Tensor, opening_angle: float,
+                       n_rays: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    dev = _require_cuda(median, hint, grad_dirs)
+    lib = _lib.load()
+    m, h = median.detach().float().contiguous(), hint.detach().float().contiguous()
+    g = grad_dirs.float().contiguous()
+    P = m.shape[0]
+    with torch.cuda.device(dev):
+        gm = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        gh = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.diffus_fan_directions_backward(m.data_ptr(), h.data_ptr(), g.data_ptr(), P, n_rays, float(opening_angle),
+                                                      gm.data_ptr(), gh.data_ptr(), _stream(dev)),
+                   "diffus_fan_directions_backward")
+        _count(1)
+    return gm, gh
+
+
+class FanDirectionsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, median, hint, opening_angle, n_rays):
+        ctx.save_for_backward(median, hint)
+        ctx.angle, ctx.n_rays = float(opening_angle), int(n_rays)
+        return fan_directions_fwd(median, hint, opening_angle, n_rays)
+
+    @staticmethod
+    def backward(ctx, grad):
+        median, hint = ctx.saved_tensors
+        gm, gh = fan_directions_bwd(median, hint, grad, ctx.angle, ctx.n_rays)
+        return gm.to(median.dtype), gh.to(hint.dtype), None, None
+
+
+def fan_directions(median: torch.Tensor, normal_hint: torch.Tensor, opening_angle: float, n_rays: int) -> torch.Tensor:
+    """Fans of a batch of poses from their parameters, on the device and differentiable: (P,3) median directions and
+    (P,3) in-plane hints -> (P,R,3) float32 unit directions ``cos(a) m^ + sin(a) u^`` -- ``generate_cone_directions``
+    (reference ``src/cone.py:242-259``) generalised from the z = 0 plane to the plane spanned by median and hint."""
+    return FanDirectionsFunction.apply(median, normal_hint, opening_angle, n_rays)
+
+
 def gather_probe(buffer_mib: int = 64, reads_per_thread: int = 64, n_threads: int = 148 * 8 * 256, repeats: int = 5,
                  device: Optional[torch.device] = None) -> dict:
     """Roofline probe: random 32-byte-sector reads over a ``buffer_mib`` MiB buffer, timed with CUDA events.

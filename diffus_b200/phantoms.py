@@ -86,10 +86,11 @@ def fan_directions(median: torch.Tensor, normal_hint: torch.Tensor, opening_angl
 
 def pose_sweep(n_poses: int, n_rays: int = 128, n: int = 256, seed: int = 0,
                opening_angle: float = math.radians(60.0), radius_frac: float = 120.0 / 256.0,
-               jitter_deg: float = 10.0):
+               jitter_deg: float = 10.0, return_params: bool = False):
     """Config 3/4/5 poses: probes on a sphere about the volume centre looking inwards.
 
-    Returns ``sources`` (P,3) float32 and ``directions`` (P,R,3) float32.
+    Returns ``sources`` (P,3) float32 and ``directions`` (P,R,3) float32; with ``return_params`` also the (P,3)
+    float32 median directions and in-plane hints the fans were built from (the inputs of ``ops.fan_directions``).
     """
     g = torch.Generator().manual_seed(seed)
     c = (n - 1) / 2.0
@@ -100,6 +101,8 @@ def pose_sweep(n_poses: int, n_rays: int = 128, n: int = 256, seed: int = 0,
     median = -v + math.tan(math.radians(jitter_deg)) * 0.5 * jit
     hint = torch.randn((n_poses, 3), generator=g, dtype=torch.float64)
     dirs = fan_directions(median, hint, opening_angle, n_rays)
+    if return_params:
+        return sources.float().contiguous(), dirs, median.float().contiguous(), hint.float().contiguous()
     return sources.float().contiguous(), dirs
 
 

@@ -163,6 +163,17 @@ int32_t diffus_echo_backward(const float* refl, const float* grad_echo, int64_t 
 int32_t diffus_cone_directions(const double* median, int64_t n_poses, int64_t n_rays,
                                double opening_angle, float* out, void* stream);
 
+/* Fans in an arbitrary plane from pose PARAMETERS: generate_cone_directions (src/cone.py:242-259) generalised from the
+ * z = 0 plane.  median (P,3) and hint (P,3) float32: m^ = median/|median|, u^ = hint made orthogonal to m^ and
+ * normalised; out (P,R,3) float32, ray i = cos(a_i) m^ + sin(a_i) u^, a = linspace(-angle/2, angle/2, R), float64
+ * arithmetic like the reference.  The backward maps d loss / d directions (P,R,3) to d loss / d median and
+ * d loss / d hint (P,3 each, overwritten), so a pose-recovery step moves 9 floats per pose instead of 3R. */
+int32_t diffus_fan_directions(const float* median, const float* hint, int64_t n_poses, int64_t n_rays,
+                              double opening_angle, float* out, void* stream);
+int32_t diffus_fan_directions_backward(const float* median, const float* hint, const float* grad_directions,
+                                       int64_t n_poses, int64_t n_rays, double opening_angle,
+                                       float* grad_median, float* grad_hint, void* stream);
+
 /* ImpedanceEstimator (src/impedance.py:6-17): Linear(1,32)-ReLU-Linear(32,32)-ReLU-Linear(32,1).
  * params is the 1153-float concatenation [W1(32x1) b1(32) W2(32x32 row-major out,in) b2(32)
  * W3(1x32) b3(1)] in nn.Linear layout.  out[i] = out_scale * mlp(x[i]); when mask != NULL

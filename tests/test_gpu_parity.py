@@ -778,3 +778,60 @@ def test_gather_probe_reports_a_plausible_roof():
     hbm = ops.gather_probe(512, reads_per_thread=32, repeats=2)
     assert l2["sectors_per_s"] > 2.0 * hbm["sectors_per_s"] > 0
     assert 100 < hbm["gb_per_s"] < 8000 and l2["gb_per_s"] < 40000
+
+
+def test_fan_directions_device_matches_host_and_autograd():
+    """Fans from pose parameters (median, in-plane hint, aperture): device forward vs the float64 host construction, and
+    the backward (d/d median, d/d hint through the normalisation and the Gram-Schmidt step) vs float64 autograd."""
+    from diffus_b200 import fan_directions
+    from diffus_b200 import phantoms
+    g = torch.Generator().manual_seed(11)
+    P, R, angle = 7, 33, 1.1
+    median = torch.randn((P, 3), generator=g) * 3.0
+    hint = torch.randn((P, 3), generator=g)
+    want = phantoms.fan_directions(median, hint, angle, R)
+    m = median.to(dev()).requires_grad_(True)
+    h = hint.to(dev()).requires_grad_(True)
+    got = fan_directions(m, h, angle, R)
+    assert got.shape == (P, R, 3) and got.dtype == torch.float32
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.numpy(), rtol=0, atol=2e-7)
+    w = torch.randn((P, R, 3), generator=g)
+    (got * w.to(dev())).sum().backward()
+    m64 = median.double().requires_grad_(True)
+    h64 = hint.double().requires_grad_(True)
+    mh = m64 / m64.norm(dim=-1, keepdim=True)
+    u = h64 - (h64 * mh).sum(-1, keepdim=True) * mh
+    u = u / u.norm(dim=-1, keepdim=True)
+    a = torch.linspace(-angle / 2, angle / 2, R, dtype=torch.float64)
+    d64 = torch.cos(a).view(1, -1, 1) * mh.unsqueeze(1) + torch.sin(a).view(1, -1, 1) * u.unsqueeze(1)
+    (d64 * w.double()).sum().backward()
+    assert_grad_close(m.grad.cpu().numpy(), m64.grad.numpy(), "d/d median", rtol=1e-5)
+    assert_grad_close(h.grad.cpu().numpy(), h64.grad.numpy(), "d/d hint", rtol=1e-5)
+    one = fan_directions(m[:1], h[:1], angle, 1)                      # a single ray sits at -angle/2 like numpy.linspace
+    np.testing.assert_allclose(one.detach().cpu().numpy()[0, 0], want.numpy()[0, 0], atol=2e-7)
+
+
+def test_graphed_fan_pose_step_matches_eager():
+    from diffus_b200 import PreparedVolume, fan_directions, render_frames, render_mse_loss
+    from diffus_b200.graphs import GraphedFanPoseStep
+    from diffus_b200.phantoms import layered_phantom, pose_sweep
+    vol = layered_phantom(32, seed=1).to(dev())
+    angle = math.radians(50.0)
+    src, dirs, med, hint = pose_sweep(5, 16, 32, seed=3, opening_angle=angle, return_params=True)
+    src, dirs, med, hint = src.to(dev()), dirs.to(dev()), med.to(dev()), hint.to(dev())
+    pv = PreparedVolume(vol, "brick")
+    with torch.no_grad():
+        target = render_frames(pv, src + 0.6, dirs, 96, 1e-3, sampler="trilinear")
+    step = GraphedFanPoseStep(pv, target, 16, 96, angle, 1e-3)
+    for shift in (0.0, 0.3):
+        s = (src + shift).clone().requires_grad_(True)
+        m = med.clone().requires_grad_(True)
+        h = hint.clone().requires_grad_(True)
+        loss = render_mse_loss(pv, s, fan_directions(m, h, angle, 16), target, 96, 1e-3)
+        loss.backward()
+        gl, gs, gm, gh = step(s.detach(), m.detach(), h.detach())
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(gl.item(), loss.item(), rtol=1e-6)
+        torch.testing.assert_close(gs, s.grad, rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(gm, m.grad, rtol=1e-5, atol=1e-12)
+        torch.testing.assert_close(gh, h.grad, rtol=1e-5, atol=1e-12)
