@@ -153,7 +153,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout must carry exactly one JSON line, and NCCL prints its banner ("NCCL version ...") to stdout when the
+        # communicator is created: point fd 1 at stderr while the process group comes up (eagerly, plus one collective)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     P = args.poses
     vol_h, src_h, dir_h, med_h, hint_h = build_scene(dev, P, seed=1000 + rank, return_params=True)   # every rank: its own pose shard
     vol = PreparedVolume(vol_h.to(dev), args.layout) if args.layout != "linear" else vol_h.to(dev)
