@@ -159,8 +159,9 @@ int64_t diffus_render_workspace_bytes(const DiffusRenderArgs* a) {
 }
 
 int32_t diffus_render_forward(const DiffusRenderArgs* a, void* stream) {
-    int32_t e = check_render(a, true);
+    int32_t e = check_render(a, a && !a->seg_prefix);      // frame may be NULL in a prefix-only run
     if (e) return e;
+    if (!a->frame && a->n_samples - a->start <= PREFIX_STRIDE) return DIFFUS_OK;   // nothing to produce
     cudaStream_t st = (cudaStream_t)stream;
     RenderParams p = pack(a);
     const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;

@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p
     const float med = p.median ? __ldg(p.median + pose) : 0.f;
     float* out = p.frame + ray * (int64_t)p.Sout;
     if (lane == 0) zbuf[0] = 0.f;
-    const int nseg = (p.Sout + G::SEG - 1) / G::SEG;
+    // without a frame to write only the prefixes entering segments 1.. are wanted: the last segment is not walked at all
+    const int nseg = (p.Sout + G::SEG - 1) / G::SEG - (p.frame ? 0 : 1);
 
     M2 carry = m2_identity();
     for (int s = 0; s < nseg; ++s) {
@@ -321,14 +322,23 @@ __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p
         // chunk phase: lane = 16 consecutive columns
         float r[G::CHUNK];
         chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r);
-        carry = forward_chunk<G>(r, carry, obuf, lane);
+        if (p.frame) {
+            carry = forward_chunk<G>(r, carry, obuf, lane);
+        } else {                                 // prefix-only run (for the fused backward of rays longer than one pass)
+            M2 T = m2_identity();
+#pragma unroll
+            for (int i = 0; i < G::CHUNK; ++i) T = m2_mul_interface(T, r[i]);
+            carry = m2_shfl(m2_mul(warp_exclusive_prefix(T, carry, lane), T), 31);
+        }
         if (p.seg_prefix && lane == 0 && c0 + G::SEG < p.Sout) store_prefix(p, ray, c0 + G::SEG, carry);
         __syncwarp();
         // tile phase: attenuate and write, lane = consecutive column
+        if (p.frame) {
 #pragma unroll 4
-        for (int t = 0; t < ntile; ++t) {
-            int idx = t * 32 + lane;
-            if (idx < ncol) __stcs(out + c0 + idx, __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]));   // streaming store: frames are write-once
+            for (int t = 0; t < ntile; ++t) {
+                int idx = t * 32 + lane;
+                if (idx < ncol) __stcs(out + c0 + idx, __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]));   // streaming store: frames are write-once
+            }
         }
         if (lane == 0) zbuf[G::pad(0)] = zbuf[G::pad(G::SEG)];   // sample c0+SEG-1 becomes the next segment's left neighbour
         __syncwarp();

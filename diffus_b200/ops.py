@@ -112,7 +112,9 @@ def _check_inputs(volume, bricks, dims, sources, directions):
 # ---------------------------------------------------------------------------------------
 def render_fwd_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
                directions: torch.Tensor, n_samples: int, start: int, alpha: float, sampler: int,
-               product_f32: bool, save_prefix: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+               product_f32: bool, save_prefix: bool, prefix_only: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``prefix_only``: only the 512-column transfer-matrix prefixes are wanted (the fused backward of long rays):
+    no frame is formed or written and the last segment is not walked."""
     dev = _require_cuda(volume, bricks, sources, directions)
     _check_inputs(volume, bricks, dims, sources, directions)
     lib = _lib.load()
@@ -121,8 +123,9 @@ def render_fwd_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
                                  product_f32)
         sout = n_samples - start
-        frame = torch.empty((P, R, max(sout, 0)), dtype=torch.float32, device=dev)
         nseg = _nseg(sout)
+        prefix_only = prefix_only and save_prefix and nseg > 1
+        frame = torch.empty((0,) if prefix_only else (P, R, max(sout, 0)), dtype=torch.float32, device=dev)
         prefix = torch.empty((P, R, nseg - 1, 4) if (save_prefix and nseg > 1) else (0,), dtype=torch.float32,
                              device=dev)
         a.frame = frame.data_ptr() if frame.numel() else None
@@ -300,7 +303,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         prefix = None
         if _nseg(sout) > 1:
             _, prefix = render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
-                                        product_f32, True)
+                                        product_f32, True, prefix_only=True)
         n = P * R * sout
         def empty():                      # outputs of a custom op must not alias each other
             return torch.empty((0,), dtype=torch.float32, device=dev)

@@ -83,7 +83,9 @@ typedef struct DiffusRenderArgs {
                                    is replaced by the lower median over that pose's rays     */
     int32_t sampler;            /* DIFFUS_SAMPLER_*                                          */
     float attenuation;          /* alpha: frame[k] = echo[k] * exp(-alpha k), k from 0 after crop */
-    float* frame;               /* out (P,R,S-start)                                         */
+    float* frame;               /* out (P,R,S-start); may be NULL when seg_prefix is given: a
+                                   prefix-only run (no frame is formed or written, the last 512-column
+                                   segment is not walked)                                       */
     float* seg_prefix;          /* out, optional: (P,R,ceil((S-start)/512)-1,4) transfer-matrix
                                    prefixes at every 512th column, consumed by the backward;
                                    may be NULL (always unused when S-start <= 512)           */
