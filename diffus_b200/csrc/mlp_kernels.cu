@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) mlp_bwd_kernel(const float* __
 __global__ void mlp_bwd_reduce_kernel(const float* __restrict__ block_partials, int n_blocks, float* __restrict__ grad_params) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= DIFFUS_MLP_NPARAMS) return;
-    float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += block_partials[(int64_t)b * DIFFUS_MLP_NPARAMS + i];
-    grad_params[i] += s;
+    double s = 0.0;                          // a few hundred partials of mixed sign: summed in double, fixed order
+    for (int b = 0; b < n_blocks; ++b) s += (double)block_partials[(int64_t)b * DIFFUS_MLP_NPARAMS + i];
+    grad_params[i] += (float)s;
 }
 
 static int mlp_bwd_blocks(int64_t n) {
