@@ -83,7 +83,7 @@ struct ZTail {
 //   vin         adjoint flowing into the segment's last column from later segments
 //   ncol_lane   number of existing columns in this lane's chunk (may be <= 0 or > CHUNK)
 // returns the adjoint flowing out of the segment's first column (into the previous segment)
-template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false>
+template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false, bool FULL = false>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
                                              float& loss_acc, int lane, ZTail* zt = nullptr,
@@ -118,7 +118,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         if (LOSS == LOSS_MSE) {
             float fr = __fmul_rn(nan_to_num(e), att);
             float diff = fr - gbuf[base + i];
-            if (i < ncol_lane) {
+            if (FULL || i < ncol_lane) {
                 loss_acc += diff * diff;
                 if (frame_lane) frame_lane[i] = fr;      // 8 consecutive floats per lane: whole 32-byte sectors
             }
@@ -126,7 +126,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         } else {
             ge = gbuf[base + i] * att;
         }
-        if (!finite || i >= ncol_lane) ge = 0.f;           // columns that do not exist: the table beyond Sout is not filled
+        if (!finite || (!FULL && i >= ncol_lane)) ge = 0.f;   // columns that do not exist: the table beyond Sout is not filled
         gbuf[base + i] = ge;
         const float2 dcol = make_float2(ge * inv, -ge * e * inv);   // D = [[0, da], [0, db]];  B += D G^T
         B.c0 = __ffma2_rn(dcol, bcast(G.b()), B.c0);
@@ -159,7 +159,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     }
     // one column's d loss / d Z: stored for the volume scatter and / or folded into the pose accumulators
     auto emit = [&](int i, float zbar) {
-        if (!(zbar == zbar) || i >= ncol_lane) zbar = 0.f;
+        if (!(zbar == zbar) || (!FULL && i >= ncol_lane)) zbar = 0.f;
         if (STORE_ZBAR) gbuf[base + i] = zbar;
         if (POSE_GRAD) {                                  // (d/dsource, d/ddirection) += zbar dZ/dp (1, k), one packed FMA per axis
             const float2 one_k = make_float2(1.f, zt->kbase + (float)i);
@@ -190,7 +190,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
             float z_lo = zl[i];
             float sum = z_lo + z_hi;
             float w = 2.f * rbar * fast_rcp(sum * sum);
-            if (i >= ncol_lane || ((zt->skip_mask >> i) & 1u)) w = 0.f;
+            if ((!FULL && i >= ncol_lane) || ((zt->skip_mask >> i) & 1u)) w = 0.f;
             if (i == CHUNK - 1) part_last = w * z_lo;                  // its w_{c+1} lives in the next lane
             else emit(i, w * z_lo - w_prev * z_hh);
             z_hh = z_hi;
@@ -241,7 +241,9 @@ __device__ __forceinline__ void fill_attenuation_padded(float* att, int Sout, fl
 }
 
 // lane's CH reflection coefficients from the padded impedance buffer (slot s holds sample c0 + s - 1)
-template <class G>
+// FULL: every column of every lane's chunk exists (the segment is complete) -- the per-column existence tests drop
+// out and only the lane that holds the ray's first two columns patches them afterwards.
+template <class G, bool FULL = false>
 __device__ __forceinline__ void chunk_reflections(const float* zbuf, int c0, int ncol, const float* median, float med,
                                                   int lane, float r[G::CHUNK], int col_off = 0) {
     const int cl = col_off + lane * G::CHUNK;
@@ -250,11 +252,18 @@ __device__ __forceinline__ void chunk_reflections(const float* zbuf, int c0, int
 #pragma unroll
     for (int i = 0; i < G::CHUNK; ++i) {
         float zc = i + 1 < G::CHUNK ? zbuf[zb + i + 1] : zbuf[G::pad(cl + G::CHUNK)];
-        int c = c0 + cl + i;
         float ri = reflection(zp, zc);
-        if (c == 1 && median) ri = med;
-        r[i] = (c >= 1 && cl + i < ncol) ? ri : 0.f;
+        if (!FULL) {
+            int c = c0 + cl + i;
+            if (c == 1 && median) ri = med;
+            ri = (c >= 1 && cl + i < ncol) ? ri : 0.f;
+        }
+        r[i] = ri;
         zp = zc;
+    }
+    if (FULL && c0 + cl == 0) {                  // column 0 has no interface; column 1 may carry the pose's median instead
+        r[0] = 0.f;
+        if (median) r[1] = med;
     }
 }
 
@@ -489,8 +498,8 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
         static_assert(BWD_SUB <= 2, "the prefix pass keeps one sub-segment's products in registers");
         const bool have0 = BWD_SUB == 2 && nsub > 1;
         if (BWD_SUB == 1) {
-        } else if (have0) {
-            chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, 0);
+        } else if (have0) {                      // sub-segment 0 is complete whenever there is a second one
+            chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, 0);
 #pragma unroll
             for (int i = 0; i < G::CHUNK; ++i) T0 = m2_mul_interface(T0, r[i]);
             E0 = warp_exclusive_prefix(T0, carry[0], lane);
@@ -504,7 +513,9 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
         for (int h = BWD_SUB - 1; h >= 0; --h) {
             if (h < nsub) {
                 const int off = h * G::SEG;
-                chunk_reflections<G>(zbuf, c0, ncol, p.median, med, lane, r, off);
+                const bool full = ncol - off >= G::SEG;          // warp-uniform: every column of this sub-segment exists
+                if (full) chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, off);
+                else chunk_reflections<G, false>(zbuf, c0, ncol, p.median, med, lane, r, off);
                 const int lane_col = off + lane * G::CHUNK;
                 // columns without a direct impedance dependence: column 0 and the median-replaced column 1
                 zt.skip_mask = 0u;
@@ -512,9 +523,16 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
                 zt.lane_col = lane_col;
                 zt.kbase = (float)(p.start + c0 + lane_col);
                 zt.rbar1 = (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr;
-                vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD>(
-                    r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fout ? fout + c0 + lane_col : nullptr,
-                    p.grad_scale, ncol - lane_col, loss_acc, lane, &zt, (h == 0 && have0) ? &T0 : nullptr, &E0);
+                const M2* kt = (h == 0 && have0) ? &T0 : nullptr;
+                float* fl = fout ? fout + c0 + lane_col : nullptr;
+                if (full)
+                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true>(
+                        r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
+                        loss_acc, lane, &zt, kt, &E0);
+                else
+                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false>(
+                        r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
+                        loss_acc, lane, &zt, kt, &E0);
                 zt.w_after = zt.w_first;
             }
         }
