@@ -308,7 +308,21 @@ __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p
         // the trilinear sampler: measured, 28 resident warps (7 CTAs at 72 registers) hide the gather latency better than
         // deeper batches at fewer warps (0.460 vs 0.470 ms per 1024 poses)
         constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 1;
-        for (int t0 = 0; t0 < ntile; t0 += GB) {
+        const int nt_full = (ncol >> 5) / GB * GB;       // batches of complete tiles run without the per-lane bounds tests
+        for (int t0 = 0; t0 < nt_full; t0 += GB) {
+            Fetch<SAMPLER, LAYOUT> fe[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                int k = p.start + c0 + (t0 + u) * 32 + lane;
+                fe[u].issue(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
+            }
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                float g[3];
+                zbuf[G::pad((t0 + u) * 32 + lane + 1)] = fe[u].template finish<false>(g);
+            }
+        }
+        for (int t0 = nt_full; t0 < ntile; t0 += GB) {
             Fetch<SAMPLER, LAYOUT> fe[GB];
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
@@ -344,9 +358,13 @@ __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p
         // tile phase: attenuate and write, lane = consecutive column
         if (p.frame) {
 #pragma unroll 4
-            for (int t = 0; t < ntile; ++t) {
+            for (int t = 0; t < (ncol >> 5); ++t) {
                 int idx = t * 32 + lane;
-                if (idx < ncol) __stcs(out + c0 + idx, __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]));   // streaming store: frames are write-once
+                __stcs(out + c0 + idx, __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]));   // streaming store: frames are write-once
+            }
+            if (ncol & 31) {
+                int idx = (ncol & ~31) + lane;
+                if (idx < ncol) __stcs(out + c0 + idx, __fmul_rn(obuf[G::pad(idx)], att[c0 + idx]));
             }
         }
         if (lane == 0) zbuf[G::pad(0)] = zbuf[G::pad(G::SEG)];   // sample c0+SEG-1 becomes the next segment's left neighbour
@@ -433,7 +451,11 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
         // memory with cp.async at the top of the pass so its latency hides behind the gathers.
         {
             const int nt = nsub * (G::SEG / 32);
-            for (int t = 0; t < nt; ++t) {
+            for (int t = 0; t < (ncol >> 5); ++t) {      // complete tiles: no bounds test
+                int idx = t * 32 + lane;
+                cp_async_stream4(gbuf + G::pad(idx), gin + c0 + idx, stream_policy);
+            }
+            for (int t = ncol >> 5; t < nt; ++t) {
                 int idx = t * 32 + lane;
                 if (idx < ncol) cp_async_stream4(gbuf + G::pad(idx), gin + c0 + idx, stream_policy);
                 else gbuf[G::pad(idx)] = 0.f;            // columns that do not exist carry no gradient
@@ -447,7 +469,28 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
             // Measured on the one-pass pose kernel (96 registers, 5 CTAs = 20 warps per SM): batches of 1 / 2 / 4 tiles
             // run 0.753 / 0.779 / 0.785 ms per 1024 poses -- the fifth CTA hides the latency, deeper batches only spill.
             constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : ((ONE_PASS && !VOL_GRAD) ? 1 : 2));
-            for (int t0 = 0; t0 < nt; t0 += GB) {
+            // batches whose tiles are all complete run without the per-lane bounds tests; the tail keeps them
+            const int nt_full = (ncol >> 5) / GB * GB;
+            for (int t0 = 0; t0 < nt_full; t0 += GB) {
+                Fetch<SAMPLER, LAYOUT> fe[GB];
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    int k = p.start + c0 + (t0 + u) * 32 + lane;
+                    fe[u].issue(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
+                }
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    int idx = (t0 + u) * 32 + lane;
+                    float g[3];
+                    float z = fe[u].template finish<POSE_GRAD>(g);
+                    zbuf[G::pad(idx + 1)] = z;
+                    if (POSE_GRAD) {
+                        const int di = G::pad(idx);
+                        dz[di] = g[0]; dz[BWD_DZ + di] = g[1]; dz[2 * BWD_DZ + di] = g[2];
+                    }
+                }
+            }
+            for (int t0 = nt_full; t0 < nt; t0 += GB) {
                 Fetch<SAMPLER, LAYOUT> fe[GB];
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
