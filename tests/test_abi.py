@@ -88,6 +88,26 @@ def test_argument_validation_without_a_device(lib):
     dim = (C.c_int32 * 3)(10, 9, 7)
     assert lib.diffus_brick_elems(C.byref(dim)) == 3 * 3 * 4 * 32
     assert lib.diffus_cone_directions(None, 1, 1, 0.5, None, None) == -1
+    # packed layouts, fans from pose parameters, the roofline probe, the explicit MLP backward path
+    assert lib.diffus_quad_elems(C.byref(dim)) == 5 * 5 * 4 * 8 * 4
+    assert lib.diffus_volume_to_quads(0x1000, C.byref(dim), 0x1008, None) == -5     # float4 loads: 16-byte alignment
+    assert lib.diffus_volume_to_quads(None, C.byref(dim), 0x1000, None) == -1
+    a2 = DiffusRenderArgs()
+    a2.volume.data, a2.volume.layout = 0x1008, 2                                   # QUAD volume not 16-byte aligned
+    a2.volume.dim[0] = a2.volume.dim[1] = a2.volume.dim[2] = 8
+    a2.sources = a2.directions = a2.frame = 0x1000
+    a2.n_poses, a2.n_rays, a2.n_samples = 1, 4, 16
+    assert lib.diffus_render_forward(C.byref(a2), None) == -5
+    a2.volume.layout = 3
+    assert lib.diffus_render_forward(C.byref(a2), None) == -3                      # unknown layout
+    a2.volume.layout, a2.frame, a2.seg_prefix = 0, None, None
+    assert lib.diffus_render_forward(C.byref(a2), None) == -1                      # no frame and no prefix buffer
+    assert lib.diffus_fan_directions(None, 0x1000, 1, 4, 0.5, 0x1000, None) == -1
+    assert lib.diffus_fan_directions(0x1000, 0x1000, 0, 4, 0.5, 0x1000, None) == -2
+    assert lib.diffus_fan_directions_backward(0x1000, 0x1000, 0x1000, 1, 4, 0.5, None, 0x1000, None) == -1
+    assert lib.diffus_gather_probe(None, 1 << 20, 64, 256, 1, 0x1000, None) == -1
+    assert lib.diffus_gather_probe(0x1000, 1 << 20, 60, 256, 1, 0x1000, None) == -2   # reads per thread: multiples of 8
+    assert lib.diffus_mlp_backward_ex(0x1000, 0x1000, None, 0x1000, 64, 1.0, 0x1000, 0x1000, 1 << 20, 9, None) == -3
 
 
 def test_library_is_sm100a_native(lib):
