@@ -466,9 +466,10 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
             // the LDG rate and adds eight shared-memory reads per sample)
             // Tiles go in batches: all loads of a batch are issued before the first is combined, so a warp
             // keeps GB tiles of gathers in flight.
-            // Measured on the one-pass pose kernel (96 registers, 5 CTAs = 20 warps per SM): batches of 1 / 2 / 4 tiles
-            // run 0.753 / 0.779 / 0.785 ms per 1024 poses -- the fifth CTA hides the latency, deeper batches only spill.
-            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : ((ONE_PASS && !VOL_GRAD) ? 1 : 2));
+            // Measured on the one-pass pose kernel (96 registers, 5 CTAs = 20 warps per SM), batches of 1 / 2 / 4 tiles:
+            // 0.701 / 0.687 / 0.705 ms per 1024 poses (before the bounds tests left the loop below, two tiles still
+            // spilled and one tile per batch was the fastest: 0.753 / 0.779 / 0.785).
+            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2);
             // batches whose tiles are all complete run without the per-lane bounds tests; the tail keeps them
             const int nt_full = (ncol >> 5) / GB * GB;
             for (int t0 = 0; t0 < nt_full; t0 += GB) {
