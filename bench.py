@@ -449,7 +449,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=1024, help="poses per GPU per step")
-    ap.add_argument("--layout", default="brick", choices=["linear", "brick", "quad"])
+    ap.add_argument("--layout", default="brick", choices=["linear", "brick", "quad", "texture"])
     ap.add_argument("--cpu-rays", type=int, default=16, help="rays in the bounded CPU sample (~2 GB and ~0.5 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e", default="fan", choices=["fan", "graph", "eager"], help="public API used by the end-to-end loop")

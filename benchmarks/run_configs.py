@@ -36,7 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3f,4,5")
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--layout", default="auto", choices=["auto", "brick", "quad"], help="packed layout of the pose-sweep volumes")
+    ap.add_argument("--layout", default="auto", choices=["auto", "brick", "quad", "texture"], help="packed layout of the pose-sweep volumes")
     args = ap.parse_args()
     from diffus_b200 import ImpedanceEstimator, PreparedVolume, UltrasoundRenderer, render_frames, render_mse_loss
     from diffus_b200.phantoms import config1_pose, intensity_to_impedance, layered_phantom, mri_phantom, pose_sweep

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libdiffus_b200.so")
 ABI_VERSION = 1
 
 SAMPLER_NEAREST, SAMPLER_TRILINEAR = 0, 1
-LAYOUT_LINEAR, LAYOUT_BRICK, LAYOUT_QUAD = 0, 1, 2
+LAYOUT_LINEAR, LAYOUT_BRICK, LAYOUT_QUAD, LAYOUT_TEXTURE = 0, 1, 2, 3
 POSE_F32, POSE_F64 = 0, 1
 MLP_NPARAMS = 1153
 
@@ -93,6 +93,9 @@ SIGNATURES = {
     "diffus_fan_directions": (_i32, [_vp, _vp, _i64, _i64, C.c_double, _vp, _vp]),
     "diffus_fan_directions_backward": (_i32, [_vp, _vp, _vp, _i64, _i64, C.c_double, _vp, _vp, _vp]),
     "diffus_gather_probe": (_i32, [_vp, _i64, _i32, _i64, C.c_uint32, _vp, _vp]),
+    "diffus_volume_texture_create": (_i32, [_vp, _P(_i32 * 3), _P(C.c_uint64), _P(C.c_uint64), _vp]),
+    "diffus_volume_texture_update": (_i32, [C.c_uint64, _vp, _P(_i32 * 3), _vp]),
+    "diffus_volume_texture_destroy": (_i32, [C.c_uint64, C.c_uint64]),
     "diffus_quad_elems": (_i64, [_P(_i32 * 3)]),
     "diffus_volume_to_quads": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
 }

@@ -1,9 +1,31 @@
 // extern "C" entry points of libdiffus_b200.so (see include/diffus_b200.h).
 // Argument validation and parameter packing only; kernels live in the other translation units.
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 #include "launch.h"
 
 using namespace diffus;
+
+namespace diffus {
+cudaError_t prepare_kernel(const void* kernel) {
+    static std::mutex mu;
+    static std::unordered_set<uint64_t> done;        // (kernel, device) pairs whose attributes are set
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t key = (uint64_t)(uintptr_t)kernel * 64u + (uint64_t)dev;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count(key)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYNAMIC_SMEM);
+    if (e != cudaSuccess) return e;
+    done.insert(key);
+    return cudaSuccess;
+}
+}  // namespace diffus
 
 namespace {
 
@@ -14,7 +36,10 @@ int32_t check_volume(const DiffusVolume& v) {
     if (v.dim[0] < 1 || v.dim[1] < 1 || v.dim[2] < 1) return DIFFUS_E_SHAPE;
     // 32-bit element offsets (also in the padded brick layout)
     if (((int64_t)v.dim[0] + 3) * ((int64_t)v.dim[1] + 3) * ((int64_t)v.dim[2] + 1) >= ((int64_t)1 << 31)) return DIFFUS_E_UNSUPPORTED;
-    if (v.layout != DIFFUS_LAYOUT_LINEAR && v.layout != DIFFUS_LAYOUT_BRICK && v.layout != DIFFUS_LAYOUT_QUAD) return DIFFUS_E_ENUM;
+    if (v.layout != DIFFUS_LAYOUT_LINEAR && v.layout != DIFFUS_LAYOUT_BRICK && v.layout != DIFFUS_LAYOUT_QUAD &&
+        v.layout != DIFFUS_LAYOUT_TEXTURE)
+        return DIFFUS_E_ENUM;
+    if (v.layout == DIFFUS_LAYOUT_TEXTURE && (v.dim[0] > 2048 || v.dim[1] > 32768 || v.dim[2] > 32768)) return DIFFUS_E_UNSUPPORTED;
     if (v.layout == DIFFUS_LAYOUT_QUAD && ((uintptr_t)v.data & 15)) return DIFFUS_E_UNSUPPORTED;   // float4 loads
     return DIFFUS_OK;
 }
@@ -32,7 +57,7 @@ int32_t check_render(const DiffusRenderArgs* a, bool need_frame) {
     if (a->start < 0 || a->start > a->n_samples - 2) return DIFFUS_E_SHAPE;
     if (a->dir_pose_stride != 0 && a->dir_pose_stride != a->n_rays * 3) return DIFFUS_E_SHAPE;
     if (a->n_poses * a->n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
-    if (a->start > 0 && a->n_rays > 12288) return DIFFUS_E_UNSUPPORTED; // median kernel keeps a pose's rays in smem
+    if (a->start > 0 && a->n_rays > 49152) return DIFFUS_E_UNSUPPORTED; // median kernel keeps a pose's rays in shared memory
     return DIFFUS_OK;
 }
 
@@ -51,6 +76,10 @@ RenderParams pack(const DiffusRenderArgs* a) {
         p.vol.sy = nqk * 8;                 // float4 units
         p.vol.sx = nqj * nqk * 8;
         p.vol.gsy = nbk * 32;               // gradients of a QUAD volume go to a BRICK buffer
+        p.vol.gsx = nbj * nbk * 32;
+    } else if (a->volume.layout == DIFFUS_LAYOUT_TEXTURE) {
+        p.vol.sx = p.vol.sy = 0;            // addressed by the texture unit
+        p.vol.gsy = nbk * 32;               // gradients go to a BRICK buffer
         p.vol.gsx = nbj * nbk * 32;
     } else {
         p.vol.gsy = p.vol.sy = (uint32_t)p.vol.W;
@@ -75,10 +104,10 @@ RenderParams pack(const DiffusRenderArgs* a) {
     return p;
 }
 
-// forward workspace (start > 0): [median float P | argmedian int32 P]
+// forward workspace (start > 0): [median float P | number of rays tied with the median, int32 P]
 struct FwdWorkspace {
     float* median;
-    int32_t* argmedian;
+    int32_t* tie_count;
     int64_t bytes;
 };
 FwdWorkspace fwd_workspace(const DiffusRenderArgs* a, void* base) {
@@ -87,7 +116,7 @@ FwdWorkspace fwd_workspace(const DiffusRenderArgs* a, void* base) {
     if (a->start > 0) {
         w.median = (float*)((char*)base + off);
         off += align_up(a->n_poses * 4, 256);
-        w.argmedian = (int32_t*)((char*)base + off);
+        w.tie_count = (int32_t*)((char*)base + off);
         off += align_up(a->n_poses * 4, 256);
     }
     w.bytes = off;
@@ -168,7 +197,7 @@ int32_t diffus_render_forward(const DiffusRenderArgs* a, void* stream) {
     if (a->start > 0) {
         FwdWorkspace w = fwd_workspace(a, a->workspace);
         if (!a->workspace || a->workspace_bytes < w.bytes) return DIFFUS_E_WORKSPACE;
-        cudaError_t ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.median, w.argmedian, st);
+        cudaError_t ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.median, w.tie_count, st);
         if (ce != cudaSuccess) return (int32_t)ce;
         p.median = w.median;
     }
@@ -199,7 +228,7 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;
     cudaError_t ce;
     if (a->start > 0) {
-        ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.fwd.median, w.fwd.argmedian, st);
+        ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.fwd.median, w.fwd.tie_count, st);
         if (ce != cudaSuccess) return (int32_t)ce;
         p.median = w.fwd.median;
         p.first_rbar = w.first_rbar;
@@ -215,7 +244,7 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     ce = launch_render_bwd(p, a->sampler, a->volume.layout, pose64, pose_grad, vol_grad, st);
     if (ce != cudaSuccess) return (int32_t)ce;
     if (a->start > 0) {
-        ce = launch_median_backward(p, a->sampler, a->volume.layout, pose64, w.fwd.argmedian, pose_grad, vol_grad, st);
+        ce = launch_median_backward(p, a->sampler, a->volume.layout, pose64, w.fwd.tie_count, pose_grad, vol_grad, st);
         if (ce != cudaSuccess) return (int32_t)ce;
     }
     if (pose_grad && b->grad_sources) {
@@ -409,6 +438,68 @@ int32_t diffus_volume_to_quads(const float* linear, const int32_t dim[3], float*
     if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
     if ((uintptr_t)quads & 15) return DIFFUS_E_UNSUPPORTED;
     return cuda_rc(launch_to_quads(linear, dim, quads, (cudaStream_t)stream));
+}
+
+// The layered array: width = dim[2] (p2, fastest), height = dim[1], layers = dim[0].
+static cudaError_t copy_linear_to_array(cudaArray_t arr, const float* linear, const int32_t dim[3], cudaStream_t st) {
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr((void*)linear, (size_t)dim[2] * sizeof(float), (size_t)dim[2], (size_t)dim[1]);
+    cp.dstArray = arr;
+    cp.extent = make_cudaExtent((size_t)dim[2], (size_t)dim[1], (size_t)dim[0]);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    return cudaMemcpy3DAsync(&cp, st);
+}
+
+int32_t diffus_volume_texture_create(const float* linear, const int32_t dim[3], uint64_t* texture_object,
+                                     uint64_t* array_handle, void* stream) {
+    if (!linear || !dim || !texture_object || !array_handle) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
+    if (dim[0] > 2048 || dim[1] > 32768 || dim[2] > 32768) return DIFFUS_E_UNSUPPORTED;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float>();
+    cudaExtent ext = make_cudaExtent((size_t)dim[2], (size_t)dim[1], (size_t)dim[0]);
+    cudaArray_t arr = nullptr;
+    cudaError_t e = cudaMalloc3DArray(&arr, &fmt, ext, cudaArrayLayered | cudaArrayTextureGather);
+    if (e != cudaSuccess) {                  // some drivers list the gather flag for plain 2-D arrays only
+        (void)cudaGetLastError();
+        e = cudaMalloc3DArray(&arr, &fmt, ext, cudaArrayLayered);
+    }
+    if (e != cudaSuccess) return (int32_t)e;
+    e = copy_linear_to_array(arr, linear, dim, (cudaStream_t)stream);
+    cudaTextureObject_t tex = 0;
+    if (e == cudaSuccess) {
+        cudaResourceDesc res = {};
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
+    }
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        return (int32_t)e;
+    }
+    *texture_object = (uint64_t)tex;
+    *array_handle = (uint64_t)(uintptr_t)arr;
+    return DIFFUS_OK;
+}
+
+int32_t diffus_volume_texture_update(uint64_t array_handle, const float* linear, const int32_t dim[3], void* stream) {
+    if (!array_handle || !linear || !dim) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(copy_linear_to_array((cudaArray_t)(uintptr_t)array_handle, linear, dim, (cudaStream_t)stream));
+}
+
+int32_t diffus_volume_texture_destroy(uint64_t texture_object, uint64_t array_handle) {
+    cudaError_t e = cudaSuccess;
+    if (texture_object) e = cudaDestroyTextureObject((cudaTextureObject_t)texture_object);
+    if (array_handle) {
+        cudaError_t e2 = cudaFreeArray((cudaArray_t)(uintptr_t)array_handle);
+        if (e == cudaSuccess) e = e2;
+    }
+    return cuda_rc(e);
 }
 
 int32_t diffus_gather_probe(const float* buf, int64_t n_floats, int32_t reads_per_thread, int64_t n_threads, uint32_t seed,

@@ -7,13 +7,30 @@ namespace diffus {
 // ---------------------------------------------------------------------------------------
 // start > 0: the first kept reflection coefficient of every ray of a pose is replaced by
 // the LOWER median over the pose's rays (torch.median), reference src/renderer.py:241-244.
-// One CTA per pose; rank by counting (R is a few hundred at most).
+// One CTA per pose.  The median is found by a 4-pass radix select over the rays' coefficients
+// held in shared memory (O(R) per pass; the first version ranked by counting, O(R^2)).
+// Besides the median the kernel records how many rays TIE with it: torch's backward of
+// `median()` spreads the gradient evenly over the tied elements (evenly_distribute_backward),
+// and ties are the common case -- a near field outside the volume clamps to the border and
+// gives r = 0 exactly on most rays.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float first_reflection(float z0, float z1) { return (z1 - z0) / (z0 + z1); }
+
+// monotone map float -> uint32 (total order; -0 sorts below +0, which only decides which zero is returned)
+__device__ __forceinline__ uint32_t radix_key(float v) {
+    uint32_t b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
 template <int SAMPLER, int LAYOUT, bool POSE64>
-__global__ void first_refl_median_kernel(const RenderParams p, float* __restrict__ median, int32_t* __restrict__ argmedian) {
+__global__ void first_refl_median_kernel(const RenderParams p, float* __restrict__ median, int32_t* __restrict__ tie_count) {
     extern __shared__ float vals[];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sel_prefix, sel_rank, any_nan, ties;
     const int64_t pose = blockIdx.x;
     const int R = (int)p.n_rays;
+    if (threadIdx.x == 0) { sel_prefix = 0u; sel_rank = (unsigned)((R - 1) / 2); any_nan = 0u; ties = 0u; }
+    __syncthreads();
     for (int ray = threadIdx.x; ray < R; ray += blockDim.x) {
         RaySetup<POSE64> rs;
         rs.load(p.sources, p.directions, pose, ray, p.n_rays, p.dir_pose_stride, p.product_f32);
@@ -21,88 +38,109 @@ __global__ void first_refl_median_kernel(const RenderParams p, float* __restrict
         int k = p.start;
         float z0 = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
         float z1 = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k + 1), rs.coord(1, k + 1), rs.coord(2, k + 1), g);
-        vals[ray] = (z1 - z0) / (z0 + z1);
+        float v = first_reflection(z0, z1);
+        vals[ray] = v;
+        if (v != v) any_nan = 1u;             // torch.median propagates NaN
     }
     __syncthreads();
-    const int target = (R - 1) / 2;
-    for (int i = threadIdx.x; i < R; i += blockDim.x) {
-        float v = vals[i];
-        if (v != v) {                     // torch.median propagates NaN
-            median[pose] = v;
-            argmedian[pose] = i;
-            continue;
-        }
-        int rank = 0, nan_seen = 0;
-        for (int j = 0; j < R; ++j) {
-            float w = vals[j];
-            nan_seen |= (w != w);
-            rank += (w < v) || (w == v && j < i);
-        }
-        if (!nan_seen && rank == target) {
-            median[pose] = v;
-            argmedian[pose] = i;
-        }
+    if (any_nan) {
+        if (threadIdx.x == 0) { median[pose] = __int_as_float(0x7fc00000); tie_count[pose] = 0; }
+        return;
     }
+    uint32_t mask = 0u;
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0u;
+        __syncthreads();
+        const uint32_t prefix = sel_prefix;
+        for (int i = threadIdx.x; i < R; i += blockDim.x) {
+            uint32_t key = radix_key(vals[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {               // 256 bins: a serial walk is shorter than a scan's barriers
+            unsigned rank = sel_rank, d = 0;
+            while (hist[d] <= rank) { rank -= hist[d]; ++d; }
+            sel_rank = rank;
+            sel_prefix = prefix | (d << (8 * pass));
+        }
+        mask |= 0xffu << (8 * pass);
+        __syncthreads();
+    }
+    const uint32_t key = sel_prefix;
+    const uint32_t bits = (key >> 31) ? (key ^ 0x80000000u) : ~key;
+    const float med = __uint_as_float(bits);
+    unsigned mine = 0;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) mine += (vals[i] == med);
+    if (mine) atomicAdd(&ties, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) { median[pose] = med; tie_count[pose] = (int32_t)ties; }
 }
 
 cudaError_t launch_first_refl_median(const RenderParams& p, int sampler, int layout, int pose64, float* median,
-                                     int32_t* argmedian, cudaStream_t st) {
+                                     int32_t* tie_count, cudaStream_t st) {
     int threads = (int)min((int64_t)256, ((p.n_rays + 31) / 32) * 32);
     size_t smem = (size_t)p.n_rays * sizeof(float);
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    DIFFUS_DISPATCH(first_refl_median_kernel<S_, L_, P64_><<<(unsigned)p.n_poses, threads, smem, st>>>(p, median, argmedian);
+    DIFFUS_DISPATCH(auto k = first_refl_median_kernel<S_, L_, P64_>;
+                    if (smem > 40 * 1024) { cudaError_t e = ensure_smem(k, smem); if (e != cudaSuccess) return e; }
+                    k<<<(unsigned)p.n_poses, threads, smem, st>>>(p, median, tie_count);
                     return cudaGetLastError())
     return cudaErrorInvalidValue;
 }
 
-// Gradient of the median replacement: the summed d loss / d r_1 of a pose flows into the
-// two impedances of the median ray's first interface.  One warp per pose; runs after the
-// main backward kernel and before the ray reduction.
+// Gradient of the median replacement: the summed d loss / d r_1 of a pose flows back through
+// `median()` -- evenly onto every ray whose own first coefficient equals the median (one ray when
+// there is no tie) -- and from there into the two impedances of that ray's first interface.
+// One warp per pose, each lane its own rays; runs after the main backward kernel and before the ray reduction.
 template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD>
-__global__ void median_backward_kernel(const RenderParams p, const int32_t* __restrict__ argmedian) {
+__global__ void median_backward_kernel(const RenderParams p, const int32_t* __restrict__ tie_count) {
     const int64_t pose = blockIdx.x;
     const int lane = threadIdx.x;
     float acc = 0.f;
     for (int64_t ray = lane; ray < p.n_rays; ray += 32) acc += p.first_rbar[pose * p.n_rays + ray];
     acc = warp_sum(acc);
-    if (lane != 0) return;
-    const int m = argmedian[pose];
-    const int64_t ray = pose * p.n_rays + m;
-    RaySetup<POSE64> rs;
-    rs.load(p.sources, p.directions, pose, m, p.n_rays, p.dir_pose_stride, p.product_f32);
-    float g0[3], g1[3];
-    int k = p.start;
-    float z0 = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g0);
-    float z1 = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k + 1), rs.coord(1, k + 1), rs.coord(2, k + 1), g1);
-    float sum = z0 + z1;
-    float zb0 = -acc * 2.f * z1 / (sum * sum), zb1 = acc * 2.f * z0 / (sum * sum);
-    if (!(zb0 == zb0)) zb0 = 0.f;
-    if (!(zb1 == zb1)) zb1 = 0.f;
-    if (POSE_GRAD) {
+    const int ties = tie_count[pose];
+    if (ties <= 0) return;                   // NaN median: no element equals it, nothing flows
+    const float med = p.median[pose];
+    acc /= (float)ties;
+    const int k = p.start;
+    for (int64_t m = lane; m < p.n_rays; m += 32) {
+        const int64_t ray = pose * p.n_rays + m;
+        RaySetup<POSE64> rs;
+        rs.load(p.sources, p.directions, pose, m, p.n_rays, p.dir_pose_stride, p.product_f32);
+        float g0[3], g1[3];
+        float z0 = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g0);
+        float z1 = sample_volume<SAMPLER, LAYOUT, POSE_GRAD>(p.vol, rs.coord(0, k + 1), rs.coord(1, k + 1), rs.coord(2, k + 1), g1);
+        if (!(first_reflection(z0, z1) == med)) continue;
+        float sum = z0 + z1;
+        float zb0 = -acc * 2.f * z1 / (sum * sum), zb1 = acc * 2.f * z0 / (sum * sum);
+        if (!(zb0 == zb0)) zb0 = 0.f;
+        if (!(zb1 == zb1)) zb1 = 0.f;
+        if (POSE_GRAD) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            p.grad_src_partial[ray * 3 + a] += zb0 * g0[a] + zb1 * g1[a];
-            p.grad_dir[ray * 3 + a] += (float)k * zb0 * g0[a] + (float)(k + 1) * zb1 * g1[a];
+            for (int a = 0; a < 3; ++a) {
+                p.grad_src_partial[ray * 3 + a] += zb0 * g0[a] + zb1 * g1[a];
+                p.grad_dir[ray * 3 + a] += (float)k * zb0 * g0[a] + (float)(k + 1) * zb1 * g1[a];
+            }
         }
-    }
-    if (VOL_GRAD) {
-        for (int which = 0; which < 2; ++which) {
-            int kk = k + which;
-            float zb = which ? zb1 : zb0;
-            float p0 = rs.coord(0, kk), p1 = rs.coord(1, kk), p2 = rs.coord(2, kk);
-            if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
-                int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
-                atomicAdd(p.grad_volume + grad_offset<LAYOUT>(p.vol, i, j, l), zb);
-            } else {
-                TriCell c;
-                tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0]);
-                tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1]);
-                tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2]);
-                uint32_t off[8];
-                tri_offsets<GradLayout<LAYOUT>::value>(p.vol, c, off);
-                for (int q = 0; q < 8; ++q) {
-                    float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
-                    if (w != 0.f) atomicAdd(p.grad_volume + off[q], w * zb);
+        if (VOL_GRAD) {
+            for (int which = 0; which < 2; ++which) {
+                int kk = k + which;
+                float zb = which ? zb1 : zb0;
+                float p0 = rs.coord(0, kk), p1 = rs.coord(1, kk), p2 = rs.coord(2, kk);
+                if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+                    int i = nearest_index(p0, p.vol.D), j = nearest_index(p1, p.vol.H), l = nearest_index(p2, p.vol.W);
+                    atomicAdd(p.grad_volume + grad_offset<LAYOUT>(p.vol, i, j, l), zb);
+                } else {
+                    TriCell c;
+                    tri_axis(p0, p.vol.D, c.i0[0], c.i1[0], c.f[0]);
+                    tri_axis(p1, p.vol.H, c.i0[1], c.i1[1], c.f[1]);
+                    tri_axis(p2, p.vol.W, c.i0[2], c.i1[2], c.f[2]);
+                    uint32_t off[8];
+                    tri_offsets<GradLayout<LAYOUT>::value>(p.vol, c, off);
+                    for (int q = 0; q < 8; ++q) {
+                        float w = ((q & 4) ? c.f[0] : 1.f - c.f[0]) * ((q & 2) ? c.f[1] : 1.f - c.f[1]) * ((q & 1) ? c.f[2] : 1.f - c.f[2]);
+                        if (w != 0.f) atomicAdd(p.grad_volume + off[q], w * zb);
+                    }
                 }
             }
         }
@@ -110,9 +148,9 @@ __global__ void median_backward_kernel(const RenderParams p, const int32_t* __re
 }
 
 cudaError_t launch_median_backward(const RenderParams& p, int sampler, int layout, int pose64,
-                                   const int32_t* argmedian, bool pose_grad, bool vol_grad, cudaStream_t st) {
+                                   const int32_t* tie_count, bool pose_grad, bool vol_grad, cudaStream_t st) {
     if (sampler == DIFFUS_SAMPLER_NEAREST) pose_grad = false;
-#define DIFFUS_MB(PG, VG) median_backward_kernel<S_, L_, P64_, PG, VG><<<(unsigned)p.n_poses, 32, 0, st>>>(p, argmedian)
+#define DIFFUS_MB(PG, VG) median_backward_kernel<S_, L_, P64_, PG, VG><<<(unsigned)p.n_poses, 32, 0, st>>>(p, tie_count)
     DIFFUS_DISPATCH(if (pose_grad && vol_grad) DIFFUS_MB(true, true); else if (pose_grad) DIFFUS_MB(true, false);
                     else DIFFUS_MB(false, true); return cudaGetLastError())
 #undef DIFFUS_MB

@@ -115,6 +115,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 //           two 16-byte loads (i0 and i1) instead of eight 4-byte ones: a quarter of the load instructions
 //           and L1 tag look-ups for four times the footprint.  Read-only: gradients w.r.t. a QUAD volume
 //           are scattered into a BRICK buffer (gsx / gsy below).
+//   TEXTURE a layered 2-D CUDA array (layer = p0, y = p1, x = p2) behind a texture object with clamp addressing and
+//           point sampling.  A trilinear cell is two `tld4` gathers (the 2x2 (p1, p2) footprint of layer i0 and of
+//           layer i1, unfiltered fp32 texels): the texture unit does the address arithmetic and the border clamp,
+//           the footprint stays 1x (L2-resident at 256^3, unlike QUAD), and the gathers leave the LSU pipe.
+//           `data` carries the cudaTextureObject_t.  Read-only: gradients go to a BRICK buffer like QUAD's.
 // ---------------------------------------------------------------------------------------
 struct VolumeView {
     const float* data;
@@ -128,7 +133,26 @@ constexpr int QUAD_B = 2;                              // 2x2x2 float4 = one 128
 
 // layout of the gradient volume that belongs to a gathered layout
 template <int LAYOUT>
-struct GradLayout { static constexpr int value = LAYOUT == DIFFUS_LAYOUT_QUAD ? DIFFUS_LAYOUT_BRICK : LAYOUT; };
+struct GradLayout {
+    static constexpr int value = (LAYOUT == DIFFUS_LAYOUT_QUAD || LAYOUT == DIFFUS_LAYOUT_TEXTURE) ? DIFFUS_LAYOUT_BRICK : LAYOUT;
+};
+
+// texel fetches of the TEXTURE layout (x = p2, y = p1, layer = p0; unnormalised coordinates, texel centres at +0.5)
+__device__ __forceinline__ cudaTextureObject_t volume_texture(const void* data) { return (cudaTextureObject_t)(uintptr_t)data; }
+// the 2x2 footprint whose lower corner is texel (x0, y0) of `layer`, as (y0x0, y1x0, y0x1, y1x1): tld4 picks the four
+// texels bilinear filtering at (x0 + 1, y0 + 1) would blend -- (x0, y1), (x1, y1), (x1, y0), (x0, y0) in .x .y .z .w --
+// and the clamp addressing mode supplies min(x0 + 1, n - 1), the sampler's own border rule
+__device__ __forceinline__ float4 tex_gather_cell(cudaTextureObject_t tex, int layer, float x0, float y0) {
+    float4 r;
+    const float x = x0 + 1.0f, y = y0 + 1.0f;
+    asm volatile("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(tex), "r"(layer), "f"(x), "f"(y));
+    return make_float4(r.w, r.x, r.z, r.y);
+}
+__device__ __forceinline__ float tex_fetch_voxel(cudaTextureObject_t tex, int i, int j, int k) {
+    return tex2DLayered<float>(tex, (float)k + 0.5f, (float)j + 0.5f, i);
+}
 
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t axis_x(uint32_t sx, int i) {
@@ -242,6 +266,15 @@ __device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float
     i1 = min(i0 + 1, n - 1);
 }
 
+// the same cell with the lower index left as a float (texture coordinates are floats: no conversion)
+__device__ __forceinline__ void tri_axis_f(float p, int n, float& fl, float& f) {
+    float hi = (float)(n - 1);
+    bool inside = (p > 0.f) && (p < hi);
+    float pc = fminf(fmaxf(p, 0.f), hi);
+    fl = floorf(pc);
+    f = inside ? pc - fl : -0.f;
+}
+
 // offsets of the eight corners in the layout of the GRADIENT volume (also the gathered one for LINEAR / BRICK)
 template <int GLAYOUT>
 __device__ __forceinline__ void tri_offsets(const VolumeView& v, const TriCell& c, uint32_t off[8]) {
@@ -286,8 +319,21 @@ struct Fetch {
     __device__ __forceinline__ void issue(const VolumeView& v, float p0, float p1, float p2) {
         if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
             int i = nearest_index(p0, v.D), j = nearest_index(p1, v.H), k = nearest_index(p2, v.W);
-            const uint32_t off = voxel_offset<LAYOUT>(v, i, j, k);
-            q0.x = __ldg(v.data + (LAYOUT == DIFFUS_LAYOUT_QUAD ? (size_t)off * 4 : (size_t)off));
+            if (LAYOUT == DIFFUS_LAYOUT_TEXTURE) {
+                q0.x = tex_fetch_voxel(volume_texture(v.data), i, j, k);
+            } else {
+                const uint32_t off = voxel_offset<LAYOUT>(v, i, j, k);
+                q0.x = __ldg(v.data + (LAYOUT == DIFFUS_LAYOUT_QUAD ? (size_t)off * 4 : (size_t)off));
+            }
+        } else if (LAYOUT == DIFFUS_LAYOUT_TEXTURE) {
+            int i0, i1;
+            float y0, x0;
+            tri_axis(p0, v.D, i0, i1, f[0]);
+            tri_axis_f(p1, v.H, y0, f[1]);
+            tri_axis_f(p2, v.W, x0, f[2]);
+            const cudaTextureObject_t tex = volume_texture(v.data);
+            q0 = tex_gather_cell(tex, i0, x0, y0);
+            q1 = tex_gather_cell(tex, i1, x0, y0);
         } else {
             TriCell c;
             tri_axis(p0, v.D, c.i0[0], c.i1[0], f[0]);

@@ -42,13 +42,30 @@ namespace diffus {
 #else
 #define DIFFUS_DISPATCH_L2(...)
 #endif
-#define DIFFUS_DISPATCH(...) DIFFUS_DISPATCH_L0(__VA_ARGS__) DIFFUS_DISPATCH_L1(__VA_ARGS__) DIFFUS_DISPATCH_L2(__VA_ARGS__)
+#if !defined(DIFFUS_LAYOUT_SLICE) || DIFFUS_LAYOUT_SLICE == 3
+#define DIFFUS_DISPATCH_L3(...) DIFFUS_LAYOUT_CASES(DIFFUS_LAYOUT_TEXTURE, __VA_ARGS__)
+#else
+#define DIFFUS_DISPATCH_L3(...)
+#endif
+#define DIFFUS_DISPATCH(...) \
+    DIFFUS_DISPATCH_L0(__VA_ARGS__) DIFFUS_DISPATCH_L1(__VA_ARGS__) DIFFUS_DISPATCH_L2(__VA_ARGS__) DIFFUS_DISPATCH_L3(__VA_ARGS__)
+
+// api.cu: kernel attributes are set ONCE per (kernel, device), not on every launch: the largest shared-memory carveout
+// and the full 227 KB of opt-in dynamic shared memory.  Two host threads launching the same kernel with different
+// sizes can then never lower each other's limit, and the ~2 x 3 us of cudaFuncSetAttribute leave the launch path.
+constexpr size_t MAX_DYNAMIC_SMEM = 227 * 1024;
+cudaError_t prepare_kernel(const void* kernel);
+template <typename K>
+static inline cudaError_t ensure_smem(K kernel, size_t smem) {
+    if (smem > MAX_DYNAMIC_SMEM) return cudaErrorInvalidValue;
+    return prepare_kernel((const void*)kernel);
+}
 
 // render_kernels.cu
 cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st);
 cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad,
                               bool vol_grad, cudaStream_t st);
-// the same for one layout each: three translation units built from render_kernels.cu with -DDIFFUS_LAYOUT_SLICE=n
+// the same for one layout each: four translation units built from render_kernels.cu with -DDIFFUS_LAYOUT_SLICE=n
 #define DIFFUS_DECLARE_SLICE(n)                                                                                        \
     cudaError_t launch_render_fwd_layout##n(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st); \
     cudaError_t launch_render_bwd_layout##n(const RenderParams& p, int sampler, int layout, int pose64, bool pose_grad, \
@@ -56,6 +73,7 @@ cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, in
 DIFFUS_DECLARE_SLICE(0)
 DIFFUS_DECLARE_SLICE(1)
 DIFFUS_DECLARE_SLICE(2)
+DIFFUS_DECLARE_SLICE(3)
 int64_t reduce_sum_workspace_bytes();
 cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, void* workspace, cudaStream_t st);
 cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* echo, cudaStream_t st);
@@ -64,9 +82,9 @@ cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n
 
 // aux_kernels.cu
 cudaError_t launch_first_refl_median(const RenderParams& p, int sampler, int layout, int pose64, float* median,
-                                     int32_t* argmedian, cudaStream_t st);
+                                     int32_t* tie_count, cudaStream_t st);
 cudaError_t launch_median_backward(const RenderParams& p, int sampler, int layout, int pose64,
-                                   const int32_t* argmedian, bool pose_grad, bool vol_grad, cudaStream_t st);
+                                   const int32_t* tie_count, bool pose_grad, bool vol_grad, cudaStream_t st);
 cudaError_t launch_ray_indices(const RenderParams& p, int pose64, int64_t* x, int64_t* y, int64_t* z, cudaStream_t st);
 cudaError_t launch_trace_values(const RenderParams& p, int sampler, int layout, int pose64, float* out, cudaStream_t st);
 cudaError_t launch_sample_points(const RenderParams& p, int sampler, int layout, const float* pts, int64_t n, float* val,

@@ -54,6 +54,9 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
 //               diff = frame - target, ebar = grad_scale * diff * att, accumulates diff^2
 //               and (optionally) stores the frame
 constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
+#ifndef DIFFUS_TEX_GB
+#define DIFFUS_TEX_GB 2      // tiles of tld4 gathers in flight per warp in the fused backward (TEXTURE layout)
+#endif
 constexpr int BWD_DZ_STRIDE = FwdGeo::OBUF;   // floats between the per-axis rows of the spatial-gradient buffer
 
 // What the render kernels add to the plain echo backward: the impedances around the lane's columns, so that the
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
             // Measured on the one-pass pose kernel (96 registers, 5 CTAs = 20 warps per SM), batches of 1 / 2 / 4 tiles:
             // 0.701 / 0.687 / 0.705 ms per 1024 poses (before the bounds tests left the loop below, two tiles still
             // spilled and one tile per batch was the fastest: 0.753 / 0.779 / 0.785).
-            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2);
+            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : (LAYOUT == DIFFUS_LAYOUT_TEXTURE ? DIFFUS_TEX_GB : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2));
             // batches whose tiles are all complete run without the per-lane bounds tests; the tail keeps them
             const int nt_full = (ncol >> 5) / GB * GB;
             for (int t0 = 0; t0 < nt_full; t0 += GB) {
@@ -705,47 +708,53 @@ __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__
     }
 }
 
-// sum of per-ray partials -> one float, fixed order: blocks write double partials, the last block to
-// finish (atomic ticket) adds them up in index order
-__global__ void reduce_sum_kernel(const float* __restrict__ partial, int64_t n, float scale, float* __restrict__ out,
-                                  double* __restrict__ block_sums, unsigned* __restrict__ ticket) {
-    __shared__ double warp_part[32];
-    __shared__ bool last;
-    double acc = 0.0;
-    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)partial[i];
+// sum of per-ray partials -> one float in a FIXED order (run-to-run identical), without atomics, tickets or memsets:
+// up to 2^20 partials one 1024-thread block does it all (2 us for the 131 072 rays of a 1024-pose sweep); above that a
+// first launch leaves REDUCE_BLOCKS double partials in the workspace and a second one adds them up in index order.
+__device__ __forceinline__ double block_sum_fixed_order(double acc, double* warp_part) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
     __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_part[w];
+    return t;                                 // valid on thread 0
+}
+
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ partial, int64_t n, float scale,
+                                                          float* __restrict__ out, double* __restrict__ block_sums) {
+    __shared__ double warp_part[32];
+    double acc = 0.0;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)__ldg(partial + i);
+    const double t = block_sum_fixed_order(acc, warp_part);
+    if (threadIdx.x == 0) {
+        if (block_sums) block_sums[blockIdx.x] = t;
+        else out[0] = (float)(t * (double)scale);
+    }
+}
+
+__global__ void reduce_final_kernel(const double* __restrict__ block_sums, int n, float scale, float* __restrict__ out) {
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_part[w];
-        block_sums[blockIdx.x] = t;
-        __threadfence();
-        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
-        double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += ((volatile double*)block_sums)[b];
+        for (int b = 0; b < n; ++b) t += block_sums[b];
         out[0] = (float)(t * (double)scale);
-        *ticket = 0u;                        // ready for the next launch on this workspace
     }
 }
 
 constexpr int REDUCE_BLOCKS = 64;
-int64_t reduce_sum_workspace_bytes() { return REDUCE_BLOCKS * sizeof(double) + 256; }
+int64_t reduce_sum_workspace_bytes() { return REDUCE_BLOCKS * sizeof(double); }
 
 cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, void* workspace, cudaStream_t st) {
+    if (n <= ((int64_t)1 << 20)) {
+        reduce_sum_kernel<<<1, 1024, 0, st>>>(partial, n, scale, out, nullptr);
+        return cudaGetLastError();
+    }
     double* sums = (double*)workspace;
-    unsigned* ticket = (unsigned*)((char*)workspace + REDUCE_BLOCKS * sizeof(double));
-    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
-    if (e != cudaSuccess) return e;
-    int blocks = (int)max((int64_t)1, min((int64_t)REDUCE_BLOCKS, n / 1024));
-    reduce_sum_kernel<<<blocks, 256, 0, st>>>(partial, n, scale, out, sums, ticket);
+    reduce_sum_kernel<<<REDUCE_BLOCKS, 1024, 0, st>>>(partial, n, scale, out, sums);
+    reduce_final_kernel<<<1, 32, 0, st>>>(sums, REDUCE_BLOCKS, scale, out);
     return cudaGetLastError();
 }
 
@@ -759,16 +768,6 @@ static int warps_per_block(int64_t total_rays) {
     if (total_rays >= 4 * 148 * 4) return 4;
     if (total_rays >= 2 * 148 * 2) return 2;
     return 1;
-}
-
-template <typename K>
-static cudaError_t ensure_smem(K kernel, size_t smem) {
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    // ask for the largest shared-memory carveout so the CTA count per SM is set by our buffers, not the default split
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    if (smem > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    return cudaSuccess;
 }
 
 #ifdef DIFFUS_LAYOUT_SLICE
@@ -835,6 +834,7 @@ cudaError_t launch_render_fwd(const RenderParams& p, int sampler, int layout, in
         case DIFFUS_LAYOUT_LINEAR: return launch_render_fwd_layout0(p, sampler, layout, pose64, st);
         case DIFFUS_LAYOUT_BRICK: return launch_render_fwd_layout1(p, sampler, layout, pose64, st);
         case DIFFUS_LAYOUT_QUAD: return launch_render_fwd_layout2(p, sampler, layout, pose64, st);
+        case DIFFUS_LAYOUT_TEXTURE: return launch_render_fwd_layout3(p, sampler, layout, pose64, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -845,6 +845,7 @@ cudaError_t launch_render_bwd(const RenderParams& p, int sampler, int layout, in
         case DIFFUS_LAYOUT_LINEAR: return launch_render_bwd_layout0(p, sampler, layout, pose64, pose_grad, vol_grad, st);
         case DIFFUS_LAYOUT_BRICK: return launch_render_bwd_layout1(p, sampler, layout, pose64, pose_grad, vol_grad, st);
         case DIFFUS_LAYOUT_QUAD: return launch_render_bwd_layout2(p, sampler, layout, pose64, pose_grad, vol_grad, st);
+        case DIFFUS_LAYOUT_TEXTURE: return launch_render_bwd_layout3(p, sampler, layout, pose64, pose_grad, vol_grad, st);
     }
     return cudaErrorInvalidValue;
 }

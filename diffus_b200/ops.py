@@ -12,7 +12,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (LAYOUT_BRICK, LAYOUT_LINEAR, LAYOUT_QUAD, MLP_NPARAMS, POSE_F32, POSE_F64, SAMPLER_NEAREST,
+from ._lib import (LAYOUT_BRICK, LAYOUT_LINEAR, LAYOUT_QUAD, LAYOUT_TEXTURE, MLP_NPARAMS, POSE_F32, POSE_F64, SAMPLER_NEAREST,
                    SAMPLER_TRILINEAR, DiffusRenderArgs, DiffusRenderBwdArgs)
 
 SEG = 512  # PREFIX_STRIDE of csrc/common.cuh: the forward saves a 2x2 prefix every SEG columns
@@ -56,10 +56,69 @@ def _nseg(sout: int) -> int:
     return (sout + SEG - 1) // SEG
 
 
+# TEXTURE layout: the CUDA array + texture object live outside torch's allocator.  The ops receive a one-element int64
+# CUDA tensor as ``bricks`` (the token); this registry maps the token's address to the texture object it stands for.
+_TEXTURES = {}
+
+
+class VolumeTexture:
+    """A read-only copy of a (D,H,W) float32 volume in a layered 2-D CUDA array behind a texture object."""
+
+    def __init__(self, volume: torch.Tensor):
+        dev = _require_cuda(volume)
+        lib = _lib.load()
+        v = volume.detach().contiguous().float()
+        self.dims = tuple(v.shape)
+        self.device = dev
+        tex, arr = C.c_uint64(0), C.c_uint64(0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.diffus_volume_texture_create(v.data_ptr(), C.byref((C.c_int32 * 3)(*self.dims)), C.byref(tex),
+                                                        C.byref(arr), _stream(dev)), "diffus_volume_texture_create")
+            self.token = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.texture, self.array = tex.value, arr.value
+        _TEXTURES[self.token.data_ptr()] = self
+        _count(1)
+
+    def update(self, volume: torch.Tensor) -> None:
+        v = volume.detach().contiguous().float()
+        if tuple(v.shape) != self.dims:
+            raise _lib.DiffusError("volume shape changed; build a new VolumeTexture")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().diffus_volume_texture_update(self.array, v.data_ptr(), C.byref((C.c_int32 * 3)(*self.dims)),
+                                                                _stream(self.device)), "diffus_volume_texture_update")
+        _count(1)
+
+    def close(self) -> None:
+        if self.texture:
+            _TEXTURES.pop(self.token.data_ptr(), None)
+            try:
+                with torch.cuda.device(self.device):
+                    torch.cuda.current_stream(self.device).synchronize()     # no launch may still read the array
+                    _lib.load().diffus_volume_texture_destroy(self.texture, self.array)
+            finally:
+                self.texture = self.array = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _texture_of(bricks: torch.Tensor) -> "VolumeTexture":
+    try:
+        return _TEXTURES[bricks.data_ptr()]
+    except KeyError:
+        raise _lib.DiffusError("int64 `bricks` tensor is not the token of a live VolumeTexture") from None
+
+
 def _packed_layout(bricks: Optional[torch.Tensor]) -> int:
-    """Layout of the packed copy handed to the ops as ``bricks``: none -> LINEAR, 1-D -> BRICK, (n, 4) -> QUAD."""
+    """Layout of the packed copy handed to the ops as ``bricks``: none -> LINEAR, 1-D float -> BRICK, (n, 4) -> QUAD,
+    int64 token -> TEXTURE."""
     if bricks is None or bricks.numel() == 0:
         return LAYOUT_LINEAR
+    if bricks.dtype == torch.int64:
+        return LAYOUT_TEXTURE
     return LAYOUT_QUAD if bricks.dim() == 2 else LAYOUT_BRICK
 
 
@@ -76,8 +135,10 @@ def _grad_volume_shape(bricks: Optional[torch.Tensor], dims) -> Tuple[int, ...]:
 def _fill_render_args(a: DiffusRenderArgs, volume, bricks, dims, sources, directions, n_samples, start, alpha,
                       sampler, product_f32):
     layout = _packed_layout(bricks)
-    data = volume if layout == LAYOUT_LINEAR else bricks
-    a.volume.data = data.data_ptr()
+    if layout == LAYOUT_TEXTURE:
+        a.volume.data = _texture_of(bricks).texture          # the 64-bit texture object travels in the pointer field
+    else:
+        a.volume.data = (volume if layout == LAYOUT_LINEAR else bricks).data_ptr()
     a.volume.dim[0], a.volume.dim[1], a.volume.dim[2] = dims
     a.volume.layout = layout
     a.sources = sources.data_ptr()

@@ -58,7 +58,9 @@ class PreparedVolume:
     cache lines per load instruction than in the torch layout.  ``layout='quad'``: one float4 per voxel holding
     the voxel and its three +p1 / +p2 neighbours, so a trilinear cell is two 16-byte loads instead of eight
     4-byte ones (4x the memory; faster only while the copy stays L2-resident).  ``'auto'`` picks ``'quad'`` up
-    to 40 MiB of packed data (about 136^3 voxels) and ``'brick'`` above.  Building the copy costs one pass over the volume, so it pays for
+    to 40 MiB of packed data (about 136^3 voxels) and ``'brick'`` above.  ``layout='texture'``: a layered 2-D CUDA
+    array behind a texture object -- a trilinear cell is two ``tld4`` texel gathers with the address arithmetic and the
+    border clamp done by the texture unit, at 1x the memory.  Building the copy costs one pass over the volume, so it pays for
     pose sweeps, not for a single frame.  Gradients still flow to ``volume`` (the LINEAR tensor).
     """
 
@@ -67,19 +69,29 @@ class PreparedVolume:
     def __init__(self, volume: torch.Tensor, layout: str = "auto"):
         if volume.dim() != 3:
             raise ValueError("volume must be (D,H,W)")
-        if layout not in ("auto", "brick", "quad"):
-            raise ValueError("layout must be 'auto', 'brick' or 'quad'")
+        if layout not in ("auto", "brick", "quad", "texture"):
+            raise ValueError("layout must be 'auto', 'brick', 'quad' or 'texture'")
         if layout == "auto":
             layout = "quad" if volume.numel() * 16 <= self.QUAD_AUTO_MAX_BYTES else "brick"
+        if volume.dtype != torch.float32 or not volume.is_contiguous():
+            # a converted copy would silently go stale when the caller updates their own tensor in place
+            raise ValueError("PreparedVolume needs a contiguous float32 volume (it watches the tensor for in-place updates)")
         self.layout = layout
-        self.volume = volume if volume.dtype == torch.float32 else volume.float()
-        self.volume = self.volume.contiguous()
+        self.volume = volume
         self.shape = tuple(volume.shape)
+        self._texture = None
         self.refresh()
 
     def refresh(self) -> "PreparedVolume":
         """Rebuild the packed copy (done automatically when the volume tensor was modified in place)."""
-        self._bricks = ops.to_quads(self.volume) if self.layout == "quad" else ops.to_bricks(self.volume)
+        if self.layout == "texture":
+            if self._texture is None:
+                self._texture = ops.VolumeTexture(self.volume)
+            else:
+                self._texture.update(self.volume)
+            self._bricks = self._texture.token
+        else:
+            self._bricks = ops.to_quads(self.volume) if self.layout == "quad" else ops.to_bricks(self.volume)
         self._version = self.volume._version
         return self
 

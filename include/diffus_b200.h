@@ -49,6 +49,10 @@ extern "C" {
 #define DIFFUS_LAYOUT_QUAD 2   /* one float4 per voxel = the voxel and its +p1, +p2, +p1+p2 neighbours (clamped at
                                   the faces), 2x2x2 voxels per 128 B, made by diffus_volume_to_quads: a trilinear
                                   cell is two 16-byte loads.  4x the footprint; read-only (see grad_volume)        */
+#define DIFFUS_LAYOUT_TEXTURE 3 /* a layered 2-D CUDA array behind a texture object made by diffus_volume_texture_create
+                                  (layer = p0, y = p1, x = p2; clamp addressing, point sampling): a trilinear cell is two
+                                  tld4 texel gathers, address arithmetic and border clamp done by the texture unit, 1x the
+                                  footprint.  DiffusVolume.data carries the 64-bit texture object; read-only            */
 
 /* dtype tags for the probe pose (the reference's `points` dtype follows torch promotion,
    src/renderer.py:124, and is cast to float32 at :751) */
@@ -103,7 +107,7 @@ typedef struct DiffusRenderBwdArgs {
                                    fwd.seg_prefix = the buffer the forward filled (required
                                    when S-start > 512)                                        */
     const float* grad_frame;    /* (P,R,S-start)                                             */
-    float* grad_volume;         /* QUAD volumes: a BRICK buffer.  Otherwise the
+    float* grad_volume;         /* QUAD and TEXTURE volumes: a BRICK buffer.  Otherwise the
                                    same layout as fwd.volume (LINEAR (D,H,W), or diffus_brick_elems()
                                    floats for BRICK), ACCUMULATED into (caller zero-fills)    */
     float* grad_sources;        /* (P,3) overwritten; trilinear only                         */
@@ -242,6 +246,16 @@ int32_t diffus_bricks_to_volume(const float* bricks, const int32_t dim[3], float
 /* LINEAR -> QUAD copy; the quad buffer holds diffus_quad_elems(dim) FLOATS (4 per padded voxel, 16-byte aligned). */
 int64_t diffus_quad_elems(const int32_t dim[3]);
 int32_t diffus_volume_to_quads(const float* linear, const int32_t dim[3], float* quads, void* stream);
+
+/* TEXTURE layout.  The ONLY entry points of this library that allocate and free device memory (a CUDA array of
+ * dim[0] layers x dim[1] x dim[2] float32 texels and a texture object): create once per volume, update after the
+ * LINEAR tensor changed (one device-to-device copy enqueued on `stream`), destroy when done.  `*texture_object` is what
+ * goes into DiffusVolume.data (cast to a pointer) with layout = DIFFUS_LAYOUT_TEXTURE; `*array_handle` is opaque.
+ * Limits: dim[0] <= 2048 layers, dim[1], dim[2] <= 32768. */
+int32_t diffus_volume_texture_create(const float* linear, const int32_t dim[3], uint64_t* texture_object,
+                                     uint64_t* array_handle, void* stream);
+int32_t diffus_volume_texture_update(uint64_t array_handle, const float* linear, const int32_t dim[3], void* stream);
+int32_t diffus_volume_texture_destroy(uint64_t texture_object, uint64_t array_handle);
 
 /* Measurement aid for the roofline, not part of the render path: every thread issues
  * `reads_per_thread` independent 4-byte loads at pseudo-random 32-byte-sector-aligned positions of buf (n_floats

@@ -264,13 +264,93 @@ def impedance_volume_cases(ref):
     np.savez_compressed(os.path.join(OUT, "impedance_volume.npz"), **out)
 
 
+def _volume_fingerprint(vol):
+    """A few numbers that pin a seeded volume regenerated on another machine (the 64 MiB tensor is not stored)."""
+    v = vol.double().reshape(-1)
+    idx = torch.arange(0, v.numel(), 104729)          # a prime stride
+    return np.array([v.sum().item(), v.square().sum().item(), (v[idx] * torch.arange(1, idx.numel() + 1)).sum().item()])
+
+
+def config1_full_cases(ref):
+    """BASELINE config 1 AT FULL SIZE from the real reference: layered 256^3 phantom, 128 rays x 512 samples, nearest,
+    forward, fp32 and fp64 (about 75 s + 150 s on 8 cores).  The volume is regenerated from its seed by the tests
+    (``layered_phantom(256, seed=0)``) and checked against the stored fingerprint."""
+    R = ref.renderer
+    sys.path.insert(0, ROOT)
+    from diffus_b200.phantoms import config1_pose, layered_phantom
+    vol = layered_phantom(256, seed=0)
+    src, dirs = config1_pose(256, 128)
+    ren = R.UltrasoundRenderer(512, 1e-4)
+    with RL.quiet():
+        x, y, z, f32 = ren.plot_beam_frame(volume=vol.clone(), source=src, directions=dirs, plot=False, artifacts=False, start=0)
+        _, _, _, f64 = ren.plot_beam_frame(volume=vol.double(), source=src, directions=dirs.double(), plot=False,
+                                           artifacts=False, start=0)
+    out = {"volume_fingerprint": _volume_fingerprint(vol), "source": _np(src), "dirs": _np(dirs), "S": np.int64(512),
+           "alpha": np.float64(1e-4), "frame32": _np(f32), "frame64": _np(f64),
+           "x": _np(x).astype(np.int16), "y": _np(y).astype(np.int16), "z": _np(z).astype(np.int16)}
+    np.savez_compressed(os.path.join(OUT, "config1_full.npz"), **out)
+
+
+def config2_reduced_cases(ref):
+    """BASELINE config 2's geometry from the real reference with its trilinear sampler installed: the same 256^3 phantom
+    and 128-ray fan, the first 128 samples (torch autograd through the dense solves needs ~190 GB at 512), fp64:
+    frame, d/dsource, d/ddirections and the non-zero part of d/dvolume of sum(frame * w)."""
+    R = ref.renderer
+    sys.path.insert(0, ROOT)
+    from diffus_b200.phantoms import config1_pose, layered_phantom
+    vol = layered_phantom(256, seed=0)
+    src, dirs = config1_pose(256, 128)
+    S = 128
+    g = torch.Generator().manual_seed(22)
+    v64 = vol.double().requires_grad_(True)
+    s64 = src.double().requires_grad_(True)
+    d64 = dirs.double().requires_grad_(True)
+    ren = R.UltrasoundRenderer(S, 1e-4)
+    with RL.trilinear_sampler_installed(ref), RL.quiet():
+        x, y, z, f = ren.plot_beam_frame(volume=v64, source=s64, directions=d64, plot=False, start=0)
+    w = torch.randn(f.shape, generator=g, dtype=torch.float32).double()      # float32-representable: the kernels get the same weights
+    gv, gs, gd = torch.autograd.grad((f * w).sum(), [v64, s64, d64])
+    nz = gv.reshape(-1).nonzero().reshape(-1)
+    out = {"volume_fingerprint": _volume_fingerprint(vol), "source": _np(src), "dirs": _np(dirs), "S": np.int64(S),
+           "alpha": np.float64(1e-4), "frame64": _np(f), "w": _np(w).astype(np.float32),
+           "grad_source": _np(gs), "grad_dirs": _np(gd),
+           "grad_volume_index": _np(nz).astype(np.int32), "grad_volume_value": _np(gv.reshape(-1)[nz]).astype(np.float32)}
+    np.savez_compressed(os.path.join(OUT, "config2_reduced.npz"), **out)
+
+
+def median_tie_cases(ref):
+    """start > 0 with the near field OUTSIDE the volume: the border clamp makes the first kept coefficient exactly 0 on
+    most rays, so the median over rays is a tie.  Forward from the real reference (its autograd raises here,
+    src/renderer.py:243-244); the tie rule of the gradient is torch's ``median()`` backward (evenly distributed over the
+    tied elements), recorded on a small vector."""
+    R, C = ref.renderer, ref.cone
+    out = {}
+    vol = _blocky_volume((24, 24, 24), 11, block=3)
+    dirs = C.generate_cone_directions([0.0, 1.0], math.radians(70), 15)
+    src = torch.tensor([12.0, -9.0, 12.0])              # 9 voxels in front of the p1 = 0 face
+    for name, start in (("tie4", 4), ("tie9", 9), ("tie12", 12)):
+        ren = R.UltrasoundRenderer(40, 1e-3)
+        with RL.quiet():
+            x, y, z, f64 = ren.plot_beam_frame(volume=vol.double(), source=src, directions=dirs.double(), plot=False, start=start)
+            xs, ys, zs, rs = ren.simulate_rays(vol.double(), src, dirs.double())
+        out[f"{name}_start"], out[f"{name}_frame64"], out[f"{name}_x"] = np.int64(start), _np(f64), _np(x)
+        out[f"{name}_first_refl"] = _np(rs[:, start])
+    out["volume"], out["source"], out["dirs"] = _np(vol), _np(src), _np(dirs)
+    t = torch.tensor([0.0, 0.0, 3.0, 1.0, -1.0, 0.0, 2.0, 5.0], dtype=torch.float64, requires_grad=True)
+    t.median().backward()
+    out["tie_rule_input"], out["tie_rule_grad"] = _np(t), _np(t.grad)
+    np.savez_compressed(os.path.join(OUT, "median_ties.npz"), **out)
+
+
 def main():
     ref = RL.load()
     if ref is None:
         raise SystemExit("reference tree not found at " + RL.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
-    for fn in (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases, impedance_volume_cases, brain_phantom2d_cases):
+    fns = (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases, impedance_volume_cases, brain_phantom2d_cases,
+           median_tie_cases, config2_reduced_cases, config1_full_cases)      # the last one takes ~4 minutes
+    for fn in fns:
         if only and fn.__name__ not in only:
             continue
         fn(ref)

@@ -1,7 +1,7 @@
 """GPU parity: the CUDA path (through the Python drop-in -> torch.library -> C ABI) against the
 golden fixtures produced by the unmodified reference, and against the CPU oracle on seeded
-inputs.  Frames: |a-b| <= 1e-4 + 1e-5 |b| (north_star); gradients: <= 1e-4 of the largest
-reference entry; indices bit-exact."""
+inputs.  Tolerances (tests/conftest.py, north_star): frames |a-b| <= 1e-4 peak + 1e-5 |b|;
+gradients 1e-4 relative element-wise above 1e-3 of the largest entry; indices bit-exact."""
 import math
 
 import numpy as np
@@ -80,17 +80,17 @@ def test_simulate_rays_is_differentiable_like_the_reference(sampler):
         x, y, z, R = ren.simulate_rays(PreparedVolume(v) if prepared else v, s, dd, sampler=sampler)
         np.testing.assert_allclose(R.detach().cpu().numpy(), R64.detach().numpy(), rtol=1e-4, atol=1e-7)
         (R * w.float().to(dev())).sum().backward()
-        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d R / d volume", rtol=2e-4)
+        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d R / d volume")
         if sampler == "trilinear":
-            assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d R / d source", rtol=2e-4)
-            assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d R / d directions", rtol=2e-4)
+            assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d R / d source")
+            assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d R / d directions")
         else:
             assert s.grad is None
 
 
 @pytest.mark.parametrize("name", NEAREST_CASES)
 def test_packed_layouts_match_linear(golden_frames, name):
-    """BRICK and QUAD copies hold the same voxels and the kernels do the same arithmetic on them: bit-equal frames."""
+    """BRICK, QUAD and TEXTURE copies hold the same voxels and the kernels do the same arithmetic on them: bit-equal frames."""
     from diffus_b200 import PreparedVolume, render_frames
     g = golden_frames
     vol = torch.tensor(g[f"{name}_volume"], device=dev())
@@ -99,7 +99,7 @@ def test_packed_layouts_match_linear(golden_frames, name):
     S, alpha = int(g[f"{name}_S"]), float(g[f"{name}_alpha"])
     for sampler in ("nearest", "trilinear"):
         a = render_frames(vol, src, dirs, S, alpha, _start(g, name), sampler=sampler)
-        for layout in ("brick", "quad"):
+        for layout in ("brick", "quad", "texture"):
             b = render_frames(PreparedVolume(vol, layout), src, dirs, S, alpha, _start(g, name), sampler=sampler)
             assert torch.equal(a, b), f"{name} {sampler}: {layout} layout changes the result"
 
@@ -221,7 +221,8 @@ def test_batched_poses_vs_oracle(sampler, S, start):
 
 
 @pytest.mark.parametrize("sampler", ["nearest", "trilinear"])
-@pytest.mark.parametrize("S,start,prepared", [(96, 0, None), (700, 0, "quad"), (1300, 11, None), (513, 3, "brick"), (300, 0, "quad")])
+@pytest.mark.parametrize("S,start,prepared", [(96, 0, None), (700, 0, "quad"), (1300, 11, None), (513, 3, "brick"), (300, 0, "quad"),
+                                              (512, 0, "texture"), (1100, 5, "texture")])
 def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
     """render_mse_loss (one fused kernel) == mse_loss(render_frames) through autograd == fp64 oracle."""
     from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
@@ -295,10 +296,10 @@ def test_edge_shapes_vs_oracle(dims, R, S, start, sampler):
     loss = render_mse_loss(v, s, dd, tgt.float().to(dev()), S, alpha, start, sampler=sampler)
     loss.backward()
     if want[0].abs().max() > 0:
-        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume", rtol=2e-4)
+        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume")
     if sampler == "trilinear" and want[1] is not None and want[1].abs().max() > 0:
-        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources", rtol=2e-4)
-        assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d/ddirections", rtol=2e-4)
+        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources")
+        assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d/ddirections")
 
 
 @pytest.mark.parametrize("seed", range(24))
@@ -315,7 +316,7 @@ def test_randomised_configurations_vs_oracle(seed):
     start = rnd.choice([0, 0, 0, 1, S // 3, max(S - 2, 0)]) if S > 3 else 0
     sampler = rnd.choice(["nearest", "trilinear"])
     u = rnd.random()
-    prepared = None if u >= 0.5 else ("brick" if u < 0.2 else "quad")
+    prepared = None if u >= 0.5 else ("brick" if u < 0.15 else ("texture" if u < 0.33 else "quad"))
     shared = rnd.random() < 0.3
     pose64 = rnd.random() < 0.25
     alpha = rnd.choice([0.0, 1e-4, 1e-2, 0.5])
@@ -347,13 +348,13 @@ def test_randomised_configurations_vs_oracle(seed):
             loss = torch.nn.functional.mse_loss(f, tgt.to(dev()))
         loss.backward()
         assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), what)
-        np.testing.assert_allclose(loss.item(), l64.item(), rtol=2e-4, atol=1e-12, err_msg=what)
+        np.testing.assert_allclose(loss.item(), l64.item(), rtol=1e-4, atol=1e-12, err_msg=what)
         if want[0].abs().max() > 0:
-            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), what + " d/dvolume", rtol=3e-4)
+            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), what + " d/dvolume")
         if sampler == "trilinear":
             if want[1].abs().max() > 0:
-                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), what + " d/dsources", rtol=3e-4)
-                assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), what + " d/ddirections", rtol=3e-4)
+                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), what + " d/dsources")
+                assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), what + " d/ddirections")
         else:
             assert s.grad is None and dd.grad is None
 
@@ -525,10 +526,10 @@ def test_mlp_render_training_step_vs_oracle():
             vol_in = TrainingVolume(mri.to(dev())) if mode == "prepared" else mri.to(dev())
             loss = mlp_render_mse_loss(m, vol_in, s, dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
         loss.backward()
-        np.testing.assert_allclose(loss.item(), l64.item(), rtol=2e-4)
+        np.testing.assert_allclose(loss.item(), l64.item())
         for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
-            assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"d/d{name} ({mode})", rtol=3e-4)
-        assert_grad_close(s.grad.cpu().numpy(), s64.grad.numpy(), "d/dsources", rtol=3e-4)
+            assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"d/d{name} ({mode})")
+        assert_grad_close(s.grad.cpu().numpy(), s64.grad.numpy(), "d/dsources")
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     l0 = train_step(m, opt, mri.to(dev()), sources.to(dev()), dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
     for _ in range(10):
@@ -761,12 +762,12 @@ def test_prepared_volume_layouts_and_auto_choice():
     src, dirs = pose_sweep(3, n_rays=6, n=40, seed=4)
     src, dirs = src.to(dev()), dirs.to(dev())
     grads = {}
-    for layout in (None, "brick", "quad"):
+    for layout in (None, "brick", "quad", "texture"):
         v = vol.clone().requires_grad_(True)
         f = render_frames(PreparedVolume(v, layout) if layout else v, src, dirs, 90, 1e-3, 5, sampler="trilinear")
         f.square().sum().backward()
         grads[layout] = (f.detach(), v.grad)
-    for layout in ("brick", "quad"):
+    for layout in ("brick", "quad", "texture"):
         assert torch.equal(grads[layout][0], grads[None][0])
         torch.testing.assert_close(grads[layout][1], grads[None][1], rtol=1e-5, atol=1e-12)     # atomics: order varies
 

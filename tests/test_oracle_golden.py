@@ -176,3 +176,69 @@ def test_notebook_brain_phantom_2d():
     np.testing.assert_array_equal(r.numpy(), g["r"])
     np.testing.assert_array_equal(port.echo_dense_solve(r).numpy(), g["echo32"])
     np.testing.assert_allclose(port.echo_closed_form(r.double()).numpy(), g["echo64"], atol=1e-13)
+
+
+# ----------------------------------------------------------------------------------------
+# BASELINE sizes: the closed-form port against the reference's own full-size outputs
+# ----------------------------------------------------------------------------------------
+def _fingerprint(vol):
+    v = vol.double().reshape(-1)
+    idx = torch.arange(0, v.numel(), 104729)
+    return np.array([v.sum().item(), v.square().sum().item(), (v[idx] * torch.arange(1, idx.numel() + 1)).sum().item()])
+
+
+@pytest.fixture(scope="module")
+def layered256():
+    from diffus_b200.phantoms import layered_phantom
+    return layered_phantom(256, seed=0)
+
+
+def test_config1_full_size_port_vs_reference(layered256):
+    """Config 1 at full size (128 x 512 on the 256^3 phantom): the O(S) closed form equals the reference's 512 dense
+    solves per ray to 1e-13 in fp64, indices bit-exact; the reference's fp32 run is 1e-5 of peak away from both."""
+    from conftest import load_golden
+    g = load_golden("config1_full.npz")
+    np.testing.assert_allclose(_fingerprint(layered256), g["volume_fingerprint"], rtol=1e-12)
+    src, dirs = torch.tensor(g["source"]), torch.tensor(g["dirs"])
+    x, y, z, f = port.plot_beam_frame(layered256.double(), src, dirs.double(), int(g["S"]), float(g["alpha"]))
+    np.testing.assert_array_equal(x.numpy(), g["x"].astype(np.int64))
+    np.testing.assert_array_equal(y.numpy(), g["y"].astype(np.int64))
+    np.testing.assert_array_equal(z.numpy(), g["z"].astype(np.int64))
+    peak = np.abs(g["frame64"]).max()
+    assert 0.05 < peak < 0.1                      # SURVEY 8(d): frame range [-0.081, 0.067]
+    np.testing.assert_allclose(f.numpy(), g["frame64"], rtol=0, atol=1e-12 * peak + 1e-13)
+    assert np.abs(g["frame32"] - g["frame64"]).max() < 5e-5 * peak
+
+
+def test_config2_reduced_port_vs_reference(layered256):
+    """Config 2's scene, 128 samples, through the reference with its trilinear sampler: the port's frame and all three
+    gradients (autograd through the closed form vs autograd through the dense solves) in fp64."""
+    from conftest import load_golden
+    g = load_golden("config2_reduced.npz")
+    np.testing.assert_allclose(_fingerprint(layered256), g["volume_fingerprint"], rtol=1e-12)
+    v64 = layered256.double().requires_grad_(True)
+    s64 = torch.tensor(g["source"]).double().requires_grad_(True)
+    d64 = torch.tensor(g["dirs"]).double().requires_grad_(True)
+    f = port.plot_beam_frame(v64, s64, d64, int(g["S"]), float(g["alpha"]), sampler="trilinear")[3]
+    np.testing.assert_allclose(f.detach().numpy(), g["frame64"], rtol=0, atol=1e-12)
+    gv, gs, gd = torch.autograd.grad((f * torch.tensor(g["w"]).double()).sum(), [v64, s64, d64])
+    np.testing.assert_allclose(gs.numpy(), g["grad_source"], rtol=1e-8, atol=1e-10 * np.abs(g["grad_source"]).max())
+    np.testing.assert_allclose(gd.numpy(), g["grad_dirs"], rtol=1e-8, atol=1e-10 * np.abs(g["grad_dirs"]).max())
+    want = np.zeros(256 ** 3)
+    want[g["grad_volume_index"]] = g["grad_volume_value"]
+    np.testing.assert_allclose(gv.numpy().reshape(-1), want, rtol=2e-7, atol=2e-7 * np.abs(want).max())   # stored as float32
+
+
+def test_median_ties_port_vs_reference():
+    """start > 0 with a tie at the median: forward vs the reference; torch's even split of the gradient over the ties."""
+    from conftest import load_golden
+    g = load_golden("median_ties.npz")
+    vol, src, dirs = torch.tensor(g["volume"]), torch.tensor(g["source"]), torch.tensor(g["dirs"])
+    for name in ("tie4", "tie9", "tie12"):
+        start = int(g[f"{name}_start"])
+        x, _, _, f = port.plot_beam_frame(vol.double(), src, dirs.double(), 40, 1e-3, start=start)
+        np.testing.assert_array_equal(x.numpy(), g[f"{name}_x"])
+        np.testing.assert_allclose(f.numpy(), g[f"{name}_frame64"], rtol=0, atol=1e-13)
+    t = torch.tensor(g["tie_rule_input"], requires_grad=True)
+    t.median().backward()
+    np.testing.assert_array_equal(t.grad.numpy(), g["tie_rule_grad"])
