@@ -98,8 +98,18 @@ def test_argument_validation_without_a_device(lib):
     a2.sources = a2.directions = a2.frame = 0x1000
     a2.n_poses, a2.n_rays, a2.n_samples = 1, 4, 16
     assert lib.diffus_render_forward(C.byref(a2), None) == -5
-    a2.volume.layout = 3
+    a2.volume.layout = 4
     assert lib.diffus_render_forward(C.byref(a2), None) == -3                      # unknown layout
+    # TEXTURE layout: the only allocating entry points validate before touching the device
+    t, arr = C.c_uint64(0), C.c_uint64(0)
+    assert lib.diffus_volume_texture_create(None, C.byref(dim), C.byref(t), C.byref(arr), None) == -1
+    big = (C.c_int32 * 3)(4096, 8, 8)
+    assert lib.diffus_volume_texture_create(0x1000, C.byref(big), C.byref(t), C.byref(arr), None) == -5   # > 2048 layers
+    assert lib.diffus_volume_texture_update(0, 0x1000, C.byref(dim), None) == -1
+    a2.volume.layout = 3
+    a2.volume.dim[0] = 4096
+    assert lib.diffus_render_forward(C.byref(a2), None) == -5                      # more layers than a layered array holds
+    a2.volume.dim[0] = 8
     a2.volume.layout, a2.frame, a2.seg_prefix = 0, None, None
     assert lib.diffus_render_forward(C.byref(a2), None) == -1                      # no frame and no prefix buffer
     assert lib.diffus_fan_directions(None, 0x1000, 1, 4, 0.5, 0x1000, None) == -1
