@@ -22,9 +22,16 @@ done
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --layout texture > $O/plain_tex.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:render_bwd -s 3 -c 1 -o $O/prof_fused_texture \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --layout texture > $O/ncu_tex.log 2>&1
+export_rep() {   # the .ncu-rep files are ~20 MB each and gpurun_out/ is capped at 64 MiB: keep the csv pages, drop the report
+  ncu -i $1.ncu-rep --page raw --csv > $1.raw.csv 2>/dev/null
+  ncu -i $1.ncu-rep --page source --csv > $1.source.csv 2>/dev/null
+  rm -f $1.ncu-rep
+}
+export_rep $O/prof_fused_texture
 for s in trilinear nearest; do
   python benchmarks/experiments/scatter_step.py --sampler $s --poses 1024 --iters 1 > $O/plain_scatter_$s.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:render_bwd -s 2 -c 1 -o $O/prof_scatter_$s \
       python benchmarks/experiments/scatter_step.py --sampler $s --poses 1024 --iters 1 > $O/ncu_scatter_$s.log 2>&1
+  export_rep $O/prof_scatter_$s
 done
 ls -la $O
