@@ -14,6 +14,16 @@ One JSON line on stdout (rank 0).  `value` is device-timed with everything resid
 and the loss + pose gradients read back to the host inside the timed region (the volume and
 the target frames are uploaded once: they are the scene and the dataset of a pose-recovery
 run, the poses are what changes per step).
+
+Besides the headline (weak scaling: 1024 poses PER GPU) the line carries, at every N:
+  `strong`       BASELINE config 3 as worded -- 1024 poses in total, sharded over the N ranks;
+  `config4`      the MLP -> render -> MSE training step (4096 frames per step in total, sharded) with the NCCL all-reduce
+                 of the weight gradients INSIDE the timed region, and the fused Adam update;
+  `nccl_parity`  a small scene rendered rank-sharded: gathered frames and all-reduced weight gradients against the full
+                 batch computed on rank 0 alone;
+  `config5`      (N = 1) the 512^3 / 512 x 2048 stress case on >= 1024 poses spread over the sphere.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref archive or /root/reference) on the host cores: all 128 rays of
+a pose at the first 128 samples, forward + backward, plus one full config-1 frame (forward).
 """
 from __future__ import annotations
 
@@ -141,6 +151,194 @@ def build_scene(device, n_poses, seed, return_params=False):
     return vol, sources, dirs
 
 
+def headline_config(P, world, layout):
+    """The `config` object: identical in both arms (the reference arm times a bounded sample OF THIS workload)."""
+    return {
+        "workload": f"config3 pose sweep fwd+bwd: {P} poses/GPU x {N_RAYS} rays x {N_SAMPLES} samples, "
+                    f"{VOL_N}^3 MRI-shaped impedance volume, trilinear, MSE vs target frames, "
+                    "gradients to every pose's source and directions",
+        "poses_per_gpu": P, "rays": N_RAYS, "samples": N_SAMPLES, "volume": f"{VOL_N}^3 f32",
+        "volume_layout": layout, "parallelism": f"pose-sharded x{world}, volume replicated",
+        "l2": "no explicit flush: inputs exceed L2 -- every step streams its own 268 MB of target frames per "
+              "1024 poses (>> 126 MB L2, marked evict-first); the 64 MiB volume is meant to stay L2-resident",
+    }
+
+
+def timed_steps(fn, warmup, steps, barrier):
+    """CUDA-event time of `steps` back-to-back calls of fn after `warmup` calls, bracketed by barriers (ms per step)."""
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def max_over_ranks(values, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def strong_scaling_record(dev, rank, world, barrier, layout):
+    """BASELINE config 3 as worded: 1024 poses IN TOTAL, sharded over the ranks (each rank: its contiguous block)."""
+    from diffus_b200 import PreparedVolume, ops, render_frames
+    from diffus_b200 import distributed as D
+    from diffus_b200._lib import SAMPLER_TRILINEAR
+    from diffus_b200.graphs import GraphedPoseStep
+    total = 1024
+    vol_h, src_h, dir_h = build_scene(dev, total, seed=1000)
+    sl = D.pose_shard(total, rank, world)
+    pv = PreparedVolume(vol_h.to(dev), layout)
+    src, dirs = src_h[sl].to(dev).contiguous(), dir_h[sl].to(dev).contiguous()
+    with torch.no_grad():
+        target = render_frames(pv, src + torch.tensor([1.5, 0.0, -1.0], device=dev), dirs, N_SAMPLES, ALPHA, 0, sampler="trilinear")
+    dims = list(pv.volume.shape)
+
+    def eager():
+        ops.render_mse_impl(pv.volume, pv.bricks, dims, src, dirs, target, N_SAMPLES, 0, ALPHA, SAMPLER_TRILINEAR, False, False, True, False)
+    ms_eager = timed_steps(eager, 5, 200, barrier)
+    g = GraphedPoseStep(pv, target, N_RAYS, N_SAMPLES, ALPHA)
+    g.sources.copy_(src)
+    g.directions.copy_(dirs)
+    ms_graph = timed_steps(g.graph.replay, 5, 200, barrier)
+    ms_eager, ms_graph = max_over_ranks([ms_eager, ms_graph], dev, world)
+    return {"what": "config 3 strong scaling: 1024 poses in total, contiguous pose blocks per rank, fused fwd+MSE+bwd step, no collective "
+                    "on the path; max over ranks of the CUDA-event time",
+            "poses_total": total, "poses_per_gpu": sl.stop - sl.start, "ms_per_step_op_calls": ms_eager, "ms_per_step_cuda_graph": ms_graph,
+            "frames_per_s_op_calls": total / (ms_eager * 1e-3), "frames_per_s_cuda_graph": total / (ms_graph * 1e-3)}
+
+
+def config4_record(dev, rank, world, barrier):
+    """BASELINE config 4: MLP over a T2-shaped 256^3 volume -> 4096 frames per step IN TOTAL (sharded) -> MSE ->
+    weight gradients -> NCCL all-reduce -> Adam, everything inside the timed region (FusedTrainer.step)."""
+    from diffus_b200 import ImpedanceEstimator, PreparedVolume, render_frames
+    from diffus_b200 import distributed as D
+    from diffus_b200.phantoms import mri_phantom, pose_sweep
+    from diffus_b200.training import FusedTrainer
+    total = 4096
+    torch.manual_seed(0)
+    model = ImpedanceEstimator(1)
+    with torch.no_grad():
+        model.model[4].bias.fill_(1.5)
+        model.model[4].weight.mul_(0.3)
+    model = model.to(dev)
+    mri = (mri_phantom(VOL_N, "t2") / 1000.0).to(dev)
+    s_h, d_h = pose_sweep(total, N_RAYS, VOL_N, seed=2)
+    sl = D.pose_shard(total, rank, world)
+    s, d = s_h[sl].to(dev).contiguous(), d_h[sl].to(dev).contiguous()
+    out = {"what": "config 4 training step: MLP(256^3) -> frames -> MSE -> d/dweights -> NCCL all-reduce (4.6 KB flat buffer) -> fused Adam; "
+                   "4096 frames per step in total, sharded; CUDA-event time of FusedTrainer.step, max over ranks",
+           "frames_total": total, "frames_per_gpu": sl.stop - sl.start}
+    with torch.no_grad():
+        z_tgt = model.impedance_volume(mri, None, 1e6, 400.0) * 1.01
+    for sampler in ("trilinear", "nearest"):
+        with torch.no_grad():
+            tgt = render_frames(PreparedVolume(z_tgt), s, d, N_SAMPLES, ALPHA, sampler=sampler)
+        tr = FusedTrainer(model, mri, lr=1e-4, sampler=sampler, out_scale=1e6)
+        n_total = total * N_RAYS * N_SAMPLES
+        losses = []
+
+        def step():
+            losses.append(tr.step(s, d, tgt, N_SAMPLES, ALPHA, n_total=n_total))
+        ms = timed_steps(step, 3, 10, barrier)
+        (ms,) = max_over_ranks([ms], dev, world)
+        out[sampler] = {"ms_per_step": ms, "frames_per_s": total / (ms * 1e-3), "gsamples_per_s": n_total / (ms * 1e-3) / 1e9,
+                        "loss_first": float(losses[0]), "loss_last": float(losses[-1])}
+        del tr, tgt
+    return out
+
+
+def nccl_parity_record(dev, rank, world):
+    """A small scene rendered rank-sharded through NCCL against the full batch on rank 0 alone: gathered frames must be
+    bit-equal, the all-reduced weight gradients and the loss must agree to rounding (the volume scatter uses atomics)."""
+    import copy
+    import torch.distributed as dist
+    from diffus_b200 import ImpedanceEstimator, render_frames
+    from diffus_b200 import distributed as D
+    from diffus_b200.phantoms import mri_phantom, pose_sweep
+    from diffus_b200.training import FusedTrainer
+    P, R, S, n = 8 * max(world, 1) + 3, 6, 48, 24                 # ragged on purpose when world > 1
+    torch.manual_seed(7)
+    model = ImpedanceEstimator(1)
+    with torch.no_grad():
+        model.model[4].bias.fill_(1.5)
+        model.model[4].weight.mul_(0.3)
+    mri = (mri_phantom(n, "t2", seed=2) / 1000.0).to(dev)
+    s_h, d_h = pose_sweep(P, R, n, seed=9)
+    tgt_h = 0.01 * torch.randn((P, R, S), generator=torch.Generator().manual_seed(3))
+    sl = D.pose_shard(P, rank, world)
+    tr = FusedTrainer(copy.deepcopy(model).to(dev), mri, lr=1e-3, sampler="trilinear", out_scale=1e6)
+    z = tr.forward_volume().clone()
+    from diffus_b200 import ops
+    z_lin = ops.from_bricks(z, [n, n, n])
+    frames_local = render_frames(z_lin, s_h[sl].to(dev), d_h[sl].to(dev), S, 1e-3, sampler="trilinear")
+    frames = D.gather_frames(frames_local)                          # ragged shards: sizes are exchanged first
+    loss = tr.step(s_h[sl].to(dev).contiguous(), d_h[sl].to(dev).contiguous(), tgt_h[sl].to(dev).contiguous(), S, 1e-3,
+                   n_total=P * R * S)
+    grads = tr.grads.clone()
+    rec = None
+    if rank == 0:
+        full = FusedTrainer(copy.deepcopy(model).to(dev), mri, lr=1e-3, sampler="trilinear", out_scale=1e6)
+        frames_full = render_frames(z_lin, s_h.to(dev), d_h.to(dev), S, 1e-3, sampler="trilinear")
+        # rank 0 alone on the whole batch: temporarily a world of one (no collective is issued)
+        saved = D.world
+        D.world = lambda: (0, 1)
+        try:
+            loss_full = full.step(s_h.to(dev), d_h.to(dev), tgt_h.to(dev), S, 1e-3, n_total=P * R * S)
+        finally:
+            D.world = saved
+        gerr = float((grads - full.grads).abs().max() / full.grads.abs().max())
+        lerr = float(abs(loss.item() - loss_full.item()) / abs(loss_full.item()))
+        rec = {"what": f"{P} poses x {R} rays x {S} samples on a {n}^3 volume, ragged pose shards over {world} rank(s): gathered frames "
+                       "vs the full batch on rank 0 (bit-equal), all-reduced MLP weight gradients and loss vs the full batch",
+               "frames_bit_equal": bool(torch.equal(frames, frames_full)), "weight_grad_max_rel_err": gerr, "loss_rel_err": lerr,
+               "ok": bool(torch.equal(frames, frames_full)) and gerr <= 1e-4 and lerr <= 1e-5}
+    if world > 1:
+        dist.barrier()
+    return rec
+
+
+def config5_record(dev, poses, layout):
+    """BASELINE config 5 on one GPU: 512^3 volume (512 MiB: four times the L2), 512 rays x 2048 samples, `poses` poses spread
+    over the sphere, fused fwd + MSE + bwd (pose gradients).  BASELINE's 4096 poses are `4096 / poses` such launches."""
+    from diffus_b200 import PreparedVolume, ops, render_frames
+    from diffus_b200._lib import SAMPLER_TRILINEAR
+    from diffus_b200.phantoms import layered_phantom, pose_sweep
+    n, R, S = 512, 512, 2048
+    pv = PreparedVolume(layered_phantom(n, 0).to(dev), layout)
+    s_h, d_h = pose_sweep(poses, R, n, seed=3)
+    s, d = s_h.to(dev), d_h.to(dev)
+    with torch.no_grad():
+        tgt = render_frames(pv, s + torch.tensor([1.5, 0.0, -1.0], device=dev), d, S, ALPHA, sampler="trilinear")
+    dims = [n, n, n]
+
+    def step():
+        ops.render_mse_impl(pv.volume, pv.bricks, dims, s, d, tgt, S, 0, ALPHA, SAMPLER_TRILINEAR, False, False, True, False)
+    ms = timed_steps(step, 2, 5, torch.cuda.synchronize)
+    samples = poses * R * S
+    peak, _ = load_peaks()
+    gs = samples / (ms * 1e-3) / 1e9
+    rec = {"what": f"config 5: {n}^3 volume ({layout}), {R} rays x {S} samples, {poses} poses over the sphere, fused fwd+MSE+bwd with pose "
+                   "gradients: prefix-only forward pre-pass + four 512-column backward passes per ray",
+           "poses": poses, "ms_per_step": ms, "gsamples_per_s": gs, "frames_per_s": poses / (ms * 1e-3),
+           "ms_for_4096_poses": ms * 4096 / poses, "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
+           "hbm_frac_at_36B": gs * BYTES_PER_SAMPLE_FUSED / peak}
+    try:
+        hbm = ops.gather_probe(2048, device=dev)
+        # 8 gathers per sample in the backward passes + 8 in the prefix pre-pass over 3 of 4 segments
+        rec["hbm_random_sector_roof"] = {"sectors_per_s": hbm["sectors_per_s"], "buffer_mib": 2048}
+    except Exception as exc:
+        rec["hbm_random_sector_roof"] = {"error": str(exc)}
+    return rec
+
+
 def run_ours(args):
     import torch.distributed as dist
     from diffus_b200 import PreparedVolume, ops, render_frames, render_mse_loss
@@ -174,7 +372,6 @@ def run_ours(args):
     with torch.no_grad():
         shift = torch.tensor([1.5, 0.0, -1.0], device=dev)
         target = render_frames(vol, src_d + shift, dir_d, N_SAMPLES, ALPHA, 0, sampler="trilinear")
-    n_elem = target.numel()
     samples_per_step = P * N_RAYS * N_SAMPLES
     bricks = vol.bricks if isinstance(vol, PreparedVolume) else None
     vol_t = vol.volume if isinstance(vol, PreparedVolume) else vol
@@ -184,8 +381,8 @@ def run_ours(args):
     def step_device(ev=None):
         if ev:
             ev[0].record()
-        loss, _, _, gs, gd = ops.render_mse(vol_t, bricks, dims, src_d, dir_d, target, N_SAMPLES, 0, ALPHA,
-                                            SAMPLER_TRILINEAR, False, False, True, False)
+        loss, _, _, gs, gd = ops.render_mse_impl(vol_t, bricks, dims, src_d, dir_d, target, N_SAMPLES, 0, ALPHA,
+                                                 SAMPLER_TRILINEAR, False, False, True, False)
         if ev:
             ev[1].record()
         return loss, gs, gd
@@ -196,7 +393,7 @@ def run_ours(args):
     out_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
     # A pose sweep repeats the same shapes every step: the user-facing call for that is a CUDA-graph wrapper of the
-    # fused step (diffus_b200.graphs); eager autograd costs ~0.15 ms more.  "fan" (default) drives the step with the
+    # fused step (diffus_b200.graphs); eager autograd costs more.  "fan" (default) drives the step with the
     # pose PARAMETERS north_star names -- source, median direction, in-plane hint, aperture (9 floats per pose in, 9
     # gradient floats + the loss out; the fans are built and their gradient folded back on the device) -- "graph" and
     # "eager" pass explicit (P,R,3) direction tensors like the reference's plot_beam_frame.
@@ -272,17 +469,34 @@ def run_ours(args):
             torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
-    times = torch.tensor([ms_total, e2e_ms_total, step_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total, step_ms = times.tolist()
+    ms_total, e2e_ms_total, step_ms = max_over_ranks([ms_total, e2e_ms_total, step_ms], dev, world)
     ms_per_step = ms_total / K
     frames_per_s = world * P / (ms_per_step * 1e-3)
     e2e_frames_per_s = world * P / (e2e_ms_total / K * 1e-3)
+    loss_value, loss_e2e = float(loss), (float(out_pin[-1]) if args.e2e == "fan" else float(out_loss))
+
+    # ---- the other records: every rank takes part (collectives inside), rank 0 reports; a failure never costs the headline ----
+    del target, fstep, gstep
+    extras = {}
+    if not args.no_extras:
+        for name, fn in (("strong", lambda: strong_scaling_record(dev, rank, world, barrier, args.layout)),
+                         ("config4", lambda: config4_record(dev, rank, world, barrier)),
+                         ("nccl_parity", lambda: nccl_parity_record(dev, rank, world))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:                        # noqa: BLE001
+                extras[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+        if world == 1 and args.config5_poses > 0:
+            try:
+                extras["config5"] = config5_record(dev, args.config5_poses, args.layout)
+            except Exception as exc:                        # noqa: BLE001
+                extras["config5"] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        dom = "render_bwd_kernel<trilinear, pose_grad, LOSS_MSE> (fused forward + MSE + backward)"
+        dom = f"render_bwd_kernel<trilinear, {args.layout}, pose_grad, LOSS_MSE> (fused forward + MSE + backward)"
         dom_bytes = samples_per_step * BYTES_PER_SAMPLE_FUSED
         achieved = dom_bytes / (step_ms * 1e-3) / 1e9
         line = {
@@ -290,15 +504,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "gsamples_per_s": world * samples_per_step / (ms_per_step * 1e-3) / 1e9,
-            "config": {
-                "workload": f"config3 pose sweep fwd+bwd: {P} poses/GPU x {N_RAYS} rays x {N_SAMPLES} samples, "
-                            f"{VOL_N}^3 MRI-shaped impedance volume, trilinear, MSE vs target frames, "
-                            "gradients to every pose's source and directions",
-                "poses_per_gpu": P, "rays": N_RAYS, "samples": N_SAMPLES, "volume": f"{VOL_N}^3 f32",
-                "volume_layout": args.layout, "parallelism": f"pose-sharded x{world}, volume replicated",
-                "l2": "no explicit flush: inputs exceed L2 -- every step streams its own 268 MB of target frames per "
-                      "1024 poses (>> 126 MB L2, marked evict-first); the 64 MiB volume is meant to stay L2-resident",
-            },
+            "config": headline_config(P, world, args.layout),
             "e2e": {"value": e2e_frames_per_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(poses_pin.numel() * 4) if args.e2e == "fan"
                                           else int(src_pin.numel() * 4 + dir_pin.numel() * 4),
@@ -319,12 +525,15 @@ def run_ours(args):
                          "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
                          "bytes_note": "SURVEY 8(d) counts 72 B/sample for forward+backward done as two passes "
                                        "(2 x (8 gathers x 4 B + 4 B)); the fused kernel gathers once and reads the "
-                                       "target once, so its own algorithmic traffic is 36 B/sample",
+                                       "target once, so its own algorithmic traffic is 36 B/sample.  The volume is L2-resident "
+                                       "by design (DRAM is ~6 % busy): the kernel is bound by issue slots and the L1 / texture "
+                                       "path, see gather_roof and profiles/",
                          "frac_vs_two_pass_bytes": samples_per_step * 72 / (step_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,
-            "loss": float(loss),
-            "loss_e2e": float(out_pin[-1]) if args.e2e == "fan" else float(out_loss),
+            "loss": loss_value,
+            "loss_e2e": loss_e2e,
         }
+        line.update(extras)
         # the L2 gather roof from our own microbenchmark (random 32-byte sectors over a 64 MiB buffer), and
         # the same over 512 MiB (HBM random sectors: what a volume copy that does not fit L2 would run at)
         try:
@@ -339,63 +548,85 @@ def run_ours(args):
                 roof["kernel_l2_sector_reads_per_s"] = rate
                 roof["frac_of_l2_gather_roof"] = rate / l2["sectors_per_s"]
                 roof["note"] = ("the kernel's L2 -> L1 sector reads per launch are the ncu count "
-                                "(lts__t_sectors_srcunit_tex_op_read) of the committed capture; 83 % of its gather sectors "
+                                "(lts__t_sectors_srcunit_tex_op_read) of the committed capture; the rest of its gather sectors "
                                 "hit L1 and never reach L2")
             line["roofline"]["gather_roof"] = roof
         except Exception as exc:                       # the probe must never take the headline number down with it
             line["roofline"]["gather_roof"] = {"error": str(exc)}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_rays)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_rays)
+            except Exception as exc:                    # noqa: BLE001
+                line["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_sample_step(vol, src, dirs, target):
-    """One bounded sample of the workload on the CPU with the reference's own algorithm (dense solves)."""
-    from oracle import port
-    s = src.clone().requires_grad_(True)
-    d = dirs.clone().requires_grad_(True)
-    _, _, _, f = port.plot_beam_frame(vol, s, d, N_SAMPLES, ALPHA, sampler="trilinear", propagation="dense")
-    loss = torch.nn.functional.mse_loss(f, target)
-    loss.backward()
-    return float(loss.detach())
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the UNMODIFIED reference on the host cores (oracle/reference_loader.py: /root/reference or the staged archive);
+# the oracle's literal dense-solve port stands in only if neither exists (kind "port").
+# ---------------------------------------------------------------------------------------------------------------------
+CPU_SAMPLES = 128          # depth of the bounded CPU sample: the first 128 of the 512 samples of every ray
+# 128 -> 512 samples: the reference's own forward (compute_echo_traces, 128 rays) measured 1.25 s at S = 128 and 68.0 s at
+# S = 512 on 8 cores -- x54.4; its flop count grows as S^4 (x256).  The smaller factor is used.
+CPU_DEPTH_FACTOR = 68.0 / 1.25
 
 
-def cpu_scene(n_rays):
+def cpu_scene():
+    """All 128 rays of one pose of the workload, truncated to the first CPU_SAMPLES samples: the echo at depth k depends on
+    the samples up to k only, so these ARE the first 128 columns of the workload's frame."""
     from oracle import port
     vol, src, dirs = build_scene(None, 1, seed=1000)
-    lo = N_RAYS // 2 - n_rays // 2
-    d = dirs[0, lo:lo + n_rays].contiguous()
-    s = src[0]
+    d, s = dirs[0].contiguous(), src[0]
     with torch.no_grad():
-        _, _, _, target = port.plot_beam_frame(vol, s + torch.tensor([1.5, 0.0, -1.0]), d, N_SAMPLES, ALPHA,
+        _, _, _, target = port.plot_beam_frame(vol, s + torch.tensor([1.5, 0.0, -1.0]), d, CPU_SAMPLES, ALPHA,
                                                sampler="trilinear", propagation="closed_form")
     return vol, s, d, target.float()
 
 
-def bounded_cpu_rays(n_rays):
-    """The dense per-depth solves keep ~2 GB of autograd state per ray at 512 samples: stay under a quarter of free RAM."""
-    try:
-        import psutil
-        return max(1, min(n_rays, int(psutil.virtual_memory().available / 2**30 / 4 / 2)))
-    except Exception:
-        return min(n_rays, 4)
+def cpu_sample_step(vol, src, dirs, target):
+    """One bounded sample of the workload on the CPU: forward + MSE + backward to the pose through the reference's own
+    ``UltrasoundRenderer.plot_beam_frame`` (its dense per-depth solves, torch autograd) with the trilinear sampler of its
+    notebooks installed -- the only form in which the reference has pose gradients.  Returns (loss, kind)."""
+    from oracle import port
+    from oracle import reference_loader as RL
+    s = src.clone().requires_grad_(True)
+    d = dirs.clone().requires_grad_(True)
+    ref = RL.load()
+    if ref is not None:
+        ren = ref.renderer.UltrasoundRenderer(CPU_SAMPLES, ALPHA)
+        with RL.trilinear_sampler_installed(ref), RL.quiet():
+            _, _, _, f = ren.plot_beam_frame(volume=vol, source=s, directions=d, plot=False, artifacts=False, start=0)
+        kind = "reference"
+    else:
+        _, _, _, f = port.plot_beam_frame(vol, s, d, CPU_SAMPLES, ALPHA, sampler="trilinear", propagation="dense")
+        kind = "port"
+    loss = torch.nn.functional.mse_loss(f, target)
+    loss.backward()
+    return float(loss.detach()), kind
 
 
-def cpu_baseline(n_rays):
-    """Reference algorithm (oracle port: one dense solve per depth + torch autograd) on a bounded sample."""
-    n_rays = bounded_cpu_rays(n_rays)
-    vol, s, d, target = cpu_scene(n_rays)
+def sample_text(kind, dt):
+    how = ("the UNMODIFIED reference (UltrasoundRenderer.plot_beam_frame: dense per-depth solves, its notebooks' trilinear sampler, "
+           "torch autograd)" if kind == "reference" else "the oracle's literal port of the reference's dense per-depth solves + torch autograd")
+    return (f"all {N_RAYS} rays of one pose of the workload truncated to the first {CPU_SAMPLES} of {N_SAMPLES} samples, forward + MSE + "
+            f"backward to the pose, by {how}: {dt:.1f} s; the full depth does not run (about 190 GB of autograd state), so "
+            f"frames/s = 1 / (time x {CPU_DEPTH_FACTOR:.1f}), the factor being the reference's own measured forward-time ratio between "
+            f"{CPU_SAMPLES} and {N_SAMPLES} samples (its flop count, S^4, would give x256)")
+
+
+def cpu_record(dt, kind):
+    return {"value": 1.0 / (dt * CPU_DEPTH_FACTOR), "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
+            "kind": kind, "sample": sample_text(kind, dt), "sample_seconds": dt,
+            "extrapolation": {"from_samples": CPU_SAMPLES, "to_samples": N_SAMPLES, "factor": CPU_DEPTH_FACTOR}}
+
+
+def cpu_baseline(_unused=None):
+    vol, s, d, target = cpu_scene()
     t = time.perf_counter()
-    cpu_sample_step(vol, s, d, target)
-    dt = time.perf_counter() - t
-    frames = n_rays / N_RAYS
-    return {"value": frames / dt, "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
-            "kind": "port",
-            "sample": f"{n_rays} of {N_RAYS} rays of one pose, all {N_SAMPLES} samples, forward+backward with the "
-                      f"reference's per-depth dense solves (oracle/port.py propagation='dense') in {dt:.1f} s; "
-                      "frames/s = (rays/128)/time", "seconds": dt}
+    _, kind = cpu_sample_step(vol, s, d, target)
+    return cpu_record(time.perf_counter() - t, kind)
 
 
 def run_reference(args):
@@ -412,33 +643,43 @@ def run_reference(args):
         sys.stderr.write(out.stderr[-2000:])
         sys.stdout.flush()
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W = args.steps, args.warmup
-    args.cpu_rays = bounded_cpu_rays(args.cpu_rays)
-    vol, s, d, target = cpu_scene(args.cpu_rays)
+    vol, s, d, target = cpu_scene()
+    kind = "reference"
     for _ in range(min(W, 1)):
-        cpu_sample_step(vol, s, d, target)
+        _, kind = cpu_sample_step(vol, s, d, target)
     # every step is a bounded sample; the whole arm is bounded too (the GPU arm's default K is sized for a
     # 1 ms step, the CPU sample takes seconds): stop after K steps or ~100 s, whichever comes first
     t = time.perf_counter()
     done = 0
     while done < K and (done == 0 or time.perf_counter() - t < 100.0):
-        cpu_sample_step(vol, s, d, target)
+        _, kind = cpu_sample_step(vol, s, d, target)
         done += 1
     dt = (time.perf_counter() - t) / done
-    K_req, K = K, done
-    value = (args.cpu_rays / N_RAYS) / dt
+    rec = cpu_record(dt, kind)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": K, "steps_requested": K_req, "warmup": min(W, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"config3 pose sweep fwd+bwd sample: {args.cpu_rays} of {N_RAYS} rays x {N_SAMPLES} samples of one "
-                               f"pose per step, {VOL_N}^3 volume, trilinear, MSE vs target frame (CPU, reference algorithm)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{args.cpu_rays}/{N_RAYS} rays of one frame per step, dense per-depth solves + autograd"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world,
+        "steps": done, "steps_requested": K, "warmup": min(W, 1), "ms_per_step": dt * CPU_DEPTH_FACTOR * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": headline_config(args.poses, world, args.layout),
+        "cpu_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_cpu_config1 and kind == "reference":
+        # BASELINE config 1 exactly as the reference runs it: ONE full 128 x 512 frame, nearest sampler, forward only (measured, no factor)
+        from diffus_b200.phantoms import config1_pose, layered_phantom
+        from oracle import reference_loader as RL
+        ref = RL.load()
+        v1 = layered_phantom(VOL_N, seed=0)
+        s1, d1 = config1_pose(VOL_N, N_RAYS)
+        t = time.perf_counter()
+        with RL.quiet(), torch.no_grad():
+            ref.renderer.UltrasoundRenderer(N_SAMPLES, ALPHA).plot_beam_frame(volume=v1, source=s1, directions=d1, plot=False, artifacts=False)
+        t1 = time.perf_counter() - t
+        line["config1_forward"] = {"what": "BASELINE config 1 by the unmodified reference: one full 128 x 512 frame, nearest sampler, forward "
+                                           "only, measured (no extrapolation)", "s_per_frame": t1, "frames_per_s": 1.0 / t1}
     print(json.dumps(line), flush=True)
 
 
@@ -449,9 +690,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--poses", type=int, default=1024, help="poses per GPU per step")
-    ap.add_argument("--layout", default="brick", choices=["linear", "brick", "quad", "texture"])
-    ap.add_argument("--cpu-rays", type=int, default=16, help="rays in the bounded CPU sample (~2 GB and ~0.5 s each)")
+    ap.add_argument("--layout", default="texture", choices=["linear", "brick", "quad", "texture"])
+    ap.add_argument("--cpu-rays", type=int, default=128, help="(kept for compatibility; the CPU sample is all 128 rays at 128 samples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip the strong / config4 / nccl_parity / config5 records")
+    ap.add_argument("--config5-poses", type=int, default=1024, help="poses of the 512^3 stress record (N = 1 only; 0 = skip)")
+    ap.add_argument("--no-cpu-config1", action="store_true", help="reference arm: skip the full config-1 frame (~75 s on 8 cores)")
     ap.add_argument("--e2e", default="fan", choices=["fan", "graph", "eager"], help="public API used by the end-to-end loop")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -96,6 +96,17 @@ SIGNATURES = {
     "diffus_volume_texture_create": (_i32, [_vp, _P(_i32 * 3), _P(C.c_uint64), _P(C.c_uint64), _vp]),
     "diffus_volume_texture_update": (_i32, [C.c_uint64, _vp, _P(_i32 * 3), _vp]),
     "diffus_volume_texture_destroy": (_i32, [C.c_uint64, C.c_uint64]),
+    "diffus_adam_step": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "diffus_volume_slice": (_i32, [_vp, _P(_i32 * 3), _i32, _i32, _i32, _vp, _i32, _vp]),
+    "diffus_rotate_around_apex": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "diffus_log_compress_forward": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "diffus_log_compress_backward": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "diffus_rf_to_bmode": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "diffus_masked_mse_edge_forward": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp]),
+    "diffus_masked_mse_edge_backward": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "diffus_ssim_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "diffus_ssim_loss_forward": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _i64, _vp]),
+    "diffus_ssim_loss_backward": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "diffus_quad_elems": (_i64, [_P(_i32 * 3)]),
     "diffus_volume_to_quads": (_i32, [_vp, _P(_i32 * 3), _vp, _vp]),
 }

@@ -393,6 +393,96 @@ int32_t diffus_splat_backward(const float* c0, const float* c1, const float* c2,
                                     (cudaStream_t)stream));
 }
 
+int32_t diffus_adam_step(float* params, const float* grads, float* state, int64_t n, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, float grad_scale, void* stream) {
+    if (!params || !grads || !state) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    if (n > 65536) return DIFFUS_E_UNSUPPORTED;       // one CTA: every thread reads the step counter before it is advanced
+    return cuda_rc(launch_adam_step(params, grads, state, n, lr, beta1, beta2, eps, weight_decay, grad_scale, (cudaStream_t)stream));
+}
+
+int32_t diffus_volume_slice(float* volume, const int32_t dim[3], int32_t layout, int32_t axis, int32_t index, float* slice,
+                            int32_t scatter, void* stream) {
+    if (!volume || !dim || !slice) return DIFFUS_E_NULL;
+    if (dim[0] < 1 || dim[1] < 1 || dim[2] < 1 || axis < 0 || axis > 2 || index < 0 || index >= dim[axis]) return DIFFUS_E_SHAPE;
+    if (layout != DIFFUS_LAYOUT_LINEAR && layout != DIFFUS_LAYOUT_BRICK) return DIFFUS_E_ENUM;
+    return cuda_rc(launch_volume_slice(volume, dim, layout, axis, index, slice, scatter != 0, (cudaStream_t)stream));
+}
+
+int32_t diffus_rotate_around_apex(const float* x, const float* z, int64_t n, float cos_a, float sin_a, float shift, float apex0,
+                                  float apex1, float* x_rot, float* z_rot, void* stream) {
+    if (!x || !z || !x_rot || !z_rot) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_rotate_apex(x, z, n, cos_a, sin_a, shift, apex0, apex1, x_rot, z_rot, (cudaStream_t)stream));
+}
+
+int32_t diffus_log_compress_forward(const float* img, int64_t n, float* out, float* max_out, void* stream) {
+    if (!img || !out) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_log_compress_fwd(img, n, out, max_out, (cudaStream_t)stream));
+}
+
+int32_t diffus_log_compress_backward(const float* img, const float* grad_out, int64_t n, float* grad_img, void* stream) {
+    if (!img || !grad_out || !grad_img) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_log_compress_bwd(img, grad_out, n, grad_img, (cudaStream_t)stream));
+}
+
+int32_t diffus_rf_to_bmode(const float* profiles, int64_t n_rays, int32_t n_samples, const float* hilbert_kernel, float* out,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!profiles || !hilbert_kernel || !out) return DIFFUS_E_NULL;
+    if (n_rays < 1 || n_samples < 1 || n_rays >= ((int64_t)1 << 31)) return DIFFUS_E_SHAPE;
+    if (n_samples > 28000) return DIFFUS_E_UNSUPPORTED;          // a line and its kernel live in shared memory
+    if (!workspace || workspace_bytes < 4) return DIFFUS_E_WORKSPACE;
+    return cuda_rc(launch_rf_to_bmode(profiles, n_rays, n_samples, hilbert_kernel, out, workspace, (cudaStream_t)stream));
+}
+
+int32_t diffus_masked_mse_edge_forward(const float* synth, const float* real, const uint8_t* mask, int32_t H, int32_t W,
+                                       float edge_weight, float* stats, void* stream) {
+    if (!synth || !real || !mask || !stats) return DIFFUS_E_NULL;
+    if (H < 1 || W < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_masked_mse_edge_fwd(synth, real, mask, H, W, edge_weight, stats, (cudaStream_t)stream));
+}
+
+int32_t diffus_masked_mse_edge_backward(const float* synth, const float* real, const uint8_t* mask, int32_t H, int32_t W,
+                                        float edge_weight, const float* stats, const float* grad_loss, float* grad_synth,
+                                        void* stream) {
+    if (!synth || !real || !mask || !stats || !grad_loss || !grad_synth) return DIFFUS_E_NULL;
+    if (H < 1 || W < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_masked_mse_edge_bwd(synth, real, mask, H, W, edge_weight, stats, grad_loss, grad_synth, (cudaStream_t)stream));
+}
+
+int64_t diffus_ssim_workspace_bytes(int32_t H, int32_t W, int32_t ksize) {
+    if (ksize < 1 || ksize > 33 || H < ksize || W < ksize) return 0;
+    return ssim_workspace_bytes(H, W, ksize);
+}
+
+static int32_t check_ssim(const float* synth, const float* real, int32_t H, int32_t W, int32_t ksize, float sigma, void* workspace,
+                          int64_t workspace_bytes) {
+    if (!synth || !real) return DIFFUS_E_NULL;
+    if (ksize < 1 || H < ksize || W < ksize || !(sigma > 0.f)) return DIFFUS_E_SHAPE;
+    if (ksize > 33 || !(ksize & 1)) return DIFFUS_E_UNSUPPORTED;
+    if (!workspace || workspace_bytes < ssim_workspace_bytes(H, W, ksize)) return DIFFUS_E_WORKSPACE;
+    return DIFFUS_OK;
+}
+
+int32_t diffus_ssim_loss_forward(const float* synth, const float* real, int32_t H, int32_t W, int32_t ksize, float sigma, float k1,
+                                 float k2, int32_t normalize, float* loss, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!loss) return DIFFUS_E_NULL;
+    int32_t e = check_ssim(synth, real, H, W, ksize, sigma, workspace, workspace_bytes);
+    if (e) return e;
+    return cuda_rc(launch_ssim_fwd(synth, real, H, W, ksize, sigma, k1, k2, normalize, loss, workspace, (cudaStream_t)stream));
+}
+
+int32_t diffus_ssim_loss_backward(const float* synth, const float* real, int32_t H, int32_t W, int32_t ksize, float sigma,
+                                  int32_t normalize, const float* grad_loss, float* grad_synth, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    if (!grad_loss || !grad_synth) return DIFFUS_E_NULL;
+    int32_t e = check_ssim(synth, real, H, W, ksize, sigma, workspace, workspace_bytes);
+    if (e) return e;
+    return cuda_rc(launch_ssim_bwd(synth, real, H, W, ksize, sigma, normalize, grad_loss, grad_synth, workspace, (cudaStream_t)stream));
+}
+
 int32_t diffus_brain_mask(const float* volume, const int32_t dim[3], float threshold, int32_t iterations, uint8_t* mask,
                           uint8_t* scratch, void* stream) {
     if (!volume || !dim || !mask || !scratch) return DIFFUS_E_NULL;

@@ -116,6 +116,28 @@ cudaError_t launch_brain_mask(const float* volume, const int32_t dim[3], float t
                               uint8_t* scratch, cudaStream_t st);
 cudaError_t launch_masked_zscore(const float* volume, const uint8_t* mask, int64_t n, float* out, void* ws, cudaStream_t st);
 
+// train_kernels.cu
+cudaError_t launch_adam_step(float* params, const float* grads, float* state, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, float grad_scale, cudaStream_t st);
+cudaError_t launch_volume_slice(float* vol, const int32_t dim[3], int layout, int axis, int index, float* slice, bool scatter,
+                                cudaStream_t st);
+cudaError_t launch_rotate_apex(const float* x, const float* z, int64_t n, float cos_a, float sin_a, float shift, float apex0,
+                               float apex1, float* xr, float* zr, cudaStream_t st);
+cudaError_t launch_log_compress_fwd(const float* x, int64_t n, float* out, float* max_out, cudaStream_t st);
+cudaError_t launch_log_compress_bwd(const float* x, const float* gout, int64_t n, float* gx, cudaStream_t st);
+cudaError_t launch_rf_to_bmode(const float* rf, int64_t n_rays, int S, const float* g, float* out, void* workspace, cudaStream_t st);
+
+// loss_kernels.cu
+cudaError_t launch_masked_mse_edge_fwd(const float* a, const float* b, const uint8_t* mask, int H, int W, float edge_weight,
+                                       float* stats, cudaStream_t st);
+cudaError_t launch_masked_mse_edge_bwd(const float* a, const float* b, const uint8_t* mask, int H, int W, float edge_weight,
+                                       const float* stats, const float* grad_loss, float* ga, cudaStream_t st);
+int64_t ssim_workspace_bytes(int H, int W, int K);
+cudaError_t launch_ssim_fwd(const float* s, const float* y, int H, int W, int K, float sigma, float k1, float k2, int normalize,
+                            float* loss, void* workspace, cudaStream_t st);
+cudaError_t launch_ssim_bwd(const float* s, const float* y, int H, int W, int K, float sigma, int normalize, const float* grad_loss,
+                            float* grad_s, void* workspace, cudaStream_t st);
+
 // mlp_kernels.cu
 cudaError_t launch_mlp_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale,
                            float fill, float* out, cudaStream_t st);

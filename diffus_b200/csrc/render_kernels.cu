@@ -409,6 +409,128 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// d loss / d volume into a BRICK-layout gradient buffer with VECTOR reductions (red.global.add.v4.f32, sm_90+).
+//
+// What the L2 charges for a scattered reduction is the (instruction, 32-byte sector) pair -- about 195 G of them per
+// second on a B200 whether the lane carries one float or four (benchmarks/micro/red_probe.cu, profiles/r2_red_probe.md)
+// -- and the scalar scatter above pays 4.2 of them per sample.  Here a lane owns 16 CONSECUTIVE samples of the ray and
+// walks them in order, keeping in registers one 16-byte "quad" accumulator (1 x 2 x 2 voxels = 4 consecutive floats of a
+// brick: (j & 1, k & 1) at fixed i) per PARITY SLOT (i & 1, (j >> 1) & 1, (k >> 1) & 1).  A trilinear cell spans two
+// i-planes and at most two quads along j and along k, one of each parity, so its 8 corners fall into the 8 slots; along
+// a straight ray the samples that touch a given quad are consecutive, and a quad can only ever live in its own slot.  A
+// slot is therefore flushed -- ONE red.v4 -- exactly when the ray has left its quad: 1.4 vector reductions per sample
+// instead of 4.2 scalar ones (5.6 atomics), with no shared-memory atomics, no tags in memory and no divergent control flow.
+// ---------------------------------------------------------------------------------------
+#ifndef DIFFUS_SCATTER_QUADS
+#define DIFFUS_SCATTER_QUADS 1
+#endif
+constexpr uint32_t QUAD_NONE = 0xffffffffu;
+constexpr int SCATTER_RUN = PREFIX_STRIDE / 32;      // consecutive samples per lane in the scatter phase
+
+__device__ __forceinline__ void red_add_v4(float* base, uint32_t quad, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + (size_t)quad * 4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// one parity slot: accumulate `v` under `key`; when the slot holds another quad, that quad is complete -- flush it first
+__device__ __forceinline__ void quad_slot_update(float* grad, uint32_t& K, float4& acc, uint32_t key, const float4& v, bool nz) {
+    const bool miss = nz && key != K;
+    if (miss && K != QUAD_NONE) red_add_v4(grad, K, acc);
+    if (miss) { K = key; acc = make_float4(0.f, 0.f, 0.f, 0.f); }
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;          // v is all zero when !nz
+}
+
+// the two voxels (v0, v0 + 1 clamped) of a cell along j or k, split over the quad of each parity:
+// q[par] = quad index, w[par][local] = weight of the voxel at position `local` of that quad (0 if the cell does not reach it)
+__device__ __forceinline__ void split_over_quads(int v0, float f, uint32_t q[2], float w[2][2]) {
+    const float w0 = 1.f - f, w1 = f;
+    const uint32_t q0 = (uint32_t)v0 >> 1;
+    const bool odd = v0 & 1, same0 = (q0 & 1u) == 0u;
+    const float s0 = odd ? 0.f : w0, s1 = odd ? w0 : w1, o0 = odd ? w1 : 0.f;       // the quad of v0 / the next quad
+    q[0] = same0 ? q0 : q0 + 1u;
+    q[1] = same0 ? q0 + 1u : q0;
+    w[0][0] = same0 ? s0 : o0; w[0][1] = same0 ? s1 : 0.f;
+    w[1][0] = same0 ? o0 : s0; w[1][1] = same0 ? 0.f : s1;
+}
+
+template <int SAMPLER, bool POSE64>
+__device__ __forceinline__ void scatter_pass_quads(const RenderParams& p, const RaySetup<POSE64>& rs, const float* gbuf, int c0, int ncol,
+                                                   int lane) {
+    using G = BwdGeo;
+    const uint32_t qsx = p.vol.gsx >> 2, qsy = p.vol.gsy >> 2;      // brick strides in quads
+    float* grad = p.grad_volume;
+    const int col0 = lane * SCATTER_RUN;
+    if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
+        uint32_t K = QUAD_NONE;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int i = 0; i < SCATTER_RUN; ++i) {
+            const int c = col0 + i;
+            const float zbar = c < ncol ? gbuf[G::pad(c)] : 0.f;
+            const int k = p.start + c0 + c;
+            const int vi = nearest_index(rs.coord(0, k), p.vol.D), vj = nearest_index(rs.coord(1, k), p.vol.H),
+                      vk = nearest_index(rs.coord(2, k), p.vol.W);
+            const uint32_t key = ((uint32_t)vi >> 2) * qsx + (((uint32_t)vi & 3u) << 1) + ((uint32_t)vj >> 2) * qsy + (((uint32_t)vj >> 1) & 1u) +
+                                 (((uint32_t)vk >> 1) << 3);
+            const int pos = ((vj & 1) << 1) | (vk & 1);
+            const float4 v = make_float4(pos == 0 ? zbar : 0.f, pos == 1 ? zbar : 0.f, pos == 2 ? zbar : 0.f, pos == 3 ? zbar : 0.f);
+            quad_slot_update(grad, K, acc, key, v, zbar != 0.f);
+        }
+        if (K != QUAD_NONE) red_add_v4(grad, K, acc);
+        return;
+    }
+    uint32_t K[8];
+    float4 acc[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { K[s] = QUAD_NONE; acc[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll 1
+    for (int i = 0; i < SCATTER_RUN; ++i) {
+        const int c = col0 + i;
+        const float zbar = c < ncol ? gbuf[G::pad(c)] : 0.f;
+        const int k = p.start + c0 + c;
+        int i0, i1, j0, j1, k0, k1;
+        float f0, f1, f2;
+        tri_axis(rs.coord(0, k), p.vol.D, i0, i1, f0);
+        tri_axis(rs.coord(1, k), p.vol.H, j0, j1, f1);
+        tri_axis(rs.coord(2, k), p.vol.W, k0, k1, f2);
+        // i: one plane per parity (the clamped top plane repeats i0 with weight 0: a no-op)
+        const bool iodd = i0 & 1;
+        const int ip[2] = {iodd ? i1 : i0, iodd ? i0 : i1};
+        const float wi[2] = {(iodd ? f0 : 1.f - f0) * zbar, (iodd ? 1.f - f0 : f0) * zbar};
+        uint32_t jq[2], kq[2];
+        float wj[2][2], wk[2][2];
+        split_over_quads(j0, f1, jq, wj);
+        split_over_quads(k0, f2, kq, wk);
+        uint32_t X[2], Y[2], Z[2];
+        bool nzi[2], nzj[2], nzk[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            X[a] = ((uint32_t)ip[a] >> 2) * qsx + (((uint32_t)ip[a] & 3u) << 1);
+            Y[a] = (jq[a] >> 1) * qsy + (jq[a] & 1u);
+            Z[a] = kq[a] << 3;
+            nzi[a] = wi[a] != 0.f;
+            nzj[a] = wj[a][0] != 0.f || wj[a][1] != 0.f;
+            nzk[a] = wk[a][0] != 0.f || wk[a][1] != 0.f;
+        }
+#pragma unroll
+        for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+            for (int pj = 0; pj < 2; ++pj) {
+                const float a0 = wi[pi] * wj[pj][0], a1 = wi[pi] * wj[pj][1];
+#pragma unroll
+                for (int pk = 0; pk < 2; ++pk) {
+                    const int s = (pi << 2) | (pj << 1) | pk;
+                    const float4 v = make_float4(a0 * wk[pk][0], a0 * wk[pk][1], a1 * wk[pk][0], a1 * wk[pk][1]);
+                    quad_slot_update(grad, K[s], acc[s], X[pi] + Y[pj] + Z[pk], v, nzi[pi] && nzj[pj] && nzk[pk]);
+                }
+            }
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+        if (K[s] != QUAD_NONE) red_add_v4(grad, K[s], acc[s]);
+}
+
 // ONE_PASS: the ray fits one 512-column pass (every BASELINE config but the 2048-sample stress case).  The pass
 // loop disappears, so the accumulators and the adjoint carried between passes are not live during the gather; the
 // pose-only kernels then fit 96 registers and run 5 CTAs (20 warps) per SM: 0.817 -> 0.753 ms per 1024 poses.
@@ -589,11 +711,15 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
 
         // tile phase, only for the volume gradient: scatter d loss / d Z_c with lane = consecutive sample
         if (VOL_GRAD) {
-            for (int t = 0; t < ntile; ++t) {
-                int idx = t * 32 + lane;
-                if (idx < ncol) {
-                    float zbar = gbuf[G::pad(idx)];
-                    if (zbar != 0.f) scatter_volume_grad<SAMPLER, LAYOUT, POSE64>(p, rs, p.start + c0 + idx, zbar);
+            if (DIFFUS_SCATTER_QUADS && GradLayout<LAYOUT>::value == DIFFUS_LAYOUT_BRICK) {
+                scatter_pass_quads<SAMPLER, POSE64>(p, rs, gbuf, c0, ncol, lane);       // lane = 16 consecutive samples
+            } else {
+                for (int t = 0; t < ntile; ++t) {                                        // lane = consecutive sample
+                    int idx = t * 32 + lane;
+                    if (idx < ncol) {
+                        float zbar = gbuf[G::pad(idx)];
+                        if (zbar != 0.f) scatter_volume_grad<SAMPLER, LAYOUT, POSE64>(p, rs, p.start + c0 + idx, zbar);
+                    }
                 }
             }
             __syncwarp();

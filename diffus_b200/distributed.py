@@ -44,16 +44,54 @@ def shard_sizes(n_poses: int, world_size: int) -> List[int]:
             for r in range(world_size)]
 
 
-def allreduce_grads(tensors: Sequence[torch.Tensor], average: bool = False, group=None) -> None:
-    """Sum (or average) ``tensors`` over ranks IN PLACE with a single collective on a flat buffer."""
+class FlatBuffer:
+    """One persistent flat float32 buffer whose views REPLACE the given tensors' storage.
+
+    Whatever writes those tensors (autograd accumulating into ``p.grad``, a kernel handed ``view.data_ptr()``) writes
+    straight into the buffer, and the collective runs on the buffer itself -- no ``cat`` before and no ``copy_`` after."""
+
+    def __init__(self, tensors: Sequence[torch.Tensor]):
+        tensors = list(tensors)
+        n = sum(t.numel() for t in tensors)
+        self.flat = torch.zeros((n,), dtype=torch.float32, device=tensors[0].device)
+        self.views = []
+        off = 0
+        for t in tensors:
+            v = self.flat[off:off + t.numel()].view(t.shape)
+            v.copy_(t)
+            t.data = v                       # the caller's tensor now lives inside the flat buffer
+            self.views.append(v)
+            off += t.numel()
+
+    def allreduce(self, weight: float = 1.0, group=None) -> torch.Tensor:
+        _, w = world()
+        if weight != 1.0:
+            self.flat.mul_(weight)
+        if w > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return self.flat
+
+
+_module_buffers = {}       # id(module) -> FlatBuffer over its parameters' .grad tensors
+
+
+def allreduce_grads(tensors: Sequence[torch.Tensor], average: bool = False, group=None, weight: float = 1.0) -> None:
+    """``tensors <- sum over ranks of weight * tensors`` (divided by the world size if ``average``) IN PLACE, one collective.
+    One-off form for arbitrary tensors; :func:`allreduce_module_grads` keeps a persistent flat buffer instead."""
     _, w = world()
     tensors = [t for t in tensors if t is not None]
-    if w == 1 or not tensors:
+    if not tensors:
+        return
+    scale = weight / (w if average else 1)
+    if w == 1:
+        if scale != 1.0:
+            for t in tensors:
+                t.mul_(scale)
         return
     flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
+    if scale != 1.0:
+        flat *= scale
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        flat /= w
     off = 0
     for t in tensors:
         n = t.numel()
@@ -61,23 +99,53 @@ def allreduce_grads(tensors: Sequence[torch.Tensor], average: bool = False, grou
         off += n
 
 
-def allreduce_module_grads(module: torch.nn.Module, average: bool = True, group=None) -> None:
-    """All-reduce ``p.grad`` of every parameter of ``module`` (missing grads count as zero)."""
-    grads = []
-    for p in module.parameters():
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-        grads.append(p.grad)
-    allreduce_grads(grads, average=average, group=group)
+def allreduce_module_grads(module: torch.nn.Module, average: bool = False, group=None, weight: Optional[float] = None) -> None:
+    """All-reduce ``p.grad`` of every parameter of ``module`` through ONE persistent flat buffer.
+
+    The first call re-homes the ``.grad`` tensors as views of that buffer (missing grads count as zero); autograd then
+    accumulates into the views in place, so later calls run the collective on the buffer as it stands.  ``weight`` scales
+    this rank's gradients first (its share of the global batch: ragged shards stay exact); ``average`` divides by the
+    world size instead (equal shards)."""
+    _, w = world()
+    if weight is None:
+        weight = 1.0 / w if average else 1.0
+    params = [p for p in module.parameters() if p.requires_grad]
+    buf = _module_buffers.get(id(module))
+    stale = buf is None or len(buf.views) != len(params) or any(
+        p.grad is None or p.grad.data_ptr() != v.data_ptr() for p, v in zip(params, buf.views))
+    if stale:
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p, dtype=torch.float32)
+        buf = FlatBuffer([p.grad for p in params])
+        _module_buffers[id(module)] = buf
+    buf.allreduce(weight=float(weight), group=group)
+
+
+def global_share(n_local: float, device) -> float:
+    """This rank's fraction of the global batch (elements), for weighting per-rank mean losses and their gradients."""
+    _, w = world()
+    if w == 1:
+        return 1.0
+    t = torch.tensor([float(n_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t)
+    return float(n_local) / float(t.item())
 
 
 def gather_frames(local_frames: torch.Tensor, n_poses: Optional[int] = None, group=None) -> torch.Tensor:
-    """All-gather pose-sharded frames (P_local, R, S) into (P, R, S) on every rank (ragged shards allowed)."""
+    """All-gather pose-sharded frames (P_local, R, S) into (P, R, S) on every rank.  Ragged shards are allowed: with
+    ``n_poses`` the sizes follow :func:`pose_shard`; without it the ranks first exchange their shard sizes."""
     rank, w = world()
     if w == 1:
         return local_frames
-    sizes = shard_sizes(n_poses, w) if n_poses is not None else None
-    if sizes is None or len(set(sizes)) == 1:
+    if n_poses is not None:
+        sizes = shard_sizes(n_poses, w)
+    else:
+        mine = torch.tensor([local_frames.shape[0]], dtype=torch.int64, device=local_frames.device)
+        every = torch.empty((w,), dtype=torch.int64, device=local_frames.device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        sizes = [int(v) for v in every.tolist()]
+    if len(set(sizes)) == 1:
         out = local_frames.new_empty((local_frames.shape[0] * w,) + tuple(local_frames.shape[1:]))
         dist.all_gather_into_tensor(out, local_frames.contiguous(), group=group)
         return out

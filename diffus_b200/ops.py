@@ -340,7 +340,8 @@ class RenderFunction(torch.autograd.Function):
 def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: List[int], sources: torch.Tensor,
                directions: torch.Tensor, target: torch.Tensor, n_samples: int, start: int, alpha: float,
                sampler: int, product_f32: bool, need_volume: bool, need_pose: bool,
-               want_frame: bool, keep_brick_grad: bool = False
+               want_frame: bool, keep_brick_grad: bool = False, n_total: Optional[int] = None,
+               grad_volume_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None
                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """loss = mean((frame - target)^2) with d loss/d volume, d loss/d sources, d loss/d directions.
 
@@ -348,6 +349,11 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns this is ONE kernel
     launch (+ two tiny reductions); longer rays first run the forward kernel for the
     512-column segment prefixes.
+
+    ``n_total``: number of frame elements of the GLOBAL batch when this call renders one rank's shard of it -- loss and
+    gradients are then this shard's share of the global mean, so that a SUM all-reduce over ranks gives exactly the
+    single-process result even for ragged shards.  ``grad_volume_out`` (a zero-filled buffer in the gradient layout) and
+    ``loss_out`` (1 float) let a training loop hand in persistent buffers instead of fresh allocations.
     """
     dev = _require_cuda(volume, bricks, sources, directions, target)
     _check_inputs(volume, bricks, dims, sources, directions)
@@ -365,14 +371,19 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         if _nseg(sout) > 1:
             _, prefix = render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
                                         product_f32, True, prefix_only=True)
-        n = P * R * sout
+        n = P * R * sout if n_total is None else int(n_total)
         def empty():                      # outputs of a custom op must not alias each other
             return torch.empty((0,), dtype=torch.float32, device=dev)
-        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev) if loss_out is None else loss_out
         frame = torch.empty((P, R, sout), dtype=torch.float32, device=dev) if want_frame else empty()
         use_bricks = bricks is not None and bricks.numel() > 0
         gshape = _grad_volume_shape(bricks, dims)
-        gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else empty()
+        if need_volume and grad_volume_out is not None:
+            if tuple(grad_volume_out.shape) != tuple(gshape) or grad_volume_out.dtype != torch.float32:
+                raise _lib.DiffusError(f"grad_volume_out must be float32 {tuple(gshape)}")
+            gvol = grad_volume_out
+        else:
+            gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else empty()
         gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         b.fwd.frame = _ptr(frame)
@@ -848,7 +859,10 @@ def _(params, x, mask, out_scale, fill):
 
 
 def mlp_bwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
-            out_scale: float) -> torch.Tensor:
+            out_scale: float, grad_params_out: Optional[torch.Tensor] = None,
+            workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``grad_params_out`` (>= 1153 floats, ACCUMULATED into) and ``workspace`` let a training loop reuse persistent buffers:
+    the weight gradient then lands directly in the flat buffer that is all-reduced."""
     dev = _require_cuda(params, x, mask, grad_out)
     lib = _lib.load()
     p = params.contiguous().float()
@@ -856,11 +870,12 @@ def mlp_bwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Ten
     g = grad_out.contiguous().float()
     m = None if mask is None else mask.contiguous().to(torch.uint8)
     with torch.cuda.device(dev):
-        gp = torch.zeros((MLP_NPARAMS,), dtype=torch.float32, device=dev)
+        gp = torch.zeros((MLP_NPARAMS,), dtype=torch.float32, device=dev) if grad_params_out is None else grad_params_out
         n = xc.numel()
         if n:
             wbytes = lib.diffus_mlp_bwd_workspace_bytes(n)
-            ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+            ws = workspace if workspace is not None and workspace.numel() >= wbytes else \
+                torch.empty((wbytes,), dtype=torch.uint8, device=dev)
             _lib.check(lib.diffus_mlp_backward_ex(p.data_ptr(), xc.data_ptr(), _ptr(m), g.data_ptr(), n, out_scale,
                                                   gp.data_ptr(), ws.data_ptr(), wbytes, _MLP_PATH, _stream(dev)),
                        "diffus_mlp_backward")
@@ -895,3 +910,185 @@ def _mlp_backward(ctx, grad):
 
 
 torch.library.register_autograd("diffus::mlp_fwd", _mlp_backward, setup_context=_mlp_setup)
+
+
+# ---------------------------------------------------------------------------------------
+# training-loop pieces: Adam, volume slices, rotate_around_apex, log compression, image losses
+# ---------------------------------------------------------------------------------------
+def adam_step(params: torch.Tensor, grads: torch.Tensor, state: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+              weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    """One ``torch.optim.Adam`` step on a flat float32 parameter vector, in place, one launch.
+
+    ``state`` is ``[exp_avg | exp_avg_sq | step]`` (2n + 1 floats, zero before the first step)."""
+    dev = _require_cuda(params, grads, state)
+    n = params.numel()
+    if grads.numel() < n or state.numel() != 2 * n + 1 or params.dtype != torch.float32 or grads.dtype != torch.float32 \
+            or state.dtype != torch.float32 or not (params.is_contiguous() and grads.is_contiguous() and state.is_contiguous()):
+        raise _lib.DiffusError("adam_step needs contiguous float32 params (n), grads (>= n) and state (2n + 1)")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().diffus_adam_step(params.data_ptr(), grads.data_ptr(), state.data_ptr(), n, lr, betas[0], betas[1], eps,
+                                                weight_decay, grad_scale, _stream(dev)), "diffus_adam_step")
+        _count(1)
+
+
+def volume_slice(volume: torch.Tensor, dims, layout: int, axis: int, index: int, slice_: Optional[torch.Tensor] = None,
+                 scatter: bool = False) -> torch.Tensor:
+    """Copy one slice out of (``scatter=False``) or into (``scatter=True``) a LINEAR / BRICK volume buffer."""
+    dev = _require_cuda(volume, slice_)
+    rest = [d for a, d in enumerate(dims) if a != axis]
+    with torch.cuda.device(dev):
+        if slice_ is None:
+            slice_ = torch.empty(rest, dtype=torch.float32, device=dev)
+        elif slice_.numel() != rest[0] * rest[1] or slice_.dtype != torch.float32 or not slice_.is_contiguous():
+            raise _lib.DiffusError(f"slice must be contiguous float32 {tuple(rest)}")
+        _lib.check(_lib.load().diffus_volume_slice(volume.data_ptr(), C.byref((C.c_int32 * 3)(*dims)), layout, axis, index,
+                                                   slice_.data_ptr(), int(scatter), _stream(dev)), "diffus_volume_slice")
+        _count(1)
+    return slice_
+
+
+class SliceInsertFunction(torch.autograd.Function):
+    """``out = volume.clone(); out[..., index (along axis) ...] = slice`` with gradients to both (LINEAR layout)."""
+
+    @staticmethod
+    def forward(ctx, volume, slice_, axis, index):
+        out = volume.detach().clone()
+        volume_slice(out, list(out.shape), LAYOUT_LINEAR, axis, index, slice_.detach().contiguous().float(), scatter=True)
+        ctx.meta = (axis, index)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        axis, index = ctx.meta
+        g = grad.contiguous().float()
+        gs = volume_slice(g, list(g.shape), LAYOUT_LINEAR, axis, index) if ctx.needs_input_grad[1] else None
+        gv = None
+        if ctx.needs_input_grad[0]:                  # the inserted slice replaced the volume's own values: no gradient there
+            gv = g.clone()
+            rest = [d for a, d in enumerate(g.shape) if a != axis]
+            volume_slice(gv, list(gv.shape), LAYOUT_LINEAR, axis, index, torch.zeros(rest, dtype=torch.float32, device=g.device),
+                         scatter=True)
+        return gv, gs, None, None
+
+
+def rotate_apex(x: torch.Tensor, z: torch.Tensor, cos_a: float, sin_a: float, shift: float, apex0: float, apex1: float):
+    dev = _require_cuda(x, z)
+    xf, zf = x.to(torch.float32).contiguous(), z.to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        xr, zr = torch.empty_like(xf), torch.empty_like(zf)
+        if xf.numel():
+            _lib.check(_lib.load().diffus_rotate_around_apex(xf.data_ptr(), zf.data_ptr(), xf.numel(), cos_a, sin_a, shift, apex0, apex1,
+                                                             xr.data_ptr(), zr.data_ptr(), _stream(dev)), "diffus_rotate_around_apex")
+            _count(1)
+    return xr, zr
+
+
+class LogCompressFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img):
+        dev = _require_cuda(img)
+        x = img.detach().contiguous().float()
+        with torch.cuda.device(dev):
+            out = torch.empty_like(x)
+            _lib.check(_lib.load().diffus_log_compress_forward(x.data_ptr(), x.numel(), out.data_ptr(), None, _stream(dev)),
+                       "diffus_log_compress_forward")
+            _count(1)
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        (x,) = ctx.saved_tensors
+        g = grad.contiguous().float()
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x)
+            _lib.check(_lib.load().diffus_log_compress_backward(x.data_ptr(), g.data_ptr(), x.numel(), gx.data_ptr(), _stream(x.device)),
+                       "diffus_log_compress_backward")
+            _count(1)
+        return gx
+
+
+def rf_to_bmode(profiles: torch.Tensor, hilbert_kernel: torch.Tensor) -> torch.Tensor:
+    dev = _require_cuda(profiles, hilbert_kernel)
+    rf = profiles.detach().contiguous().float()
+    if rf.dim() != 2 or hilbert_kernel.numel() != rf.shape[1]:
+        raise _lib.DiffusError("profiles must be (n_rays, n_samples) and the Hilbert kernel n_samples long")
+    with torch.cuda.device(dev):
+        out = torch.empty_like(rf)
+        ws = torch.empty((4,), dtype=torch.uint8, device=dev)
+        _lib.check(_lib.load().diffus_rf_to_bmode(rf.data_ptr(), rf.shape[0], rf.shape[1], hilbert_kernel.contiguous().float().data_ptr(),
+                                                  out.data_ptr(), ws.data_ptr(), 4, _stream(dev)), "diffus_rf_to_bmode")
+        _count(3)
+    return out
+
+
+class MaskedMSEEdgeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, synth, real, mask, edge_weight):
+        dev = _require_cuda(synth, real, mask)
+        if synth.dim() != 2 or real.shape != synth.shape or mask.shape != synth.shape:
+            raise _lib.DiffusError("synth, real and mask must be (H, W) images of one shape")
+        a, b = synth.detach().contiguous().float(), real.detach().contiguous().float()
+        m = mask.contiguous().to(torch.uint8)
+        H, W = a.shape
+        with torch.cuda.device(dev):
+            stats = torch.empty((3,), dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().diffus_masked_mse_edge_forward(a.data_ptr(), b.data_ptr(), m.data_ptr(), H, W, edge_weight,
+                                                                  stats.data_ptr(), _stream(dev)), "diffus_masked_mse_edge_forward")
+            _count(1)
+        ctx.save_for_backward(a, b, m, stats)
+        ctx.edge_weight = edge_weight
+        return stats[0].clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        a, b, m, stats = ctx.saved_tensors
+        H, W = a.shape
+        g = grad.reshape(1).contiguous().float()
+        with torch.cuda.device(a.device):
+            ga = torch.empty_like(a)
+            _lib.check(_lib.load().diffus_masked_mse_edge_backward(a.data_ptr(), b.data_ptr(), m.data_ptr(), H, W, ctx.edge_weight,
+                                                                   stats.data_ptr(), g.data_ptr(), ga.data_ptr(), _stream(a.device)),
+                       "diffus_masked_mse_edge_backward")
+            _count(1)
+        return ga, None, None, None
+
+
+class SSIMLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, synth, real, normalize, ksize, sigma, k1, k2):
+        dev = _require_cuda(synth, real)
+        if synth.dim() != 2 or real.shape != synth.shape:
+            raise _lib.DiffusError("synth and real must be (H, W) images of one shape")
+        a, b = synth.detach().contiguous().float(), real.detach().contiguous().float()
+        H, W = a.shape
+        lib = _lib.load()
+        wbytes = lib.diffus_ssim_workspace_bytes(H, W, ksize)
+        if wbytes <= 0:
+            raise _lib.DiffusError(f"SSIM window {ksize} does not fit a {H} x {W} image (or exceeds 33)")
+        with torch.cuda.device(dev):
+            ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+            loss = torch.empty((1,), dtype=torch.float32, device=dev)
+            _lib.check(lib.diffus_ssim_loss_forward(a.data_ptr(), b.data_ptr(), H, W, ksize, sigma, k1, k2, int(normalize), loss.data_ptr(),
+                                                    ws.data_ptr(), wbytes, _stream(dev)), "diffus_ssim_loss_forward")
+            _count(3)
+        ctx.save_for_backward(a, b, ws)
+        ctx.meta = (int(normalize), ksize, sigma)
+        return loss.reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        a, b, ws = ctx.saved_tensors
+        normalize, ksize, sigma = ctx.meta
+        H, W = a.shape
+        g = grad.reshape(1).contiguous().float()
+        with torch.cuda.device(a.device):
+            ga = torch.empty_like(a)
+            _lib.check(_lib.load().diffus_ssim_loss_backward(a.data_ptr(), b.data_ptr(), H, W, ksize, sigma, normalize, g.data_ptr(),
+                                                             ga.data_ptr(), ws.data_ptr(), ws.numel(), _stream(a.device)),
+                       "diffus_ssim_loss_backward")
+            _count(2)
+        return ga, None, None, None, None, None, None

@@ -327,19 +327,16 @@ def differentiable_splat(x, y, z, intensities, H=256, W=256, sigma=2.0):
 def rotate_around_apex(x, z, apex, median):
     """Rotate fan points so that the median direction maps onto [0, 1] (reference ``src/renderer.py:655-692``).
 
-    Same arithmetic as the reference (which shifts x by the hard-wired 128, not by the apex): a 2x2 rotation of
-    two coordinate arrays -- element-wise work on the caller's device that feeds :func:`differentiable_splat`.
+    Same arithmetic as the reference (which shifts x by the hard-wired 128, not by the apex).  The rotation angle is
+    formed from ``median`` in float32 with the reference's own torch expression (three scalars, on the host); the
+    element-wise part is ONE kernel with the reference's rounding order, feeding :func:`differentiable_splat`.
     """
-    device = x.device
-    x_shifted = x - 128
-    z_shifted = z
-    median_vec = torch.tensor(median, dtype=torch.float32, device=device)
+    median_vec = torch.as_tensor(median, dtype=torch.float32).detach().cpu()
     median_vec = median_vec / median_vec.norm()
     angle = torch.atan2(median_vec[0], median_vec[1])
-    cos_a, sin_a = torch.cos(angle), torch.sin(angle)
-    x_rot = cos_a * x_shifted - sin_a * z_shifted + apex[0]
-    z_rot = sin_a * x_shifted + cos_a * z_shifted + apex[1]
-    return x_rot, z_rot
+    cos_a, sin_a = float(torch.cos(angle)), float(torch.sin(angle))
+    apex = torch.as_tensor(apex, dtype=torch.float32).detach().cpu()
+    return ops.rotate_apex(x, z, cos_a, sin_a, 128.0, float(apex[0]), float(apex[1]))
 
 
 def custom_nearest_sampler(Z: torch.Tensor, points: torch.Tensor, visualize: bool = False, sampler: str = "prop",

@@ -227,6 +227,59 @@ int32_t diffus_splat_backward(const float* c0, const float* c1, const float* c2,
                               float* grad_intensities, void* workspace, int64_t workspace_bytes,
                               void* stream);
 
+/* ---- training-loop pieces around the path (reference notebooks) ------------------------------- */
+
+/* torch.optim.Adam step (the optimiser of src/impedance.py:26-35 and of the training notebooks; no amsgrad) on n <= 65536
+ * parameters in ONE launch: g = grad_scale * grads (+ weight_decay * p), moments, bias correction, update, step counter.
+ * state = [exp_avg (n) | exp_avg_sq (n) | step (1)] floats, zero-filled by the caller before the first step. */
+int32_t diffus_adam_step(float* params, const float* grads, float* state, int64_t n, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, float grad_scale, void* stream);
+
+/* One slice of a LINEAR or BRICK volume, `index` along `axis` (0, 1, 2), as a dense row-major 2-D array over the two other
+ * axes: scatter = 0 copies volume -> slice, scatter = 1 copies slice -> volume.  ImpedanceLearner.training_forward's slice
+ * mode (notebooks/[DEMO] Train MRI to Impedance MLP - GPU.ipynb cell 16: Z_vol = x.clone(); Z_vol[:, :, k] = mlp(x[:, :, k])). */
+int32_t diffus_volume_slice(float* volume, const int32_t dim[3], int32_t layout, int32_t axis, int32_t index, float* slice,
+                            int32_t scatter, void* stream);
+
+/* rotate_around_apex (src/renderer.py:655-692): x_rot = cos (x - shift) - sin z + apex0, z_rot = sin (x - shift) + cos z + apex1
+ * (the reference hard-wires shift = 128), one rounding per operation like the reference's torch expression. */
+int32_t diffus_rotate_around_apex(const float* x, const float* z, int64_t n, float cos_a, float sin_a, float shift, float apex0,
+                                  float apex1, float* x_rot, float* z_rot, void* stream);
+
+/* Log compression (north_star's "log-compressed B-mode"; the reference's only form is process_rf_to_bmode,
+ * notebooks/[DEMO] Renderer Alternatives.ipynb cell 14: log1p(envelope) / max).
+ * diffus_log_compress_*: out = log1p(|img|) / max(log1p(|img|)) over n pixels, and its backward (the maximum's gradient is
+ * spread evenly over its ties, torch's rule); max_out (1 float) may be NULL.
+ * diffus_rf_to_bmode: the notebook function itself on (n_rays, n_samples) RF lines: envelope = |analytic signal| with the
+ * analytic signal of scipy.signal.hilbert along the samples -- its imaginary part is the circular convolution with
+ * hilbert_kernel = Im(ifft(h)) (n_samples floats, h = scipy's one-sided spectrum weights; host-computed) -- then log1p and
+ * division by the maximum over the whole array.  workspace: 4 bytes. */
+int32_t diffus_log_compress_forward(const float* img, int64_t n, float* out, float* max_out, void* stream);
+int32_t diffus_log_compress_backward(const float* img, const float* grad_out, int64_t n, float* grad_img, void* stream);
+int32_t diffus_rf_to_bmode(const float* profiles, int64_t n_rays, int32_t n_samples, const float* hilbert_kernel, float* out,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Losses of the training notebooks on (H, W) images, forward and backward w.r.t. the synthetic image.
+ * masked MSE + edge ([DEMO] Train MRI to Impedance MLP.ipynb cell 19, UltrasoundSynthesisModel.loss / gradient_loss):
+ *   loss = mean((a - b)^2 over mask) + edge_weight * mean(| |a[:,1:] - a[:,:-1]| - |b[:,1:] - b[:,:-1]| | over mask[:,1:]);
+ *   stats (3 floats) = [loss, count(mask), count(mask[:,1:])], written by the forward and read by the backward.
+ * 1 - SSIM ([DEMO] Train MRI to Impedance MLP - GPU.ipynb cell 16): with normalize != 0 the synthetic image is first mapped
+ *   to (s - min) / (max - min + 1e-8); SSIM is piq.ssim's algorithm (Gaussian window ksize x ksize, sigma, VALID filtering,
+ *   k1, k2, data_range 1, mean over the map; piq is not vendored by the reference: defaults 11, 1.5, 0.01, 0.03).
+ *   The backward needs the workspace the forward filled. */
+int32_t diffus_masked_mse_edge_forward(const float* synth, const float* real, const uint8_t* mask, int32_t H, int32_t W,
+                                       float edge_weight, float* stats, void* stream);
+int32_t diffus_masked_mse_edge_backward(const float* synth, const float* real, const uint8_t* mask, int32_t H, int32_t W,
+                                        float edge_weight, const float* stats, const float* grad_loss, float* grad_synth,
+                                        void* stream);
+int64_t diffus_ssim_workspace_bytes(int32_t H, int32_t W, int32_t ksize);
+int32_t diffus_ssim_loss_forward(const float* synth, const float* real, int32_t H, int32_t W, int32_t ksize, float sigma,
+                                 float k1, float k2, int32_t normalize, float* loss, void* workspace, int64_t workspace_bytes,
+                                 void* stream);
+int32_t diffus_ssim_loss_backward(const float* synth, const float* real, int32_t H, int32_t W, int32_t ksize, float sigma,
+                                  int32_t normalize, const float* grad_loss, float* grad_synth, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
+
 /* MRI preprocessing in front of the MLP (src/utils.py:12-39, called from compute_impedance_volume,
  * src/impedance.py:46-47).  diffus_brain_mask: create_brain_mask = (volume > threshold), `iterations`
  * binary dilations then `iterations` binary erosions (scipy defaults: 6-neighbour cross, border value 0;

@@ -264,6 +264,76 @@ def impedance_volume_cases(ref):
     np.savez_compressed(os.path.join(OUT, "impedance_volume.npz"), **out)
 
 
+def _notebook_cell(name, index):
+    import json
+    with open(os.path.join(RL.REFERENCE_ROOT, "notebooks", name)) as f:
+        return "".join(json.load(f)["cells"][index]["source"])
+
+
+def training_loop_cases(ref):
+    """Row f3 / f1-epilogue fixtures.  rotate_around_apex: the reference function.  masked MSE + edge loss and
+    process_rf_to_bmode: the notebook cells' own source, executed (they are not importable modules).  Adam: torch.optim.Adam.
+    SSIM: piq is absent, so those numbers come from oracle/port.py's restatement (flagged in the fixture)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import port
+    R = ref.renderer
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    # rotate_around_apex on index-like coordinates (the notebooks pass x.float(), z.float())
+    x = torch.randint(0, 256, (480,), generator=g).float()          # 1-D, as HEAD's matrix product requires (:686-687)
+    z = torch.randint(0, 256, (480,), generator=g).float()
+    apex, median = [131.7, 20.25], [-0.3, -0.9]
+    with RL.quiet():
+        xr, zr = R.rotate_around_apex(x, z, apex=torch.tensor(apex), median=median)
+    out["rot_x"], out["rot_z"], out["rot_apex"], out["rot_median"] = _np(x), _np(z), np.array(apex), np.array(median)
+    out["rot_x_out"], out["rot_z_out"] = _np(xr), _np(zr)
+    # the CPU notebook's loss, from its own cell source
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "device": "cpu", "UltrasoundRenderer": R.UltrasoundRenderer,
+          "rotate_around_apex": R.rotate_around_apex, "differentiable_splat": R.differentiable_splat}
+    exec(_notebook_cell("[DEMO] Train MRI to Impedance MLP.ipynb", 19), ns)
+    usm = ns["UltrasoundSynthesisModel"].__new__(ns["UltrasoundSynthesisModel"])
+    H, W = 37, 44
+    real = torch.rand((H, W), generator=g, dtype=torch.float64)
+    synth = (real + 0.2 * torch.randn((H, W), generator=g, dtype=torch.float64)).requires_grad_(True)
+    mask = torch.rand((H, W), generator=g) > 0.35
+    mask[:, 0] = True
+    usm.us_real_norm, usm.mask = real, mask
+    with RL.quiet():
+        loss = usm.loss(synth)
+    (gs,) = torch.autograd.grad(loss, synth)
+    out["mse_edge_synth"], out["mse_edge_real"], out["mse_edge_mask"] = _np(synth), _np(real), _np(mask)
+    out["mse_edge_loss"], out["mse_edge_grad"] = _np(loss), _np(gs)
+    # process_rf_to_bmode from its notebook cell (scipy.signal.hilbert), even and odd line lengths
+    ns2 = {}
+    exec(_notebook_cell("[DEMO] Renderer Alternatives.ipynb", 14).split("def plot_bmode_image")[0], ns2)
+    stubs = {k: sys.modules.pop(k) for k in ("jax", "jax.numpy") if k in sys.modules}     # scipy's array-API probe trips over the jax stub
+    for name, shape in (("rf_even", (6, 64)), ("rf_odd", (5, 33))):
+        rf = 0.05 * torch.randn(shape, generator=g)
+        out[name], out[name + "_bmode"] = _np(rf), ns2["process_rf_to_bmode"](rf)
+    sys.modules.update(stubs)
+    # torch.optim.Adam on the 1 153 weights, lr 0.01 as in the GPU notebook
+    p0 = torch.randn(1153, generator=g)
+    grads = [torch.randn(1153, generator=g) * 10.0 ** (-i) for i in range(4)]
+    steps = port.adam_steps(p0, grads, lr=0.01)
+    out["adam_p0"], out["adam_grads"], out["adam_params"] = _np(p0), _np(torch.stack(grads)), _np(torch.stack(steps))
+    steps_wd = port.adam_steps(p0, grads, lr=1e-3, betas=(0.8, 0.99), eps=1e-6, weight_decay=0.1)
+    out["adam_params_wd"] = _np(torch.stack(steps_wd))
+    # SSIM loss (port; piq absent): a splat-like image with an exact-zero background (ties at the minimum)
+    H, W = 48, 40
+    real = torch.rand((H, W), generator=g, dtype=torch.float64)
+    synth = torch.zeros((H, W), dtype=torch.float64)
+    synth[8:40, 5:33] = real[8:40, 5:33] * 3.0 + 0.3 * torch.randn((32, 28), generator=g, dtype=torch.float64)
+    synth.requires_grad_(True)
+    for tag, norm in (("ssim_norm", True), ("ssim_raw", False)):
+        l = port.ssim_loss(synth, real, normalize=norm)
+        (gs,) = torch.autograd.grad(l, synth)
+        out[tag + "_loss"], out[tag + "_grad"] = _np(l), _np(gs)
+    out["ssim_synth"], out["ssim_real"] = _np(synth), _np(real)
+    out["ssim_made_by"] = np.array("oracle/port.py restatement of piq.ssim (piq is not installed; parity unpinned)")
+    np.savez_compressed(os.path.join(OUT, "training_loop.npz"), **out)
+
+
 def _volume_fingerprint(vol):
     """A few numbers that pin a seeded volume regenerated on another machine (the 64 MiB tensor is not stored)."""
     v = vol.double().reshape(-1)
@@ -349,7 +419,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     fns = (echo_cases, frame_cases, trilinear_cases, cone_cases, mlp_cases, splat_cases, impedance_volume_cases, brain_phantom2d_cases,
-           median_tie_cases, config2_reduced_cases, config1_full_cases)      # the last one takes ~4 minutes
+           training_loop_cases, median_tie_cases, config2_reduced_cases, config1_full_cases)      # the last one takes ~4 minutes
     for fn in fns:
         if only and fn.__name__ not in only:
             continue

@@ -361,3 +361,109 @@ def flops_dense_per_ray(n_interfaces: int) -> float:
 
 
 __all__ = [n for n in dir() if not n.startswith("_") and n not in ("math", "np", "torch", "annotations")]
+
+
+# ----------------------------------------------------------------------------------------
+# training-loop pieces  -- SURVEY row f3 / f1 epilogue
+# ----------------------------------------------------------------------------------------
+
+
+def rotate_around_apex(x, z, apex, median):
+    """``src/renderer.py:655-692``: shift x by the hard-wired 128, rotate by atan2(m_x, m_y) of the normalised median with a
+    2 x 2 matrix product over the stacked 1-D coordinate arrays, add the apex."""
+    x_shifted = x - 128
+    z_shifted = z
+    median_vec = torch.as_tensor(median, dtype=torch.float32)
+    median_vec = median_vec / median_vec.norm()
+    angle = torch.atan2(median_vec[0], median_vec[1])
+    cos_a, sin_a = torch.cos(angle), torch.sin(angle)
+    rot = torch.tensor([[cos_a, -sin_a], [sin_a, cos_a]])
+    rotated = rot @ torch.stack((x_shifted, z_shifted), dim=0)
+    return rotated[0] + apex[0], rotated[1] + apex[1]
+
+
+def masked_mse_edge_loss(a, b, mask, edge_weight=0.5):
+    """``UltrasoundSynthesisModel.loss`` + ``gradient_loss`` of ``notebooks/[DEMO] Train MRI to Impedance MLP.ipynb`` cell 19:
+    ``mse(a[mask], b[mask]) + 0.5 * l1(|a[:,1:] - a[:,:-1]|[mask[:,1:]], |b[:,1:] - b[:,:-1]|[mask[:,1:]])``."""
+    import torch.nn.functional as F
+    main = F.mse_loss(a[mask], b[mask])
+    a_grad = torch.abs(a[:, 1:] - a[:, :-1])
+    b_grad = torch.abs(b[:, 1:] - b[:, :-1])
+    return main + edge_weight * F.l1_loss(a_grad[mask[:, 1:]], b_grad[mask[:, 1:]])
+
+
+def ssim_piq(x, y, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03):
+    """``piq.ssim(x, y, data_range=1.0)`` for single-channel (H, W) images below 384 pixels (no down-sampling).
+
+    piq is a dependency of the reference's GPU training notebook (cell 16) that is neither vendored by the reference nor
+    installed here, so this is a restatement of its published algorithm (piq 0.8 ``ssim`` / ``_ssim_per_channel`` /
+    ``gaussian_filter``; Wang et al. 2004) and NOT pinned by running piq: window = outer product of
+    ``exp(-(i - (K-1)/2)^2 / (2 sigma^2))`` normalised to sum 1; VALID filtering (no padding); ``mu_x, mu_y``;
+    ``sigma_xx = E[x^2] - mu_x^2`` etc.; ``cs = (2 sigma_xy + c2) / (sigma_xx + sigma_yy + c2)``;
+    ``ss = (2 mu_x mu_y + c1) / (mu_x^2 + mu_y^2 + c1) * cs``; mean over the map; ``c1 = k1^2, c2 = k2^2`` at data_range 1.
+    """
+    import torch.nn.functional as F
+    coords = torch.arange(kernel_size, dtype=x.dtype) - (kernel_size - 1) / 2.0
+    g = coords ** 2
+    g = (-(g.unsqueeze(0) + g.unsqueeze(1)) / (2 * kernel_sigma ** 2)).exp()
+    kernel = (g / g.sum())[None, None]
+    X, Y = x[None, None], y[None, None]
+    c1, c2 = k1 ** 2, k2 ** 2
+    mu_x, mu_y = F.conv2d(X, kernel), F.conv2d(Y, kernel)
+    mu_xx, mu_yy, mu_xy = mu_x ** 2, mu_y ** 2, mu_x * mu_y
+    sigma_xx = F.conv2d(X ** 2, kernel) - mu_xx
+    sigma_yy = F.conv2d(Y ** 2, kernel) - mu_yy
+    sigma_xy = F.conv2d(X * Y, kernel) - mu_xy
+    cs = (2.0 * sigma_xy + c2) / (sigma_xx + sigma_yy + c2)
+    ss = (2.0 * mu_xy + c1) / (mu_xx + mu_yy + c1) * cs
+    return ss.mean()
+
+
+def ssim_loss(synth, real, normalize=True, **kw):
+    """``UltrasoundSynthesisModel.loss`` of ``notebooks/[DEMO] Train MRI to Impedance MLP - GPU.ipynb`` cell 16:
+    ``synth = (synth - min) / (max - min + 1e-8)``; ``1 - piq.ssim(synth, real, data_range=1.0)``."""
+    if normalize:
+        synth = (synth - synth.min()) / (synth.max() - synth.min() + 1e-8)
+    return 1 - ssim_piq(synth, real, **kw)
+
+
+def process_rf_to_bmode(profiles):
+    """``notebooks/[DEMO] Renderer Alternatives.ipynb`` cell 14: ``log1p(|hilbert(rf, axis=1)|) / max``.
+
+    ``scipy.signal.hilbert`` restated with numpy's FFT (its algorithm: ``ifft(fft(x) * h)`` with ``h = [1, 2, .., 2, 1, 0, ..]``
+    for even and ``[1, 2, .., 2, 0, ..]`` for odd lengths); the fixture in tests/golden was made by the notebook's own cell
+    with scipy."""
+    rf = profiles.detach().cpu().numpy().astype(np.float64)
+    n = rf.shape[1]
+    h = np.zeros(n)
+    if n % 2 == 0:
+        h[0] = h[n // 2] = 1
+        h[1:n // 2] = 2
+    else:
+        h[0] = 1
+        h[1:(n + 1) // 2] = 2
+    analytic = np.fft.ifft(np.fft.fft(rf, axis=1) * h[None, :], axis=1)
+    bmode = np.log1p(np.abs(analytic))
+    return bmode / np.max(bmode)
+
+
+def log_compress(img):
+    """The log-compression step alone, differentiable: ``log1p(|img|) / max(log1p(|img|))``."""
+    b = torch.log1p(img.abs())
+    return b / b.max()
+
+
+def adam_steps(params, grads, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """``torch.optim.Adam`` (the optimiser of ``src/impedance.py:26-35`` and of the training notebooks) applied to one flat
+    parameter vector for the given sequence of gradients; returns the parameter vector after every step."""
+    p = torch.nn.Parameter(params.clone())
+    opt = torch.optim.Adam([p], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+    out = []
+    for g in grads:
+        p.grad = g.clone()
+        opt.step()
+        out.append(p.detach().clone())
+    return out
+
+
+__all__ = [n for n in dir() if not n.startswith("_") and n not in ("math", "np", "torch", "annotations")]

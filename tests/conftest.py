@@ -102,21 +102,50 @@ def assert_frame_close(got, want, what="", atol=FRAME_ATOL, rtol=FRAME_RTOL):
                           f"{ratio:.2f} x the tolerance ({atol:g} x peak {peak:.3e} + {rtol:g} |ref|)")
 
 
-def assert_grad_close(got, want, what="", rtol=GRAD_RTOL, floor=GRAD_FLOOR):
+NOISE_FACTOR = 8.0
+
+
+def oracle_grads(fn, *tensors):
+    """Gradients of the CPU oracle in float64 AND the float32 noise of the same arithmetic.
+
+    ``fn(*tensors_in_dtype)`` returns ``loss`` or ``(loss, aux)``; the float tensors are cast to float64 (the reference
+    value) and to float32 (how far the reference's OWN algorithm drifts in the precision the kernels and the reference's
+    fp32 runs work in).  Returns ``(grads64, noise, aux64)`` with ``noise[i] = max |grad32_i - grad64_i|`` (0 for an unused
+    input).  ``assert_grad_close(..., noise=noise[i])`` then holds the kernel to 1e-4 element-wise OR to NOISE_FACTOR x that
+    drift, whichever is larger: sums over hundreds of samples that cancel (d/d directions = sum_k k zbar_k grad Z_k) cannot be
+    reproduced to 1e-4 of a small entry by ANY float32 evaluation, the reference's included."""
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        ins = [t.detach().to(dt).requires_grad_(True) for t in tensors]
+        res = fn(*ins)
+        loss, aux = res if isinstance(res, tuple) else (res, None)
+        grads = torch.autograd.grad(loss, ins, allow_unused=True)
+        out[dt] = (grads, aux)
+    g64, aux64 = out[torch.float64]
+    g32, _ = out[torch.float32]
+    noise = [0.0 if a is None else float((b.double() - a).abs().max()) for a, b in zip(g64, g32)]
+    return g64, noise, aux64
+
+
+def assert_grad_close(got, want, what="", rtol=GRAD_RTOL, floor=GRAD_FLOOR, noise=None, noise_factor=NOISE_FACTOR):
     """fp32 kernels vs fp64 autograd: |got - want| <= rtol |want| for every entry with |want| > floor * max|want|,
-    and <= rtol * floor * max|want| for the entries below that."""
+    and <= rtol * floor * max|want| for the entries below that.  ``noise`` (see :func:`oracle_grads`): the absolute error the
+    reference algorithm itself makes in float32 on this input; entries are then allowed ``noise_factor * noise`` if that is larger."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
     if got.size == 0:
         return
-    scale = max(float(np.abs(want).max()), 1e-300)
+    scale = max(float(np.abs(want).max()), 1e-20)
     err = np.abs(got - want)
-    tol = rtol * np.maximum(np.abs(want), floor * scale)
+    strict = rtol * np.maximum(np.abs(want), floor * scale)
+    tol = strict if noise is None else np.maximum(strict, noise_factor * float(noise))
     ratio = float((err / tol).max())
-    _record("grad", what, ratio, {"max_err_over_scale": float(err.max() / scale), "scale": scale})
+    _record("grad", what, ratio, {"max_err_over_scale": float(err.max() / scale), "scale": scale,
+                                  "strict_ratio": float((err / strict).max()),
+                                  "err_over_noise": None if not noise else float(err.max() / float(noise))})
     if _CALIBRATE:
         return
     k = np.unravel_index((err / tol).argmax(), err.shape)
     assert ratio <= 1.0, (f"{what}: entry {k}: got {got[k]:.6e} want {want[k]:.6e} (|ref| max {scale:.3e}); "
-                          f"{ratio:.2f} x the tolerance (rtol {rtol:g}, floor {floor:g})")
+                          f"{ratio:.2f} x the tolerance (rtol {rtol:g}, floor {floor:g}, fp32 noise of the oracle {noise})")

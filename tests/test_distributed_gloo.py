@@ -36,6 +36,20 @@ def _worker(rank, world, port, n_poses, q):
         D.allreduce_module_grads(model, average=True)
         want = [sum(r + 1 for r in range(world)) / world * (i + 1) for i in range(6)]
         ok_grads = all(bool(torch.allclose(p.grad, torch.full_like(p, w))) for p, w in zip(model.parameters(), want))
+        # second step: autograd-style in-place accumulation lands in the SAME persistent flat buffer (no cat / copy_ back)
+        ptrs = [p.grad.data_ptr() for p in model.parameters()]
+        for i, p in enumerate(model.parameters()):
+            p.grad.zero_()
+            p.grad.add_(float(rank + 2) * (i + 1))
+        share = D.global_share(sl.stop - sl.start, torch.device("cpu"))
+        D.allreduce_module_grads(model, weight=share)
+        sizes = D.shard_sizes(n_poses, world)
+        want2 = [sum((r + 2) * sizes[r] for r in range(world)) / n_poses * (i + 1) for i in range(6)]
+        ok_grads = ok_grads and ptrs == [p.grad.data_ptr() for p in model.parameters()] and \
+            all(bool(torch.allclose(p.grad, torch.full_like(p, w))) for p, w in zip(model.parameters(), want2))
+        # ragged shards without n_poses: the ranks exchange their sizes first
+        frames2 = D.gather_frames(local)
+        ok_gather = ok_gather and frames2.shape == (n_poses, 3, 5) and all(bool((frames2[p] == p).all()) for p in range(n_poses))
         shared = [torch.tensor([1.0, 2.0, 3.0]) * (rank + 1), None, torch.ones(2, 2) * rank]
         D.allreduce_grads(shared)
         ok_sum = bool(torch.allclose(shared[0], torch.tensor([1.0, 2.0, 3.0]) * sum(r + 1 for r in range(world)))) and \

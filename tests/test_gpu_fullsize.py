@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_frame_close, assert_grad_close, load_golden
+from conftest import assert_frame_close, assert_grad_close, load_golden, oracle_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -58,7 +58,7 @@ def test_config1_full_size_vs_reference_fixture(layout):
     # the fused one-pass kernel (the one the benchmark times) forms the same frame
     loss, fr = render_mse_loss(vv, src.to(dev()).reshape(1, 3), dirs.to(dev()), torch.zeros((1, 128, 512), device=dev()),
                                512, float(g["alpha"]), 0, sampler="nearest", return_frame=True)
-    assert_frame_close(fr[0].cpu().numpy(), g["frame64"], "config 1 through the fused kernel")
+    assert_frame_close(fr[0].detach().cpu().numpy(), g["frame64"], "config 1 through the fused kernel")
     np.testing.assert_allclose(loss.item(), float(np.mean(np.square(g["frame64"]))), rtol=1e-4)
 
 
@@ -70,6 +70,11 @@ def test_config2_reduced_vs_reference_fixture(layout):
     vol, src, dirs = _config1_scene(g)
     S, alpha = int(g["S"]), float(g["alpha"])
     w = torch.tensor(g["w"], device=dev())
+    # the reference-made gradients are the target; the port run in both precisions gives the fp32 noise of the same arithmetic
+    from oracle import port
+    w64 = torch.tensor(g["w"]).double()
+    _, noise, _ = oracle_grads(lambda v_, s_, d_: (port.plot_beam_frame(v_, s_, d_, S, alpha, sampler="trilinear")[3] * w64.to(v_.dtype)).sum(),
+                               vol, src, dirs)
     want_v = np.zeros(256 ** 3)
     want_v[g["grad_volume_index"]] = g["grad_volume_value"]
     want_v = want_v.reshape(256, 256, 256)
@@ -83,9 +88,9 @@ def test_config2_reduced_vs_reference_fixture(layout):
     _, _, _, frame = UltrasoundRenderer(S, alpha).plot_beam_frame(vv, s, d, plot=False, sampler="trilinear", return_indices=False)
     assert_frame_close(frame.detach().cpu().numpy(), g["frame64"], "config 2 (128 samples) frame")
     (frame * w).sum().backward()
-    assert_grad_close(s.grad.cpu().numpy(), g["grad_source"], "d/dsource (unfused)")
-    assert_grad_close(d.grad.cpu().numpy(), g["grad_dirs"], "d/ddirections (unfused)")
-    assert_grad_close(v.grad.cpu().numpy(), want_v, "d/dvolume (unfused)")
+    assert_grad_close(s.grad.cpu().numpy(), g["grad_source"], "d/dsource (unfused)", noise=noise[1])
+    assert_grad_close(d.grad.cpu().numpy(), g["grad_dirs"], "d/ddirections (unfused)", noise=noise[2])
+    assert_grad_close(v.grad.cpu().numpy(), want_v, "d/dvolume (unfused)", noise=noise[0])
     # (2) the fused one-pass kernel: with target = frame - (n/2) w the MSE's upstream gradient (2/n)(frame - target)
     # is w, so its gradients are those of sum(frame * w)
     n = frame.numel()
@@ -93,21 +98,30 @@ def test_config2_reduced_vs_reference_fixture(layout):
     v, vv, s, d = inputs()
     loss = render_mse_loss(vv, s.reshape(1, 3), d, target, S, alpha, 0, sampler="trilinear")
     loss.backward()
-    assert_grad_close(s.grad.cpu().numpy(), g["grad_source"], "d/dsource (fused)")
-    assert_grad_close(d.grad.cpu().numpy(), g["grad_dirs"], "d/ddirections (fused)")
-    assert_grad_close(v.grad.cpu().numpy(), want_v, "d/dvolume (fused)")
+    assert_grad_close(s.grad.cpu().numpy(), g["grad_source"], "d/dsource (fused)", noise=noise[1])
+    assert_grad_close(d.grad.cpu().numpy(), g["grad_dirs"], "d/ddirections (fused)", noise=noise[2])
+    assert_grad_close(v.grad.cpu().numpy(), want_v, "d/dvolume (fused)", noise=noise[0])
 
 
-def _port_step(vol64, sources, dirs, target, S, alpha):
-    """fp64 closed-form port + autograd: frames, mean-squared loss against ``target`` and its pose gradients."""
+def _port_step(vol, sources, dirs, target, S, alpha):
+    """Closed-form port + autograd in float64 (and float32, for the noise of the reference's own arithmetic): frames,
+    mean-squared loss against ``target``, its pose gradients, and per-pose noise of the two gradients."""
     from oracle import port
-    s64 = sources.double().requires_grad_(True)
-    d64 = dirs.double().requires_grad_(True)
-    frames = torch.stack([port.plot_beam_frame(vol64, s64[p], d64[p], S, alpha, sampler="trilinear")[3]
-                          for p in range(sources.shape[0])])
-    loss = (frames - target.double()).square().mean()
-    gs, gd = torch.autograd.grad(loss, [s64, d64])
-    return frames.detach(), loss.item(), gs, gd
+    vols = {torch.float64: vol.double(), torch.float32: vol.float()}
+
+    def oracle(s_, d_):
+        frames = torch.stack([port.plot_beam_frame(vols[s_.dtype], s_[p], d_[p], S, alpha, sampler="trilinear")[3]
+                              for p in range(sources.shape[0])])
+        return (frames - target.to(s_.dtype)).square().mean(), frames.detach()
+    out = {}
+    for dt in (torch.float64, torch.float32):
+        s_, d_ = sources.to(dt).requires_grad_(True), dirs.to(dt).requires_grad_(True)
+        loss, frames = oracle(s_, d_)
+        out[dt] = (frames, loss.item()) + tuple(torch.autograd.grad(loss, [s_, d_]))
+    f64, l64, gs, gd = out[torch.float64]
+    noise_s = (out[torch.float32][2].double() - gs).abs().amax(dim=1)                 # per pose
+    noise_d = (out[torch.float32][3].double() - gd).abs().amax(dim=(1, 2))
+    return f64, l64, gs, gd, noise_s, noise_d
 
 
 def test_config2_full_size_step_vs_port():
@@ -119,14 +133,15 @@ def test_config2_full_size_step_vs_port():
     vol = layered_phantom(256, seed=0)
     src, dirs = config1_pose(256, 128)
     S, alpha = 512, 1e-4
-    v64 = vol.double().requires_grad_(True)
-    s64, d64 = src.double().requires_grad_(True), dirs.double().requires_grad_(True)
     with torch.no_grad():
         target = port.plot_beam_frame(vol.double(), src.double() + torch.tensor([1.5, 0.0, -1.0], dtype=torch.float64),
                                       dirs.double(), S, alpha, sampler="trilinear")[3]
-    f64 = port.plot_beam_frame(v64, s64, d64, S, alpha, sampler="trilinear")[3]
-    l64 = (f64 - target).square().mean()
-    gv, gs, gd = torch.autograd.grad(l64, [v64, s64, d64])
+
+    def oracle(v_, s_, d_):
+        f_ = port.plot_beam_frame(v_, s_, d_, S, alpha, sampler="trilinear")[3]
+        l_ = (f_ - target.to(f_.dtype)).square().mean()
+        return l_, (f_, l_)
+    (gv, gs, gd), noise, (f64, l64) = oracle_grads(oracle, vol, src, dirs)
     for layout in (None, "brick"):
         v = vol.to(dev()).requires_grad_(True)
         s, d = src.to(dev()).requires_grad_(True), dirs.to(dev()).requires_grad_(True)
@@ -134,11 +149,11 @@ def test_config2_full_size_step_vs_port():
         loss, frame = render_mse_loss(vv, s.reshape(1, 3), d, target.float().to(dev()).unsqueeze(0), S, alpha, 0,
                                       sampler="trilinear", return_frame=True)
         loss.backward()
-        assert_frame_close(frame[0].cpu().numpy(), f64.detach().numpy(), f"config 2 frame ({layout})")
+        assert_frame_close(frame[0].detach().cpu().numpy(), f64.detach().numpy(), f"config 2 frame ({layout})")
         np.testing.assert_allclose(loss.item(), l64.item(), rtol=1e-4)
-        assert_grad_close(s.grad.cpu().numpy(), gs.numpy(), f"config 2 d/dsource ({layout})")
-        assert_grad_close(d.grad.cpu().numpy(), gd.numpy(), f"config 2 d/ddirections ({layout})")
-        assert_grad_close(v.grad.cpu().numpy(), gv.numpy(), f"config 2 d/dvolume ({layout})")
+        assert_grad_close(s.grad.cpu().numpy(), gs.numpy(), f"config 2 d/dsource ({layout})", noise=noise[1])
+        assert_grad_close(d.grad.cpu().numpy(), gd.numpy(), f"config 2 d/ddirections ({layout})", noise=noise[2])
+        assert_grad_close(v.grad.cpu().numpy(), gv.numpy(), f"config 2 d/dvolume ({layout})", noise=noise[0])
         # the unfused pair of kernels on the same scene
         f2 = render_frames(vv, s.detach().reshape(1, 3), d.detach(), S, alpha, sampler="trilinear")
         assert_frame_close(f2[0].cpu().numpy(), f64.detach().numpy(), f"config 2 forward kernel ({layout})")
@@ -162,15 +177,14 @@ def test_config3_sweep_poses_vs_port():
     loss, frames = render_mse_loss(pv, s, d, target, S, alpha, 0, sampler="trilinear", return_frame=True)
     loss.backward()
     # the port sees the picked poses only; the mean over all 1024 poses rescales its gradients by len(pick) / 1024
-    f64, l64, gs, gd = _port_step(vol.double(), src[pick], dirs[pick], target[pick].cpu(), S, alpha)
+    f64, l64, gs, gd, ns, nd = _port_step(vol, src[pick], dirs[pick], target[pick].cpu(), S, alpha)
     k = len(pick) / 1024.0
     for i, p in enumerate(pick):
-        assert_frame_close(frames[p].cpu().numpy(), f64[i].numpy(), f"config 3 pose {p} frame")
-        assert_grad_close(s.grad[p].cpu().numpy(), k * gs[i].numpy(), f"config 3 pose {p} d/dsource")
-        assert_grad_close(d.grad[p].cpu().numpy(), k * gd[i].numpy(), f"config 3 pose {p} d/ddirections")
+        assert_frame_close(frames[p].detach().cpu().numpy(), f64[i].numpy(), f"config 3 pose {p} frame")
+        assert_grad_close(s.grad[p].cpu().numpy(), k * gs[i].numpy(), f"config 3 pose {p} d/dsource", noise=k * ns[i].item())
+        assert_grad_close(d.grad[p].cpu().numpy(), k * gd[i].numpy(), f"config 3 pose {p} d/ddirections", noise=k * nd[i].item())
     # the targets themselves (forward kernel) against the port
-    with torch.no_grad():
-        t64 = _port_step(vol.double(), (src + shift)[pick[:2]], dirs[pick[:2]], target[pick[:2]].cpu(), S, alpha)[0]
+    t64 = _port_step(vol, (src + shift)[pick[:2]], dirs[pick[:2]], torch.zeros_like(target[pick[:2]]).cpu(), S, alpha)[0]
     for i, p in enumerate(pick[:2]):
         assert_frame_close(target[p].cpu().numpy(), t64[i].numpy(), f"config 3 pose {p} target (forward kernel)")
 
@@ -191,14 +205,12 @@ def test_config5_stress_poses_vs_port():
     d = dirs.to(dev()).requires_grad_(True)
     loss, frames = render_mse_loss(pv, s, d, target, S, alpha, 0, sampler="trilinear", return_frame=True)
     loss.backward()
-    v64 = vol.double()
-    del vol
-    f64, l64, gs, gd = _port_step(v64, src, dirs, target.cpu(), S, alpha)
+    f64, l64, gs, gd, ns, nd = _port_step(vol, src, dirs, target.cpu(), S, alpha)
     np.testing.assert_allclose(loss.item(), l64, rtol=1e-4)
     for p in range(4):
-        assert_frame_close(frames[p].cpu().numpy(), f64[p].numpy(), f"config 5 pose {p} frame")
-        assert_grad_close(s.grad[p].cpu().numpy(), gs[p].numpy(), f"config 5 pose {p} d/dsource")
-        assert_grad_close(d.grad[p].cpu().numpy(), gd[p].numpy(), f"config 5 pose {p} d/ddirections")
+        assert_frame_close(frames[p].detach().cpu().numpy(), f64[p].numpy(), f"config 5 pose {p} frame")
+        assert_grad_close(s.grad[p].cpu().numpy(), gs[p].numpy(), f"config 5 pose {p} d/dsource", noise=ns[p].item())
+        assert_grad_close(d.grad[p].cpu().numpy(), gd[p].numpy(), f"config 5 pose {p} d/ddirections", noise=nd[p].item())
 
 
 def test_median_ties_vs_reference_fixture():
@@ -222,17 +234,18 @@ def test_median_ties_vs_reference_fixture():
         np.testing.assert_array_equal(x.cpu().numpy(), g[f"{name}_x"])
         assert_frame_close(frame.cpu().numpy(), g[f"{name}_frame64"], name)
         for sampler in ("nearest", "trilinear"):
-            v64 = vol.double().requires_grad_(True)
-            s64, d64 = src.double().requires_grad_(True), dirs.double().requires_grad_(True)
-            f64 = port.plot_beam_frame(v64, s64, d64, 40, 1e-3, start=start, sampler=sampler)[3]
-            w = torch.randn(f64.shape, generator=torch.Generator().manual_seed(start), dtype=torch.float64)
-            want = torch.autograd.grad((f64 * w).sum(), [v64, s64, d64], allow_unused=True)
+            w = torch.randn((15, 40 - start), generator=torch.Generator().manual_seed(start), dtype=torch.float64)
+
+            def oracle(v_, s_, d_):
+                f_ = port.plot_beam_frame(v_, s_, d_, 40, 1e-3, start=start, sampler=sampler)[3]
+                return (f_ * w.to(f_.dtype)).sum(), f_
+            want, noise, f64 = oracle_grads(oracle, vol, src, dirs)
             v = vol.to(dev()).requires_grad_(True)
             s, d = src.to(dev()).requires_grad_(True), dirs.to(dev()).requires_grad_(True)
             f = render_frames(v, s.reshape(1, 3), d, 40, 1e-3, start, sampler=sampler)[0]
             assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), f"{name} {sampler}")
             (f * w.float().to(dev())).sum().backward()
-            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), f"{name} {sampler} d/dvolume")
+            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), f"{name} {sampler} d/dvolume", noise=noise[0])
             if sampler == "trilinear":
-                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), f"{name} {sampler} d/dsource")
-                assert_grad_close(d.grad.cpu().numpy(), want[2].numpy(), f"{name} {sampler} d/ddirections")
+                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), f"{name} {sampler} d/dsource", noise=noise[1])
+                assert_grad_close(d.grad.cpu().numpy(), want[2].numpy(), f"{name} {sampler} d/ddirections", noise=noise[2])

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_frame_close, assert_grad_close
+from conftest import assert_frame_close, assert_grad_close, oracle_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -66,12 +66,13 @@ def test_simulate_rays_is_differentiable_like_the_reference(sampler):
     sources, dirs = pose_sweep(1, n_rays=5, n=20, seed=1)
     src, d = sources[0], dirs[0]
     S = 30
-    v64, s64, d64 = vol.double().requires_grad_(True), src.double().requires_grad_(True), d.double().requires_grad_(True)
-    pts = port.ray_points(s64, d64, S)
-    imp = (port.sample_nearest if sampler == "nearest" else port.sample_trilinear)(v64, pts)[3]
-    R64 = port.reflection_coeff(imp[:, :-1], imp[:, 1:])
-    w = torch.randn(R64.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
-    want = torch.autograd.grad((R64 * w).sum(), [v64, s64, d64], allow_unused=True)
+    w = torch.randn((5, S - 1), generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+
+    def oracle(v_, s_, d_):
+        imp = (port.sample_nearest if sampler == "nearest" else port.sample_trilinear)(v_, port.ray_points(s_, d_, S))[3]
+        R_ = port.reflection_coeff(imp[:, :-1], imp[:, 1:])
+        return (R_ * w.to(R_.dtype)).sum(), R_
+    want, noise, R64 = oracle_grads(oracle, vol, src, d)
     for prepared in (False, True):
         v = vol.to(dev()).requires_grad_(True)
         s = src.to(dev()).requires_grad_(True)
@@ -80,10 +81,10 @@ def test_simulate_rays_is_differentiable_like_the_reference(sampler):
         x, y, z, R = ren.simulate_rays(PreparedVolume(v) if prepared else v, s, dd, sampler=sampler)
         np.testing.assert_allclose(R.detach().cpu().numpy(), R64.detach().numpy(), rtol=1e-4, atol=1e-7)
         (R * w.float().to(dev())).sum().backward()
-        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d R / d volume")
+        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d R / d volume", noise=noise[0])
         if sampler == "trilinear":
-            assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d R / d source")
-            assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d R / d directions")
+            assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d R / d source", noise=noise[1])
+            assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d R / d directions", noise=noise[2])
         else:
             assert s.grad is None
 
@@ -117,9 +118,14 @@ def test_trilinear_forward_and_gradients_golden(golden_tri, name):
     np.testing.assert_array_equal(x.cpu().numpy(), g[f"{name}_x"])
     w = torch.tensor(g[f"{name}_w"], device=dev(), dtype=torch.float32)
     (frame * w).sum().backward()
-    assert_grad_close(src.grad.cpu().numpy(), g[f"{name}_grad_source"], name + " d/dsource")
-    assert_grad_close(dirs.grad.cpu().numpy(), g[f"{name}_grad_dirs"], name + " d/ddirections")
-    assert_grad_close(vol.grad.cpu().numpy(), g[f"{name}_grad_volume"], name + " d/dvolume")
+    # the reference-made gradients are the target; the port in both precisions supplies the fp32 noise of the same arithmetic
+    from oracle import port
+    w64, S, alpha = torch.tensor(g[f"{name}_w"]), int(g[f"{name}_S"]), float(g[f"{name}_alpha"])
+    _, noise, _ = oracle_grads(lambda v_, s_, d_: (port.plot_beam_frame(v_, s_, d_, S, alpha, sampler="trilinear")[3] * w64.to(v_.dtype)).sum(),
+                               torch.tensor(g[f"{name}_volume"]), torch.tensor(g[f"{name}_source"]), torch.tensor(g[f"{name}_dirs"]))
+    assert_grad_close(vol.grad.cpu().numpy(), g[f"{name}_grad_volume"], name + " d/dvolume", noise=noise[0])
+    assert_grad_close(src.grad.cpu().numpy(), g[f"{name}_grad_source"], name + " d/dsource", noise=noise[1])
+    assert_grad_close(dirs.grad.cpu().numpy(), g[f"{name}_grad_dirs"], name + " d/ddirections", noise=noise[2])
 
 
 def test_nearest_volume_gradient_golden(golden_tri):
@@ -168,16 +174,18 @@ def test_echo_forward_backward_vs_oracle(B, N):
     # coefficients of a layered medium: piecewise-constant tissue impedances + 0.5 % texture
     layers = 1.4e6 + 0.3e6 * torch.rand((B, N // 40 + 2), generator=g, dtype=torch.float64)
     Z = layers.repeat_interleave(40, dim=1)[:, :N + 1] * (1 + 0.005 * torch.randn((B, N + 1), generator=g, dtype=torch.float64))
-    r64 = port.reflection_coeff(Z[:, :-1], Z[:, 1:])
-    r64.requires_grad_(True)
-    e64 = port.echo_closed_form(r64)
-    w = torch.randn(e64.shape, generator=g, dtype=torch.float64)
-    (g64,) = torch.autograd.grad((e64 * w).sum(), r64)
+    r64 = port.reflection_coeff(Z[:, :-1], Z[:, 1:]).float().double()          # float32-representable coefficients
+    w = torch.randn((B, N + 1), generator=g, dtype=torch.float64)
+
+    def oracle(r_):
+        e_ = port.echo_closed_form(r_)
+        return (e_ * w.to(e_.dtype)).sum(), e_
+    (g64,), noise, e64 = oracle_grads(oracle, r64)
     r = r64.detach().float().to(dev()).requires_grad_(True)
     e, _ = compute_echo_traces(r)
     assert_frame_close(e.detach().cpu().numpy(), e64.detach().numpy(), f"echo {B}x{N}")
     (e * w.float().to(dev())).sum().backward()
-    assert_grad_close(r.grad.cpu().numpy(), g64.numpy(), f"d echo/d r {B}x{N}")
+    assert_grad_close(r.grad.cpu().numpy(), g64.numpy(), f"d echo/d r {B}x{N}", noise=noise[0])
 
 
 def _oracle_frames(vol, sources, dirs, S, alpha, start, sampler):
@@ -199,23 +207,23 @@ def test_batched_poses_vs_oracle(sampler, S, start):
     vol = layered_phantom(n, seed=3)
     sources, dirs = pose_sweep(3, n_rays=6, n=n, seed=S)
     alpha = 2e-3
-    v64 = vol.double().requires_grad_(True)
-    s64 = sources.double().requires_grad_(True)
-    d64 = dirs.double().requires_grad_(True)
-    f64 = _oracle_frames(v64, s64, d64, S, alpha, start, sampler)
     g = torch.Generator().manual_seed(1)
-    w = torch.randn(f64.shape, generator=g, dtype=torch.float64)
-    want = torch.autograd.grad((f64 * w).sum(), [v64, s64, d64], allow_unused=True)
+    w = torch.randn((3, 6, S - start), generator=g, dtype=torch.float64)
+
+    def oracle(v_, s_, d_):
+        f_ = _oracle_frames(v_, s_, d_, S, alpha, start, sampler)
+        return (f_ * w.to(f_.dtype)).sum(), f_
+    want, noise, f64 = oracle_grads(oracle, vol, sources, dirs)
     v = vol.to(dev()).requires_grad_(True)
     s = sources.to(dev()).requires_grad_(True)
     d = dirs.to(dev()).requires_grad_(True)
     f = render_frames(v, s, d, S, alpha, start, sampler=sampler)
     assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), f"{sampler} S={S} start={start}")
     (f * w.float().to(dev())).sum().backward()
-    assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume")
+    assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume", noise=noise[0])
     if sampler == "trilinear":
-        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources")
-        assert_grad_close(d.grad.cpu().numpy(), want[2].numpy(), "d/ddirections")
+        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources", noise=noise[1])
+        assert_grad_close(d.grad.cpu().numpy(), want[2].numpy(), "d/ddirections", noise=noise[2])
     else:
         assert s.grad is None and d.grad is None
 
@@ -233,12 +241,14 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
     alpha = 1e-3
     with torch.no_grad():
         target = render_frames(vol.to(dev()), sources.to(dev()) + 0.7, dirs.to(dev()), S, alpha, start, sampler=sampler)
-    v64 = vol.double().requires_grad_(True)
-    s64 = sources.double().requires_grad_(True)
-    d64 = dirs.double().requires_grad_(True)
-    f64 = _oracle_frames(v64, s64, d64, S, alpha, start, sampler)
-    l64 = (f64 - target.cpu().double()).square().mean()
-    want = torch.autograd.grad(l64, [v64, s64, d64], allow_unused=True)
+    tgt64 = target.cpu().double()
+
+    def oracle(v_, s_, d_):
+        f_ = _oracle_frames(v_, s_, d_, S, alpha, start, sampler)
+        l_ = (f_ - tgt64.to(f_.dtype)).square().mean()
+        return l_, l_
+    want, noise, l64 = oracle_grads(oracle, vol, sources, dirs)
+    noise = [3.0 * n for n in noise]
 
     def run(fused):
         v = vol.to(dev()).requires_grad_(True)
@@ -259,12 +269,12 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
     torch.testing.assert_close(ff, fu, rtol=1e-5, atol=2e-6)
     np.testing.assert_allclose(lf.item(), l64.item(), rtol=1e-4)
     np.testing.assert_allclose(lf.item(), lu.item(), rtol=1e-5)
-    assert_grad_close(gvf.cpu().numpy(), 3.0 * want[0].numpy(), "fused d/dvolume")
-    assert_grad_close(gvu.cpu().numpy(), 3.0 * want[0].numpy(), "unfused d/dvolume")
+    assert_grad_close(gvf.cpu().numpy(), 3.0 * want[0].numpy(), "fused d/dvolume", noise=noise[0])
+    assert_grad_close(gvu.cpu().numpy(), 3.0 * want[0].numpy(), "unfused d/dvolume", noise=noise[0])
     if sampler == "trilinear":
-        assert_grad_close(gsf.cpu().numpy(), 3.0 * want[1].numpy(), "fused d/dsources")
-        assert_grad_close(gdf.cpu().numpy(), 3.0 * want[2].numpy(), "fused d/ddirections")
-        assert_grad_close(gsu.cpu().numpy(), 3.0 * want[1].numpy(), "unfused d/dsources")
+        assert_grad_close(gsf.cpu().numpy(), 3.0 * want[1].numpy(), "fused d/dsources", noise=noise[1])
+        assert_grad_close(gdf.cpu().numpy(), 3.0 * want[2].numpy(), "fused d/ddirections", noise=noise[2])
+        assert_grad_close(gsu.cpu().numpy(), 3.0 * want[1].numpy(), "unfused d/dsources", noise=noise[1])
     else:
         assert gsf is None and gdf is None
 
@@ -281,12 +291,11 @@ def test_edge_shapes_vs_oracle(dims, R, S, start, sampler):
     d = torch.randn((2, R, 3), generator=g)
     d = d / d.norm(dim=-1, keepdim=True) * 0.7                 # sub-voxel steps: long rays stay near the volume
     alpha = 1e-3
-    v64 = vol.double().requires_grad_(True)
-    s64 = src.double().requires_grad_(True)
-    d64 = d.double().requires_grad_(True)
-    f64 = _oracle_frames(v64, s64, d64, S, alpha, start, sampler)
+    def oracle(v_, s_, d_):
+        f_ = _oracle_frames(v_, s_, d_, S, alpha, start, sampler)
+        return f_.square().mean(), f_
+    want, noise, f64 = oracle_grads(oracle, vol, src, d)
     tgt = torch.zeros_like(f64)
-    want = torch.autograd.grad((f64 - tgt).square().mean(), [v64, s64, d64], allow_unused=True)
     v = vol.to(dev()).requires_grad_(True)
     s = src.to(dev()).requires_grad_(True)
     dd = d.to(dev()).requires_grad_(True)
@@ -296,10 +305,10 @@ def test_edge_shapes_vs_oracle(dims, R, S, start, sampler):
     loss = render_mse_loss(v, s, dd, tgt.float().to(dev()), S, alpha, start, sampler=sampler)
     loss.backward()
     if want[0].abs().max() > 0:
-        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume")
+        assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume", noise=noise[0])
     if sampler == "trilinear" and want[1] is not None and want[1].abs().max() > 0:
-        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources")
-        assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d/ddirections")
+        assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources", noise=noise[1])
+        assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), "d/ddirections", noise=noise[2])
 
 
 @pytest.mark.parametrize("seed", range(24))
@@ -328,13 +337,17 @@ def test_randomised_configurations_vs_oracle(seed):
     d = torch.randn((R, 3) if shared else (P, R, 3), generator=g)
     d = d / d.norm(dim=-1, keepdim=True) * min(1.0, 1.5 * max(dims) / S)        # keep long rays near the volume
     pdt = torch.float64 if pose64 else torch.float32
-    v64 = vol.double().requires_grad_(True)
-    s64 = src.to(pdt).double().requires_grad_(True)
-    d64 = d.to(pdt).double().requires_grad_(True)
-    f64 = _oracle_frames(v64, s64, d64, S, alpha, start, sampler)
-    tgt = (f64.detach() * 0.5).float()
-    l64 = (f64 - tgt.double()).square().mean()
-    want = torch.autograd.grad(l64, [v64, s64, d64], allow_unused=True)
+    with torch.no_grad():
+        tgt = (_oracle_frames(vol.double(), src.to(pdt).double(), d.to(pdt).double(), S, alpha, start, sampler) * 0.5).float()
+
+    def oracle(v_, s_, d_):
+        # float64 poses are part of the case: only the volume (and a float32 pose) drops to float32 in the noise run
+        if pose64:
+            s_, d_ = s_.double(), d_.double()
+        f_ = _oracle_frames(v_, s_, d_, S, alpha, start, sampler)
+        l_ = (f_ - tgt.to(f_.dtype)).square().mean()
+        return l_, (f_, l_)
+    want, noise, (f64, l64) = oracle_grads(oracle, vol, src.to(pdt), d.to(pdt))
     what = f"seed {seed}: dims={dims} P={P} R={R} S={S} start={start} {sampler} prepared={prepared} shared={shared} pose64={pose64}"
     for fused in (True, False):
         v = vol.to(dev()).requires_grad_(True)
@@ -350,11 +363,11 @@ def test_randomised_configurations_vs_oracle(seed):
         assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), what)
         np.testing.assert_allclose(loss.item(), l64.item(), rtol=1e-4, atol=1e-12, err_msg=what)
         if want[0].abs().max() > 0:
-            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), what + " d/dvolume")
+            assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), what + " d/dvolume", noise=noise[0])
         if sampler == "trilinear":
             if want[1].abs().max() > 0:
-                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), what + " d/dsources")
-                assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), what + " d/ddirections")
+                assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), what + " d/dsources", noise=noise[1])
+                assert_grad_close(dd.grad.cpu().numpy(), want[2].numpy(), what + " d/ddirections", noise=noise[2])
         else:
             assert s.grad is None and dd.grad is None
 
@@ -375,14 +388,12 @@ def test_shared_directions_and_float64_pose():
     s = sources.to(dev()).requires_grad_(True)
     d = dirs.to(dev()).requires_grad_(True)
     f = render_frames(vol.to(dev()), s, d, 48, 1e-3, 0, sampler="trilinear")
-    s64 = sources.double().requires_grad_(True)
-    d64 = dirs.double().requires_grad_(True)
-    f64 = _oracle_frames(vol.double(), s64, d64, 48, 1e-3, 0, "trilinear")
-    w = torch.randn(f64.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
-    gs, gd = torch.autograd.grad((f64 * w).sum(), [s64, d64])
+    w = torch.randn(tuple(f.shape), generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    (gs, gd), noise, _ = oracle_grads(lambda s_, d_: (_oracle_frames(vol.to(s_.dtype), s_, d_, 48, 1e-3, 0, "trilinear") * w.to(s_.dtype)).sum(),
+                                      sources, dirs)
     (f * w.float().to(dev())).sum().backward()
-    assert_grad_close(s.grad.cpu().numpy(), gs.numpy(), "shared fan d/dsources")
-    assert_grad_close(d.grad.cpu().numpy(), gd.numpy(), "shared fan d/ddirections")
+    assert_grad_close(s.grad.cpu().numpy(), gs.numpy(), "shared fan d/dsources", noise=noise[0])
+    assert_grad_close(d.grad.cpu().numpy(), gd.numpy(), "shared fan d/ddirections", noise=noise[1])
 
 
 def test_cone_directions_device_matches_host(golden_cone):
@@ -444,23 +455,26 @@ def test_mlp_backward_tensor_core_path_matches_cuda_cores_and_oracle(n):
     from diffus_b200.impedance import pack_params
     from oracle import port
     torch.manual_seed(100 + n)
-    model = ImpedanceEstimator(1).double()
+    model = ImpedanceEstimator(1)
     x = torch.randn(n) * 2.0
     mask = torch.rand(n) > 0.2
     gup = torch.randn(n)
     if n > 1000:
         gup[200:700] = 0.0                                  # whole tiles without an upstream gradient are skipped
-    out = port.mlp_forward(x.double().reshape(-1, 1), *model.parameters()).reshape(-1) * 3.0
-    (torch.where(mask, out, torch.zeros_like(out)) * gup.double()).sum().backward()
-    want = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).numpy()
-    params = pack_params(model.float()).detach().to(dev())
+
+    def oracle(*prm):
+        out = port.mlp_forward(x.to(prm[0].dtype).reshape(-1, 1), *prm).reshape(-1) * 3.0
+        return (torch.where(mask, out, torch.zeros_like(out)) * gup.to(out.dtype)).sum()
+    g64, noise, _ = oracle_grads(oracle, *[p.detach() for p in model.parameters()])
+    want = torch.cat([g.reshape(-1) for g in g64]).numpy()
+    params = pack_params(model).detach().to(dev())
     got = {}
     for name, path in (("cc", ops.MLP_PATH_CUDA_CORES), ("tc", ops.MLP_PATH_TENSOR)):
         with ops.mlp_path(path):
             got[name] = ops.mlp_bwd_impl(params, x.to(dev()), mask.to(dev()), gup.to(dev()), 3.0).cpu().numpy()
             again = ops.mlp_bwd_impl(params, x.to(dev()), mask.to(dev()), gup.to(dev()), 3.0).cpu().numpy()
         np.testing.assert_array_equal(got[name], again)       # fixed-order reductions: run-to-run identical
-        assert_grad_close(got[name], want, f"mlp weight gradient ({name})")
+        assert_grad_close(got[name], want, f"mlp weight gradient ({name})", noise=max(noise))
 
 
 def test_mlp_volume_masked_and_large():
@@ -505,13 +519,14 @@ def test_mlp_render_training_step_vs_oracle():
     sources, dirs = pose_sweep(3, n_rays=5, n=n, seed=9)
     g = torch.Generator().manual_seed(3)
     targets = 0.01 * torch.randn((3, 5, S), generator=g)
-    ref = ImpedanceEstimator(1).double()
-    ref.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
-    Z64 = ref.model(mri.double().reshape(-1, 1)).reshape(mri.shape) * 1e6
-    s64 = sources.double().requires_grad_(True)
-    f64 = _oracle_frames(Z64, s64, dirs.double(), S, alpha, 0, "trilinear")
-    l64 = (f64 - targets.double()).square().mean()
-    l64.backward()
+    from oracle import port as _port
+
+    def oracle(s_, *prm):
+        Z_ = _port.mlp_forward(mri.to(s_.dtype).reshape(-1, 1), *prm).reshape(mri.shape) * 1e6
+        f_ = _oracle_frames(Z_, s_, dirs.to(s_.dtype), S, alpha, 0, "trilinear")
+        l_ = (f_ - targets.to(s_.dtype)).square().mean()
+        return l_, l_
+    g64, noise, l64 = oracle_grads(oracle, sources, *[p.detach() for p in model.parameters()])
     m = model.to(dev())
     s = sources.to(dev()).requires_grad_(True)
     from diffus_b200 import render_mse_loss
@@ -527,9 +542,9 @@ def test_mlp_render_training_step_vs_oracle():
             loss = mlp_render_mse_loss(m, vol_in, s, dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
         loss.backward()
         np.testing.assert_allclose(loss.item(), l64.item())
-        for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
-            assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"d/d{name} ({mode})")
-        assert_grad_close(s.grad.cpu().numpy(), s64.grad.numpy(), "d/dsources")
+        for i, (name, p) in enumerate(m.named_parameters()):
+            assert_grad_close(p.grad.cpu().numpy(), g64[1 + i].numpy(), f"d/d{name} ({mode})", noise=noise[1 + i])
+        assert_grad_close(s.grad.cpu().numpy(), g64[0].numpy(), "d/dsources", noise=noise[0])
     opt = torch.optim.Adam(m.parameters(), lr=1e-3)
     l0 = train_step(m, opt, mri.to(dev()), sources.to(dev()), dirs.to(dev()), targets.to(dev()), S, alpha, out_scale=1e6)
     for _ in range(10):
@@ -563,7 +578,7 @@ def test_splat_golden_and_gradient(golden_splat):
     got = differentiable_splat(cx.to(dev()), cy.to(dev()), cz.to(dev()), vd, H=40, W=72, sigma=2.0)
     np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=2e-5, atol=2e-6)
     (got * w.to(dev())).sum().backward()
-    assert_grad_close(vd.grad.cpu().numpy(), gw.numpy(), "d splat / d intensities", rtol=2e-5)
+    assert_grad_close(vd.grad.cpu().numpy(), gw.numpy(), "d splat / d intensities")
     # end to end with the renderer's own outputs, as every HEAD-era notebook does
     from diffus_b200 import UltrasoundRenderer
     from diffus_b200.phantoms import layered_phantom, config1_pose

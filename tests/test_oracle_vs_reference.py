@@ -74,7 +74,7 @@ def test_mlp_and_splat_live(ref):
 
 
 def test_rotate_around_apex_live(ref):
-    from diffus_b200 import rotate_around_apex
+    from oracle.port import rotate_around_apex          # the product's version is a CUDA kernel (tests/test_gpu_training.py)
     g = torch.Generator().manual_seed(2)
     x = torch.rand(7, 11, generator=g) * 200
     z = torch.rand(7, 11, generator=g) * 200
