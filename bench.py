@@ -236,8 +236,14 @@ def config4_record(dev, rank, world, barrier):
     out = {"what": "config 4 training step: MLP(256^3) -> frames -> MSE -> d/dweights -> NCCL all-reduce (4.6 KB flat buffer) -> fused Adam; "
                    "4096 frames per step in total, sharded; CUDA-event time of FusedTrainer.step, max over ranks",
            "frames_total": total, "frames_per_gpu": sl.stop - sl.start}
+    # target frames: the same scene through a SECOND seeded MLP -- a rescaled copy of the first one
+    # would leave every reflection coefficient, hence the loss, unchanged
+    torch.manual_seed(1)
+    model_tgt = ImpedanceEstimator(1)
     with torch.no_grad():
-        z_tgt = model.impedance_volume(mri, None, 1e6, 400.0) * 1.01
+        model_tgt.model[4].bias.fill_(1.5)
+        model_tgt.model[4].weight.mul_(0.3)
+        z_tgt = model_tgt.to(dev).impedance_volume(mri, None, 1e6, 400.0)
     for sampler in ("trilinear", "nearest"):
         with torch.no_grad():
             tgt = render_frames(PreparedVolume(z_tgt), s, d, N_SAMPLES, ALPHA, sampler=sampler)

@@ -22,7 +22,11 @@ RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"
        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum",
        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
-       "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+       "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+       "l1tex__t_requests_pipe_tex_mem_texture.sum", "l1tex__t_sectors_pipe_tex_mem_texture.sum",
+       "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+       "l1tex__data_pipe_tex_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.sum",
+       "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
        "sm__cycles_elapsed.max"]
 STALLS = ["long_scoreboard", "short_scoreboard", "wait", "selected", "not_selected", "no_instructions", "math_pipe_throttle",
@@ -44,6 +48,11 @@ def launches(path):
 
 
 def ncu_csv(rep, page, extra=()):
+    """Rows of one page of a report.  `rep` is a .ncu-rep file, or the prefix of pages already exported on the GPU box
+    (`ncu -i X.ncu-rep --page raw --csv > X.raw.csv`, same for `source`: the reports are too big to bring back)."""
+    import os
+    if not rep.endswith(".ncu-rep") and os.path.exists(f"{rep}.{page}.csv"):
+        return list(csv.reader(open(f"{rep}.{page}.csv")))
     out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv", *extra], capture_output=True, text=True).stdout
     return list(csv.reader(out.splitlines()))
 

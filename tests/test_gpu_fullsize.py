@@ -156,7 +156,7 @@ def test_config2_full_size_step_vs_port():
         assert_grad_close(v.grad.cpu().numpy(), gv.numpy(), f"config 2 d/dvolume ({layout})", noise=noise[0])
         # the unfused pair of kernels on the same scene
         f2 = render_frames(vv, s.detach().reshape(1, 3), d.detach(), S, alpha, sampler="trilinear")
-        assert_frame_close(f2[0].cpu().numpy(), f64.detach().numpy(), f"config 2 forward kernel ({layout})")
+        assert_frame_close(f2[0].detach().cpu().numpy(), f64.detach().numpy(), f"config 2 forward kernel ({layout})")
 
 
 def test_config3_sweep_poses_vs_port():

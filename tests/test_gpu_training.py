@@ -143,7 +143,17 @@ def test_fused_trainer_matches_autograd_and_torch_adam(sampler):
     np.testing.assert_allclose(l1.item(), l2.item(), rtol=1e-3)
     for (name, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):       # the module's tensors are views of the flat vector
         np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-3, atol=2e-5, err_msg=name)
-    assert l1.item() < l64.item()
+    # the same six Adam steps by torch in float64 on the oracle's renderer: the loss trajectory, not only the first gradient
+    opt64 = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    ref.zero_grad()
+    for _ in range(6):
+        Z = ref.model(mri.double().reshape(-1, 1)).reshape(mri.shape) * 1e6
+        f = torch.stack([port.plot_beam_frame(Z, sources[p].double(), dirs[p].double(), S, alpha, sampler=sampler)[3] for p in range(6)])
+        l = (f - targets.double()).square().mean()
+        opt64.zero_grad()
+        l.backward()
+        opt64.step()
+    np.testing.assert_allclose(l1.item(), l.item(), rtol=5e-2)     # Adam at lr 1e-2 amplifies float32 rounding of near-zero gradients
 
 
 def test_slice_mode_training_forward_and_trainer():
