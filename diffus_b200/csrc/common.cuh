@@ -47,7 +47,6 @@ using BwdGeo = Geo<8, 2>;
 // The forward saves its transfer-matrix carry at every PREFIX_STRIDE columns; the backward
 // gathers PREFIX_STRIDE columns at a time and walks them as BWD_SUB sub-segments of BwdGeo::SEG.
 constexpr int PREFIX_STRIDE = FwdGeo::SEG;
-constexpr int BWD_SUB = PREFIX_STRIDE / BwdGeo::SEG;
 
 // 2x2 transfer matrix [[a, b], [c, d]] held as its two COLUMNS, (a, c) and (b, d), each in one 64-bit
 // register pair: every product below is then a handful of packed FP32 operations (sm_100 `fma.rn.f32x2`
@@ -139,16 +138,18 @@ struct GradLayout {
 
 // texel fetches of the TEXTURE layout (x = p2, y = p1, layer = p0; unnormalised coordinates, texel centres at +0.5)
 __device__ __forceinline__ cudaTextureObject_t volume_texture(const void* data) { return (cudaTextureObject_t)(uintptr_t)data; }
-// the 2x2 footprint whose lower corner is texel (x0, y0) of `layer`, as (y0x0, y1x0, y0x1, y1x1): tld4 picks the four
-// texels bilinear filtering at (x0 + 1, y0 + 1) would blend -- (x0, y1), (x1, y1), (x1, y0), (x0, y0) in .x .y .z .w --
-// and the clamp addressing mode supplies min(x0 + 1, n - 1), the sampler's own border rule
-__device__ __forceinline__ float4 tex_gather_cell(cudaTextureObject_t tex, int layer, float x0, float y0) {
+// The 2x2 (p1, p2) footprint of `layer` that bilinear filtering at texture coordinate (x, y) would blend, unfiltered, in
+// tld4's own order: .x = (x0, y1), .y = (x1, y1), .z = (x1, y0), .w = (x0, y0) with x0 = floor(x - 0.5) -- i.e. with
+// j = p1 = y and k = p2 = x:  (j1k0, j1k1, j0k1, j0k0), the "cell face" order of tri_combine (no register shuffling between
+// the gather and the packed arithmetic).  Clamp addressing supplies the border rule: x = x0 + 1 gives (x0, min(x0 + 1, n - 1)),
+// x = 0 gives (0, 0).
+__device__ __forceinline__ float4 tex_gather_face(cudaTextureObject_t tex, int layer, float x, float y) {
     float4 r;
-    const float x = x0 + 1.0f, y = y0 + 1.0f;
     asm volatile("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(tex), "r"(layer), "f"(x), "f"(y));
-    return make_float4(r.w, r.x, r.z, r.y);
+                 : "l"(tex), "r"(layer), "f"(x), "f"(y)
+                 : "memory");      // keeps the gathers where the software pipeline puts them (before the previous batch's combine + stores)
+    return r;
 }
 __device__ __forceinline__ float tex_fetch_voxel(cudaTextureObject_t tex, int i, int j, int k) {
     return tex2DLayered<float>(tex, (float)k + 0.5f, (float)j + 0.5f, i);
@@ -248,31 +249,49 @@ __device__ __forceinline__ int nearest_index(float p, int n) {
 
 struct TriCell {       // clamp-then-floor cell of a trilinear sample, grid_sample border semantics
     int i0[3], i1[3];
-    float f[3];        // fraction in [0, 1); -0.0f marks a coordinate at or beyond a face (see tri_axis)
+    float f[3];        // fraction in [0, 1)
 };
 
-// The derivative w.r.t. a coordinate is non-zero only strictly inside the volume.  A coordinate at or beyond a
-// face clamps to the face and its fraction is exactly 0, so "outside" travels for free in the sign bit of f:
-// -0.0f interpolates exactly like +0.0f and costs no register or predicate per sample.
-__device__ __forceinline__ bool tri_inside(float f) { return (__float_as_uint(f) >> 31) == 0u; }
-
+// grid_sample(padding_mode='border', align_corners=True) along one axis: the coordinate clamps to [0, n - 1], the cell is
+// [floor, floor + 1] and the derivative w.r.t. the coordinate is ZERO at or beyond a face (p <= 0 or p >= n - 1).
+// A clamped coordinate has fraction exactly 0, so the value never needs to know; the derivative is the difference of the
+// cell's two faces across the axis, and it vanishes by itself when both faces are the SAME voxels:
+//   * at the top face floor = n - 1 and i1 = min(i0 + 1, n - 1) = i0 already;
+//   * at the bottom face (p <= 0) the cell is collapsed explicitly, i1 = i0 = 0 -- one compare and one select per axis, and
+//     only in kernels that form the spatial gradient (COLLAPSE).  No per-sample "inside" flags travel anywhere.
+// (A volume holding inf / NaN voxels would turn 0 into NaN there; such a volume has no meaningful frame either.)
+template <bool COLLAPSE = false>
 __device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float& f) {
     float hi = (float)(n - 1);
-    bool inside = (p > 0.f) && (p < hi);
     float pc = fminf(fmaxf(p, 0.f), hi);
     float fl = floorf(pc);
-    f = inside ? pc - fl : -0.f;
+    f = pc - fl;
     i0 = (int)fl;
     i1 = min(i0 + 1, n - 1);
+    if (COLLAPSE) i1 = (p > 0.f) ? i1 : i0;
 }
 
-// the same cell with the lower index left as a float (texture coordinates are floats: no conversion)
-__device__ __forceinline__ void tri_axis_f(float p, int n, float& fl, float& f) {
+// the same for an axis addressed through the texture unit: the tld4 coordinate whose footprint is (fl, fl + 1) is fl + 1,
+// clamp addressing does the top face, and coordinate 0 selects the collapsed cell (0, 0) at the bottom face
+template <bool COLLAPSE>
+__device__ __forceinline__ void tri_axis_tex(float p, int n, float& coord, float& f) {
     float hi = (float)(n - 1);
-    bool inside = (p > 0.f) && (p < hi);
     float pc = fminf(fmaxf(p, 0.f), hi);
-    fl = floorf(pc);
-    f = inside ? pc - fl : -0.f;
+    float fl = floorf(pc);
+    f = pc - fl;
+    coord = fl + 1.0f;
+    if (COLLAPSE) coord = (p > 0.f) ? coord : 0.f;
+}
+
+// QUAD elements carry their +j / +k neighbours inside the element, so the bottom-face cell cannot be collapsed by an index:
+// there "at or below the bottom face" travels in the sign bit of f (-0.0f interpolates exactly like +0.0f)
+__device__ __forceinline__ bool tri_inside(float f) { return (__float_as_uint(f) >> 31) == 0u; }
+__device__ __forceinline__ void tri_axis_flag(float p, int n, int& i0, float& f) {
+    float hi = (float)(n - 1);
+    float pc = fminf(fmaxf(p, 0.f), hi);
+    float fl = floorf(pc);
+    f = (p > 0.f) ? pc - fl : -0.f;
+    i0 = (int)fl;
 }
 
 // offsets of the eight corners in the layout of the GRADIENT volume (also the gathered one for LINEAR / BRICK)
@@ -286,36 +305,45 @@ __device__ __forceinline__ void tri_offsets(const VolumeView& v, const TriCell& 
     off[4] = a10 + z0; off[5] = a10 + z1; off[6] = a11 + z0; off[7] = a11 + z1;
 }
 
-// Value (and optionally the spatial gradient) of the border-clamped trilinear interpolant from the two faces
-// of the cell: q0 = face i0, q1 = face i1, each (j0k0, j1k0, j0k1, j1k1) -- exactly a QUAD element.
-// Interpolation is a + f (b - a) along i (4 wide), then k (2 wide), then j, in packed FP32; the derivative
-// along an axis is the difference of the two faces across it, interpolated along the other two.
-template <bool GRAD>
+// Value (and optionally the spatial gradient) of the border-clamped trilinear interpolant from the two faces of the
+// cell: q0 = face i0, q1 = face i1, each in tld4 order (j1k0, j1k1, j0k1, j0k0) -- the pairs (x, y) and (z, w) are what the
+// packed FP32 instructions take as they come out of the gather.  Interpolation is a + f (b - a) along i (4 wide), then j
+// (2 wide: the j0 pair enters with its halves swapped, a free operand modifier), then k; the derivative along an axis is the
+// difference of the two faces across it, interpolated along the other two.  FLAGS: bottom-face flags in the sign of f[1], f[2].
+template <bool GRAD, bool FLAGS = false>
 __device__ __forceinline__ float tri_combine(const float4& q0, const float4& q1, const float f[3], float g[3]) {
-    const float2 a0 = make_float2(q0.x, q0.y), a1 = make_float2(q0.z, q0.w);      // face i0: k0 pair, k1 pair
-    const float2 d0 = __fadd2_rn(make_float2(q1.x, q1.y), make_float2(-a0.x, -a0.y));
-    const float2 d1 = __fadd2_rn(make_float2(q1.z, q1.w), make_float2(-a1.x, -a1.y));
-    const float2 fx = bcast(f[0]), fz = bcast(f[2]);
-    const float2 l0 = __ffma2_rn(d0, fx, a0), l1 = __ffma2_rn(d1, fx, a1);        // along i: (j0, j1) at k0 and at k1
-    const float2 ek = __fadd2_rn(l1, make_float2(-l0.x, -l0.y));                  // d / d k at j0, j1
-    const float2 m = __ffma2_rn(ek, fz, l0);                                      // along k: value at j0, j1
-    const float dj = m.y - m.x;
+    const float2 a0 = make_float2(q0.x, q0.y), b0 = make_float2(q0.z, q0.w);      // face i0: j1 (k0, k1), j0 (k1, k0)
+    const float2 da = __fadd2_rn(make_float2(q1.x, q1.y), make_float2(-a0.x, -a0.y));     // d / d i at j1 (k0, k1)
+    const float2 db = __fadd2_rn(make_float2(q1.z, q1.w), make_float2(-b0.x, -b0.y));     // d / d i at j0 (k1, k0)
+    const float2 fx = bcast(f[0]), fy = bcast(f[1]);
+    const float2 la = __ffma2_rn(da, fx, a0), lb = __ffma2_rn(db, fx, b0);        // along i
+    const float2 lbs = make_float2(lb.y, lb.x);                                   // j0 (k0, k1)
+    const float2 ej = __fadd2_rn(la, make_float2(-lbs.x, -lbs.y));                // d / d j at k0, k1
+    const float2 m = __ffma2_rn(ej, fy, lbs);                                     // along j: value at k0, k1
+    const float dk = m.y - m.x;
     if (GRAD) {
-        const float2 di = __ffma2_rn(__fadd2_rn(d1, make_float2(-d0.x, -d0.y)), fz, d0);   // d / d i at j0, j1
-        g[0] = tri_inside(f[0]) ? __fmaf_rn(di.y - di.x, f[1], di.x) : 0.f;
-        g[1] = tri_inside(f[1]) ? dj : 0.f;
-        g[2] = tri_inside(f[2]) ? __fmaf_rn(ek.y - ek.x, f[1], ek.x) : 0.f;
+        const float2 dbs = make_float2(db.y, db.x);
+        const float2 di = __ffma2_rn(__fadd2_rn(da, make_float2(-dbs.x, -dbs.y)), fy, dbs);   // d / d i at k0, k1
+        g[0] = __fmaf_rn(di.y - di.x, f[2], di.x);
+        g[1] = __fmaf_rn(ej.y - ej.x, f[2], ej.x);
+        g[2] = dk;
+        if (FLAGS) {
+            g[1] = tri_inside(f[1]) ? g[1] : 0.f;
+            g[2] = tri_inside(f[2]) ? g[2] : 0.f;
+        }
     }
-    return __fmaf_rn(dj, f[1], m.x);
+    return __fmaf_rn(dk, f[2], m.x);
 }
 
 // A sample split into "issue the loads" and "combine", so a gather loop can keep the next
 // tile's loads in flight while it combines the current one (software pipelining).
 template <int SAMPLER, int LAYOUT>
 struct Fetch {
-    float4 q0, q1;     // nearest: q0.x only
+    float4 q0, q1;     // nearest: q0.x only; trilinear: the cell's faces i0 and i1 in tld4 order (see tri_combine)
     float f[3];
 
+    // GRAD: the caller will ask finish<true> for the spatial gradient (the cell is collapsed at the bottom faces)
+    template <bool GRAD = false>
     __device__ __forceinline__ void issue(const VolumeView& v, float p0, float p1, float p2) {
         if (SAMPLER == DIFFUS_SAMPLER_NEAREST) {
             int i = nearest_index(p0, v.D), j = nearest_index(p1, v.H), k = nearest_index(p2, v.W);
@@ -327,31 +355,35 @@ struct Fetch {
             }
         } else if (LAYOUT == DIFFUS_LAYOUT_TEXTURE) {
             int i0, i1;
-            float y0, x0;
-            tri_axis(p0, v.D, i0, i1, f[0]);
-            tri_axis_f(p1, v.H, y0, f[1]);
-            tri_axis_f(p2, v.W, x0, f[2]);
+            float y, x;
+            tri_axis<GRAD>(p0, v.D, i0, i1, f[0]);
+            tri_axis_tex<GRAD>(p1, v.H, y, f[1]);
+            tri_axis_tex<GRAD>(p2, v.W, x, f[2]);
             const cudaTextureObject_t tex = volume_texture(v.data);
-            q0 = tex_gather_cell(tex, i0, x0, y0);
-            q1 = tex_gather_cell(tex, i1, x0, y0);
+            q0 = tex_gather_face(tex, i0, x, y);
+            q1 = tex_gather_face(tex, i1, x, y);
+        } else if (LAYOUT == DIFFUS_LAYOUT_QUAD) {
+            int i0, i1, j0, k0;
+            tri_axis<GRAD>(p0, v.D, i0, i1, f[0]);
+            tri_axis_flag(p1, v.H, j0, f[1]);
+            tri_axis_flag(p2, v.W, k0, f[2]);
+            const uint32_t base = axis_y<LAYOUT>(v.sy, j0) + axis_z<LAYOUT>(k0);
+            const float4* q = (const float4*)v.data;
+            const float4 e0 = __ldg(q + (base + axis_x<LAYOUT>(v.sx, i0)));      // (j0k0, j1k0, j0k1, j1k1)
+            const float4 e1 = __ldg(q + (base + axis_x<LAYOUT>(v.sx, i1)));
+            q0 = make_float4(e0.y, e0.w, e0.z, e0.x);
+            q1 = make_float4(e1.y, e1.w, e1.z, e1.x);
         } else {
             TriCell c;
-            tri_axis(p0, v.D, c.i0[0], c.i1[0], f[0]);
-            tri_axis(p1, v.H, c.i0[1], c.i1[1], f[1]);
-            tri_axis(p2, v.W, c.i0[2], c.i1[2], f[2]);
-            if (LAYOUT == DIFFUS_LAYOUT_QUAD) {
-                const uint32_t base = axis_y<LAYOUT>(v.sy, c.i0[1]) + axis_z<LAYOUT>(c.i0[2]);
-                const float4* q = (const float4*)v.data;
-                q0 = __ldg(q + (base + axis_x<LAYOUT>(v.sx, c.i0[0])));
-                q1 = __ldg(q + (base + axis_x<LAYOUT>(v.sx, c.i1[0])));
-            } else {
-                uint32_t x0 = axis_x<LAYOUT>(v.sx, c.i0[0]), x1 = axis_x<LAYOUT>(v.sx, c.i1[0]);
-                uint32_t y0 = axis_y<LAYOUT>(v.sy, c.i0[1]), y1 = axis_y<LAYOUT>(v.sy, c.i1[1]);
-                uint32_t z0 = axis_z<LAYOUT>(c.i0[2]), z1 = axis_z<LAYOUT>(c.i1[2]);
-                uint32_t a00 = x0 + y0, a01 = x0 + y1, a10 = x1 + y0, a11 = x1 + y1;
-                q0 = make_float4(__ldg(v.data + (a00 + z0)), __ldg(v.data + (a01 + z0)), __ldg(v.data + (a00 + z1)), __ldg(v.data + (a01 + z1)));
-                q1 = make_float4(__ldg(v.data + (a10 + z0)), __ldg(v.data + (a11 + z0)), __ldg(v.data + (a10 + z1)), __ldg(v.data + (a11 + z1)));
-            }
+            tri_axis<GRAD>(p0, v.D, c.i0[0], c.i1[0], f[0]);
+            tri_axis<GRAD>(p1, v.H, c.i0[1], c.i1[1], f[1]);
+            tri_axis<GRAD>(p2, v.W, c.i0[2], c.i1[2], f[2]);
+            uint32_t x0 = axis_x<LAYOUT>(v.sx, c.i0[0]), x1 = axis_x<LAYOUT>(v.sx, c.i1[0]);
+            uint32_t y0 = axis_y<LAYOUT>(v.sy, c.i0[1]), y1 = axis_y<LAYOUT>(v.sy, c.i1[1]);
+            uint32_t z0 = axis_z<LAYOUT>(c.i0[2]), z1 = axis_z<LAYOUT>(c.i1[2]);
+            uint32_t a00 = x0 + y0, a01 = x0 + y1, a10 = x1 + y0, a11 = x1 + y1;
+            q0 = make_float4(__ldg(v.data + (a01 + z0)), __ldg(v.data + (a01 + z1)), __ldg(v.data + (a00 + z1)), __ldg(v.data + (a00 + z0)));
+            q1 = make_float4(__ldg(v.data + (a11 + z0)), __ldg(v.data + (a11 + z1)), __ldg(v.data + (a10 + z1)), __ldg(v.data + (a10 + z0)));
         }
     }
     template <bool GRAD>
@@ -360,7 +392,7 @@ struct Fetch {
             if (GRAD) { g[0] = g[1] = g[2] = 0.f; }
             return q0.x;
         } else {
-            return tri_combine<GRAD>(q0, q1, f, g);
+            return tri_combine<GRAD, LAYOUT == DIFFUS_LAYOUT_QUAD>(q0, q1, f, g);
         }
     }
 };
@@ -368,7 +400,7 @@ struct Fetch {
 template <int SAMPLER, int LAYOUT, bool GRAD>
 __device__ __forceinline__ float sample_volume(const VolumeView& v, float p0, float p1, float p2, float g[3]) {
     Fetch<SAMPLER, LAYOUT> fe;
-    fe.issue(v, p0, p1, p2);
+    fe.template issue<GRAD>(v, p0, p1, p2);
     return fe.template finish<GRAD>(g);
 }
 

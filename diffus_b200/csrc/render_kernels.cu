@@ -9,6 +9,8 @@
 //            pose-recovery step (fused forward + loss + backward, one gather pass).
 #include <cuda_pipeline.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -54,8 +56,20 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
 //               diff = frame - target, ebar = grad_scale * diff * att, accumulates diff^2
 //               and (optionally) stores the frame
 constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
+#ifndef DIFFUS_H_ROLLED
+#define DIFFUS_H_ROLLED 0    // 1: the sub-segment loop of the reverse sweep is not unrolled (half the sweep code, one more branch)
+#endif
+#ifndef DIFFUS_GATHER_PIPE
+#define DIFFUS_GATHER_PIPE 1   // fused backward, TEXTURE layout: two batches of gathers in flight (software pipeline)
+#endif
+#ifndef DIFFUS_WIDE_SWEEP
+#define DIFFUS_WIDE_SWEEP 0    // one-pass pose-gradient kernels: single 512-column reverse sweep (see WideGeo)
+#endif
+#ifndef DIFFUS_WIDE_CTAS
+#define DIFFUS_WIDE_CTAS 4
+#endif
 #ifndef DIFFUS_TEX_GB
-#define DIFFUS_TEX_GB 2      // tiles of tld4 gathers in flight per warp in the fused backward (TEXTURE layout)
+#define DIFFUS_TEX_GB 1      // tiles of tld4 gathers in flight per warp in the fused backward (TEXTURE layout)
 #endif
 constexpr int BWD_DZ_STRIDE = FwdGeo::OBUF;   // floats between the per-axis rows of the spatial-gradient buffer
 
@@ -534,9 +548,15 @@ __device__ __forceinline__ void scatter_pass_quads(const RenderParams& p, const 
 // ONE_PASS: the ray fits one 512-column pass (every BASELINE config but the 2048-sample stress case).  The pass
 // loop disappears, so the accumulators and the adjoint carried between passes are not live during the gather; the
 // pose-only kernels then fit 96 registers and run 5 CTAs (20 warps) per SM: 0.817 -> 0.753 ms per 1024 poses.
-template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS>
-__global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_bwd_kernel(const RenderParams p) {
-    using G = BwdGeo;
+// WIDE (one-pass rays longer than 256 columns): the reverse sweep walks the pass as ONE 512-column segment, 16 columns per
+// lane with a prefix checkpoint every 4 (Geo<16, 4>), instead of two 256-column sub-segments of 8 columns per lane: one
+// prefix scan and one suffix scan per ray instead of two of each, no prefix pre-pass over the first sub-segment, for 1.5
+// instead of 0.5 recomputed transfer products per column.
+using WideGeo = Geo<16, 4>;
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false>
+__global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD && !(WIDE && DIFFUS_WIDE_CTAS == 4)) ? 5 : 4) render_bwd_kernel(const RenderParams p) {
+    using G = typename std::conditional<WIDE, WideGeo, BwdGeo>::type;
+    constexpr int BWD_SUB = PREFIX_STRIDE / G::SEG;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
     extern __shared__ float smem[];
     float* att = smem;                       // padded like the column buffers: conflict free in the chunk phase
@@ -597,13 +617,14 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
             constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : (LAYOUT == DIFFUS_LAYOUT_TEXTURE ? DIFFUS_TEX_GB : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2));
             // batches whose tiles are all complete run without the per-lane bounds tests; the tail keeps them
             const int nt_full = (ncol >> 5) / GB * GB;
-            for (int t0 = 0; t0 < nt_full; t0 += GB) {
-                Fetch<SAMPLER, LAYOUT> fe[GB];
+            auto issue_batch = [&](Fetch<SAMPLER, LAYOUT>(&fe)[GB], int t0) {
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
                     int k = p.start + c0 + (t0 + u) * 32 + lane;
-                    fe[u].issue(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
+                    fe[u].template issue<POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
                 }
+            };
+            auto finish_batch = [&](const Fetch<SAMPLER, LAYOUT>(&fe)[GB], int t0) {
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
                     int idx = (t0 + u) * 32 + lane;
@@ -615,6 +636,30 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
                         dz[di] = g[0]; dz[BWD_DZ + di] = g[1]; dz[2 * BWD_DZ + di] = g[2];
                     }
                 }
+            };
+            // The gather phase is latency-bound (profiles/r2_fused_kernel_texture.md: the first use of a tld4 result holds
+            // 17 % of all warp time): with texture gathers, which return in order, the next batch is issued BEFORE the
+            // current one is combined, so the combine + shared-memory stores overlap the flight of the next gathers.
+            constexpr bool PIPELINED = DIFFUS_GATHER_PIPE && SAMPLER == DIFFUS_SAMPLER_TRILINEAR && LAYOUT == DIFFUS_LAYOUT_TEXTURE;
+            if (PIPELINED && nt_full > 0 && nt_full % (2 * GB) == 0) {        // (warp-uniform) branch-free steady state
+                Fetch<SAMPLER, LAYOUT> fa[GB], fb[GB];
+                issue_batch(fa, 0);
+                int t0 = 0;
+                for (; t0 + 2 * GB < nt_full; t0 += 2 * GB) {
+                    issue_batch(fb, t0 + GB);
+                    finish_batch(fa, t0);
+                    issue_batch(fa, t0 + 2 * GB);
+                    finish_batch(fb, t0 + GB);
+                }
+                issue_batch(fb, t0 + GB);
+                finish_batch(fa, t0);
+                finish_batch(fb, t0 + GB);
+            } else {
+                for (int t0 = 0; t0 < nt_full; t0 += GB) {
+                    Fetch<SAMPLER, LAYOUT> fe[GB];
+                    issue_batch(fe, t0);
+                    finish_batch(fe, t0);
+                }
             }
             for (int t0 = nt_full; t0 < nt; t0 += GB) {
                 Fetch<SAMPLER, LAYOUT> fe[GB];
@@ -623,7 +668,7 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
                     int idx = (t0 + u) * 32 + lane;
                     if (idx < ncol) {
                         int k = p.start + c0 + idx;
-                        fe[u].issue(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
+                        fe[u].template issue<POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
                     }
                 }
 #pragma unroll
@@ -678,7 +723,11 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
         }
         // reverse scan, last sub-segment first; it ends in d loss / d Z per column and the pose accumulators
         zt.w_after = (c0 + ncol < p.Sout) ? carry_w : 0.f;
+#if DIFFUS_H_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int h = BWD_SUB - 1; h >= 0; --h) {
             if (h < nsub) {
                 const int off = h * G::SEG;
@@ -693,14 +742,16 @@ __global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD) ? 5 : 4) render_b
                 zt.kbase = (float)(p.start + c0 + lane_col);
                 zt.rbar1 = (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr;
                 const M2* kt = (h == 0 && have0) ? &T0 : nullptr;
+                M2 ch = carry[0];                        // (a select, not an indexed read: the loop may be rolled)
+                if (BWD_SUB == 2 && h == 1) ch = carry[BWD_SUB - 1];
                 float* fl = fout ? fout + c0 + lane_col : nullptr;
                 if (full)
                     vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true>(
-                        r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
+                        r, ch, vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
                         loss_acc, lane, &zt, kt, &E0);
                 else
                     vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false>(
-                        r, carry[h], vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
+                        r, ch, vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
                         loss_acc, lane, &zt, kt, &E0);
                 zt.w_after = zt.w_first;
             }
@@ -918,6 +969,13 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
 #define DIFFUS_BWD_GO(PG, VG)                                                   \
     {                                                                           \
         /* the one-pass specialisation exists for float32 poses only (build time) */ \
+        if (DIFFUS_WIDE_SWEEP && !P64_ && TRI && PG && !VG && p.Sout <= PREFIX_STRIDE && p.Sout > BwdGeo::SEG) { \
+            auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true, (DIFFUS_WIDE_SWEEP && TRI && PG && !VG)>; \
+            cudaError_t e = ensure_smem(k, smem);                               \
+            if (e != cudaSuccess) return e;                                     \
+            k<<<grid, threads, smem, st>>>(p);                                  \
+            return cudaGetLastError();                                          \
+        }                                                                       \
         if (!P64_ && p.Sout <= PREFIX_STRIDE) {                                 \
             auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true>;      \
             cudaError_t e = ensure_smem(k, smem);                               \

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_frame_close, assert_grad_close, oracle_grads
+from conftest import GRAD_RTOL, NOISE_FACTOR, assert_frame_close, assert_grad_close, oracle_grads
 
 pytestmark = pytest.mark.gpu
 
@@ -220,7 +220,11 @@ def test_batched_poses_vs_oracle(sampler, S, start):
     f = render_frames(v, s, d, S, alpha, start, sampler=sampler)
     assert_frame_close(f.detach().cpu().numpy(), f64.detach().numpy(), f"{sampler} S={S} start={start}")
     (f * w.float().to(dev())).sum().backward()
-    assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume", noise=noise[0])
+    # (S, start) = (130, 128): every ray has left the volume, the only column with a gradient is the median-replaced one and
+    # its two contributions +-w / (2 Z) land on the SAME clamped voxel: the reference gradient is exactly zero by cancellation,
+    # so the check is against the size of one cancelling term instead of against max |reference| = 0
+    term = float(w.abs().max() / (2.0 * vol.min())) if float(want[0].abs().max()) == 0.0 else 0.0
+    assert_grad_close(v.grad.cpu().numpy(), want[0].numpy(), "d/dvolume", noise=max(noise[0], GRAD_RTOL * term / NOISE_FACTOR))
     if sampler == "trilinear":
         assert_grad_close(s.grad.cpu().numpy(), want[1].numpy(), "d/dsources", noise=noise[1])
         assert_grad_close(d.grad.cpu().numpy(), want[2].numpy(), "d/ddirections", noise=noise[2])

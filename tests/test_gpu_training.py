@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_frame_close, assert_grad_close, load_golden
+from conftest import oracle_grads, assert_frame_close, assert_grad_close, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -49,19 +49,22 @@ def test_ssim_loss_matches_port(normalize):
     loss = ssim_loss(s, y, normalize=normalize)
     np.testing.assert_allclose(loss.item(), float(g[tag + "_loss"]), rtol=2e-5)
     (2.0 * loss).backward()
-    assert_grad_close(s.grad.cpu().numpy(), 2.0 * g[tag + "_grad"], f"d (1 - ssim) / d synth ({tag})")
+    # SSIM's local variances are differences of window means (E[x^2] - mu^2): the reference's own float32 evaluation is that
+    # far from its float64 one, so the element-wise 1e-4 is widened by the measured float32 drift of the port (oracle_grads)
+    y_cpu = torch.tensor(g["ssim_real"])
+    _, noise, _ = oracle_grads(lambda s_: 2.0 * port.ssim_loss(s_, y_cpu.to(s_.dtype), normalize=normalize), torch.tensor(g["ssim_synth"]))
+    assert_grad_close(s.grad.cpu().numpy(), 2.0 * g[tag + "_grad"], f"d (1 - ssim) / d synth ({tag})", noise=noise[0])
     # a 256 x 256 image (the notebooks' size) against the port run on the host, other window parameters too
     gen = torch.Generator().manual_seed(5)
     real = torch.rand((256, 256), generator=gen)
     synth = (real * 0.7 + 0.2 * torch.rand((256, 256), generator=gen)).requires_grad_(True)
-    s64 = synth.detach().double().requires_grad_(True)
-    want = port.ssim_loss(s64, real.double(), normalize=normalize, kernel_size=7, kernel_sigma=1.0)
-    (gw,) = torch.autograd.grad(want, s64)
+    fn = lambda s_: (lambda l_: (l_, l_))(port.ssim_loss(s_, real.to(s_.dtype), normalize=normalize, kernel_size=7, kernel_sigma=1.0))
+    (gw,), noise, want = oracle_grads(fn, synth)
     sd = synth.detach().to(dev()).requires_grad_(True)
     got = ssim_loss(sd, real.to(dev()), normalize=normalize, kernel_size=7, kernel_sigma=1.0)
     np.testing.assert_allclose(got.item(), want.item(), rtol=2e-5)
     got.backward()
-    assert_grad_close(sd.grad.cpu().numpy(), gw.numpy(), "d (1 - ssim) / d synth, 256 x 256")
+    assert_grad_close(sd.grad.cpu().numpy(), gw.numpy(), "d (1 - ssim) / d synth, 256 x 256", noise=noise[0])
 
 
 def test_log_compression():
@@ -167,20 +170,29 @@ def test_slice_mode_training_forward_and_trainer():
     k, S, alpha = 11, 40, 1e-3
     src = torch.tensor([12.0, 0.0, float(k)])
     dirs = generate_cone_directions([0.1, 1.0], 0.9, 7)          # the fan lies in the slice p2 = k
-    ref = copy.deepcopy(model).double()
-    zs = ref.model(mri[:, :, k].double().reshape(-1, 1)).reshape(mri.shape[0], mri.shape[1])
-    Z64 = mri.double().clone()
-    Z64[:, :, k] = zs
-    f64 = port.plot_beam_frame(Z64, src.double(), dirs.double(), S, alpha)[3]
-    w = torch.randn(f64.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
-    (f64 * w).sum().backward()
+    w = None
+
+    def slice_oracle(dt):
+        nonlocal w
+        r_ = copy.deepcopy(model).to(dt)
+        zs = r_.model(mri[:, :, k].to(dt).reshape(-1, 1)).reshape(mri.shape[0], mri.shape[1])
+        Z = mri.to(dt).clone()
+        Z[:, :, k] = zs
+        f_ = port.plot_beam_frame(Z, src.to(dt), dirs.to(dt), S, alpha)[3]
+        if w is None:
+            w = torch.randn(f_.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+        (f_ * w.to(dt)).sum().backward()
+        return r_, f_
+    ref, f64 = slice_oracle(torch.float64)
+    ref32, _ = slice_oracle(torch.float32)          # the same arithmetic in float32: the drift the 1e-4 may be widened by
     m = copy.deepcopy(model).to(dev())
     x, y, z, frame = training_forward(m, UltrasoundRenderer(S, alpha), mri.to(dev()), src.to(dev()), dirs.to(dev()), slice_idx=k)
     assert_frame_close(frame.detach().cpu().numpy(), f64.detach().numpy(), "slice-mode frame")
     assert (z == k).all()
     (frame * w.float().to(dev())).sum().backward()
-    for (name, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
-        assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"slice mode d/d{name}")
+    for (name, p), (_, q), (_, q32) in zip(m.named_parameters(), ref.named_parameters(), ref32.named_parameters()):
+        assert_grad_close(p.grad.cpu().numpy(), q.grad.numpy(), f"slice mode d/d{name}",
+                          noise=float((q32.grad.double() - q.grad).abs().max()))
     # the fused trainer in slice mode: first gradient vs the oracle's MSE gradient
     target = 0.5 * f64.detach().float()
     ref2 = copy.deepcopy(model).double()
