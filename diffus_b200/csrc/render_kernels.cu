@@ -63,10 +63,13 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #define DIFFUS_GATHER_PIPE 1   // fused backward, TEXTURE layout: two batches of gathers in flight (software pipeline)
 #endif
 #ifndef DIFFUS_WIDE_SWEEP
-#define DIFFUS_WIDE_SWEEP 0    // one-pass pose-gradient kernels: single 512-column reverse sweep (see WideGeo)
+#define DIFFUS_WIDE_SWEEP 1    // one-pass pose-gradient kernels: single 512-column reverse sweep (see WideGeo)
 #endif
 #ifndef DIFFUS_WIDE_CTAS
-#define DIFFUS_WIDE_CTAS 4
+#define DIFFUS_WIDE_CTAS 4      // resident 4-warp CTA equivalents per SM of the WIDE kernels (4: 128 registers, 5: 96 and spills)
+#endif
+#ifndef DIFFUS_WIDE_WPB
+#define DIFFUS_WIDE_WPB 4       // rays (warps) per CTA of the WIDE kernels on large batches
 #endif
 #ifndef DIFFUS_TEX_GB
 #define DIFFUS_TEX_GB 1      // tiles of tld4 gathers in flight per warp in the fused backward (TEXTURE layout)
@@ -554,7 +557,8 @@ __device__ __forceinline__ void scatter_pass_quads(const RenderParams& p, const 
 // instead of 0.5 recomputed transfer products per column.
 using WideGeo = Geo<16, 4>;
 template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false>
-__global__ void __launch_bounds__(128, (ONE_PASS && !VOL_GRAD && !(WIDE && DIFFUS_WIDE_CTAS == 4)) ? 5 : 4) render_bwd_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(WIDE ? 32 * DIFFUS_WIDE_WPB : 128, WIDE ? DIFFUS_WIDE_CTAS * 4 / DIFFUS_WIDE_WPB : ((ONE_PASS && !VOL_GRAD) ? 5 : 4))
+render_bwd_kernel(const RenderParams p) {
     using G = typename std::conditional<WIDE, WideGeo, BwdGeo>::type;
     constexpr int BWD_SUB = PREFIX_STRIDE / G::SEG;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
@@ -971,9 +975,12 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
         /* the one-pass specialisation exists for float32 poses only (build time) */ \
         if (DIFFUS_WIDE_SWEEP && !P64_ && TRI && PG && !VG && p.Sout <= PREFIX_STRIDE && p.Sout > BwdGeo::SEG) { \
             auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true, (DIFFUS_WIDE_SWEEP && TRI && PG && !VG)>; \
-            cudaError_t e = ensure_smem(k, smem);                               \
+            int wpb_ = threads / 32;                                            \
+            if (wpb_ == 4) wpb_ = DIFFUS_WIDE_WPB;                              \
+            const size_t smem_ = ((size_t)p.att_slots_padded + (size_t)wpb_ * BWD_SMEM_PER_WARP) * sizeof(float); \
+            cudaError_t e = ensure_smem(k, smem_);                              \
             if (e != cudaSuccess) return e;                                     \
-            k<<<grid, threads, smem, st>>>(p);                                  \
+            k<<<(unsigned)((p.total_rays + wpb_ - 1) / wpb_), wpb_ * 32, smem_, st>>>(p); \
             return cudaGetLastError();                                          \
         }                                                                       \
         if (!P64_ && p.Sout <= PREFIX_STRIDE) {                                 \
