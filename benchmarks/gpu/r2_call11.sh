@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, GPU call 11: where the piecewise-linear MLP kernels spend their time (size sweep + ncu)
+set -u
+O=gpurun_out/r2k
+mkdir -p $O
+for n in 65536 1048576 16777216 134217728; do python benchmarks/experiments/mlp_paths.py --n $n >> $O/sweep.jsonl 2>> $O/sweep.err; done
+cat $O/sweep.jsonl
+python benchmarks/experiments/mlp_paths.py --iters 1 > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:mlp_pwl -c 8 -o $O/prof_pwl python benchmarks/experiments/mlp_paths.py --iters 1 > $O/ncu.log 2>&1
+ncu -i $O/prof_pwl.ncu-rep --page raw --csv > $O/prof_pwl.raw.csv 2>/dev/null
+ncu -i $O/prof_pwl.ncu-rep --page source --csv > $O/prof_pwl.source.csv 2>/dev/null
+rm -f $O/prof_pwl.ncu-rep
+ls -la $O

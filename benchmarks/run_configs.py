@@ -132,13 +132,21 @@ def main():
         from diffus_b200 import ops
         from diffus_b200.impedance import pack_params
         pk = pack_params(model).detach()
-        for name, path in (("cuda cores", ops.MLP_PATH_CUDA_CORES), ("tcgen05 3xTF32", ops.MLP_PATH_TENSOR)):
+        gz = torch.randn(mri.numel(), device=dev)
+        paths = (("cuda cores", ops.MLP_PATH_CUDA_CORES), ("tcgen05 3xTF32", ops.MLP_PATH_TENSOR),
+                 ("piecewise-linear table", ops.MLP_PATH_PIECEWISE))
+        for name, path in paths:
             with ops.mlp_path(path):
                 t_ms = timed(lambda: ops.mlp_fwd_impl(pk, mri.reshape(-1), None, 1e6, 400.0), args.iters)
+                b_ms = timed(lambda: ops.mlp_bwd_impl(pk, mri.reshape(-1), None, gz, 1e6), max(3, args.iters // 4))
             print(json.dumps({"config": f"4: MLP forward over 256^3 voxels, {name}", "ms": t_ms,
                               "gvoxels_per_s": mri.numel() / (t_ms * 1e-3) / 1e9,
-                              "tflops_layer2": mri.numel() * 2048 / (t_ms * 1e-3) / 1e12}), flush=True)
-        gz = torch.randn(mri.numel(), device=dev)
+                              "tflops_layer2": mri.numel() * 2048 / (t_ms * 1e-3) / 1e12,
+                              "hbm_gb_per_s": mri.numel() * 8 / (t_ms * 1e-3) / 1e9}), flush=True)
+            print(json.dumps({"config": f"4: MLP weight gradient over 256^3 voxels (dense d loss / d Z), {name}", "ms": b_ms,
+                              "gvoxels_per_s": mri.numel() / (b_ms * 1e-3) / 1e9,
+                              "tflops_layer2": mri.numel() * 6144 / (b_ms * 1e-3) / 1e12,
+                              "hbm_gb_per_s": mri.numel() * 8 / (b_ms * 1e-3) / 1e9}), flush=True)
         bwd_ms = timed(lambda: ops.mlp_bwd_impl(pk, mri.reshape(-1), None, gz, 1e6), max(3, args.iters // 4))
         fwd_ms = timed(lambda: ops.mlp_fwd_impl(pk, mri.reshape(-1), None, 1e6, 400.0), args.iters)
         report("4: MLP(256^3) -> 4096 frames -> MSE -> d/dweights (one training step, 1 GPU)", ms, P * 65536, P, 68,

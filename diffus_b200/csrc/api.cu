@@ -338,9 +338,11 @@ int32_t diffus_mlp_forward_ex(const float* params, const float* x, const uint8_t
                               float fill, float* out, int32_t path, void* stream) {
     if (!params || !x || !out) return DIFFUS_E_NULL;
     if (n < 1) return DIFFUS_E_SHAPE;
-    if (path < DIFFUS_MLP_PATH_AUTO || path > DIFFUS_MLP_PATH_TENSOR) return DIFFUS_E_ENUM;
-    // volumes go through the tcgen05 kernel (128-voxel tiles); a handful of samples is not worth a TMEM allocation
-    const bool tensor = path == DIFFUS_MLP_PATH_TENSOR || (path == DIFFUS_MLP_PATH_AUTO && n >= 16384);
+    if (path < DIFFUS_MLP_PATH_AUTO || path > DIFFUS_MLP_PATH_PIECEWISE) return DIFFUS_E_ENUM;
+    // volumes go through the piecewise-linear table; a handful of samples is not worth building it
+    if (path == DIFFUS_MLP_PATH_PIECEWISE || (path == DIFFUS_MLP_PATH_AUTO && n >= 1024))
+        return cuda_rc(launch_mlp_pwl_fwd(params, x, mask, n, out_scale, fill, out, (cudaStream_t)stream));
+    const bool tensor = path == DIFFUS_MLP_PATH_TENSOR;
     if (tensor) return cuda_rc(launch_mlp_fwd_tc(params, x, mask, n, out_scale, fill, out, (cudaStream_t)stream));
     return cuda_rc(launch_mlp_fwd(params, x, mask, n, out_scale, fill, out, (cudaStream_t)stream));
 }
@@ -357,9 +359,12 @@ int32_t diffus_mlp_backward_ex(const float* params, const float* x, const uint8_
                                void* stream) {
     if (!params || !x || !grad_out || !grad_params) return DIFFUS_E_NULL;
     if (n < 1) return DIFFUS_E_SHAPE;
-    if (path < DIFFUS_MLP_PATH_AUTO || path > DIFFUS_MLP_PATH_TENSOR) return DIFFUS_E_ENUM;
+    if (path < DIFFUS_MLP_PATH_AUTO || path > DIFFUS_MLP_PATH_PIECEWISE) return DIFFUS_E_ENUM;
     if (!workspace || workspace_bytes < mlp_bwd_workspace_bytes(n)) return DIFFUS_E_WORKSPACE;
-    const bool tensor = path == DIFFUS_MLP_PATH_TENSOR || (path == DIFFUS_MLP_PATH_AUTO && n >= 16384);
+    if (((uintptr_t)workspace & 7u) != 0) return DIFFUS_E_WORKSPACE;
+    if (path == DIFFUS_MLP_PATH_PIECEWISE || (path == DIFFUS_MLP_PATH_AUTO && n >= 1024))
+        return cuda_rc(launch_mlp_pwl_bwd(params, x, mask, grad_out, n, out_scale, grad_params, workspace, (cudaStream_t)stream));
+    const bool tensor = path == DIFFUS_MLP_PATH_TENSOR;
     return cuda_rc(launch_mlp_bwd(params, x, mask, grad_out, n, out_scale, grad_params, workspace, tensor, (cudaStream_t)stream));
 }
 

@@ -146,7 +146,15 @@ cudaError_t launch_mlp_fwd_tc(const float* params, const float* x, const uint8_t
 int64_t mlp_bwd_workspace_bytes(int64_t n);
 cudaError_t launch_mlp_bwd(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
                            float out_scale, float* grad_params, void* workspace, bool tensor_cores, cudaStream_t st);
+cudaError_t launch_mlp_bwd_gated(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                                 float out_scale, float* grad_params, void* workspace, const int* gate, cudaStream_t st);
 int mlp_bwd_tc_blocks(int64_t n);
+// mlp_pwl_kernels.cu: the scalar-input MLP as a piecewise-linear table
+int64_t mlp_pwl_bwd_workspace_bytes(int64_t n);
+cudaError_t launch_mlp_pwl_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale, float fill,
+                               float* out, cudaStream_t st);
+cudaError_t launch_mlp_pwl_bwd(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                               float out_scale, float* grad_params, void* workspace, cudaStream_t st);
 cudaError_t launch_mlp_bwd_tc(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
                               float out_scale, float* block_partials, int blocks, cudaStream_t st);
 

@@ -99,7 +99,9 @@ constexpr int TILE_LD = H + 4;     // padded row: float4 reads stay aligned, row
 __global__ void __launch_bounds__(BWD_WARPS * 32) mlp_bwd_kernel(const float* __restrict__ params, const float* __restrict__ x,
                                                                  const uint8_t* __restrict__ mask,
                                                                  const float* __restrict__ grad_out, int64_t n,
-                                                                 float out_scale, float* __restrict__ block_partials) {
+                                                                 float out_scale, float* __restrict__ block_partials,
+                                                                 const int* __restrict__ gate) {
+    if (gate && *gate == 0) return;          // fallback launch behind the piecewise-linear path: not needed
     __shared__ __align__(16) float h1_tile[BWD_WARPS][32 * TILE_LD];
     __shared__ __align__(16) float dh2_tile[BWD_WARPS][32 * TILE_LD];
     __shared__ float xs[BWD_WARPS][32], gs[BWD_WARPS][32];
@@ -220,9 +222,10 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) mlp_bwd_kernel(const float* __
     for (int i = threadIdx.x; i < DIFFUS_MLP_NPARAMS; i += blockDim.x) dst[i] = red[i];
 }
 
-__global__ void mlp_bwd_reduce_kernel(const float* __restrict__ block_partials, int n_blocks, float* __restrict__ grad_params) {
+__global__ void mlp_bwd_reduce_kernel(const float* __restrict__ block_partials, int n_blocks, float* __restrict__ grad_params,
+                                      const int* __restrict__ gate) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= DIFFUS_MLP_NPARAMS) return;
+    if (i >= DIFFUS_MLP_NPARAMS || (gate && *gate == 0)) return;
     double s = 0.0;                          // a few hundred partials of mixed sign: summed in double, fixed order
     for (int b = 0; b < n_blocks; ++b) s += (double)block_partials[(int64_t)b * DIFFUS_MLP_NPARAMS + i];
     grad_params[i] += (float)s;
@@ -234,9 +237,21 @@ static int mlp_bwd_blocks(int64_t n) {
     return (int)max((int64_t)1, min(want, (int64_t)148 * 4));
 }
 
-int64_t mlp_bwd_workspace_bytes(int64_t n) {
+static int64_t mlp_bwd_dense_workspace_bytes(int64_t n) {
     int blocks = max(mlp_bwd_blocks(n), mlp_bwd_tc_blocks(n));
     return (int64_t)blocks * DIFFUS_MLP_NPARAMS * sizeof(float);
+}
+
+// enough for every path: the piecewise-linear path's tables and partial moments, then the dense block partials (its fallback)
+int64_t mlp_bwd_workspace_bytes(int64_t n) { return mlp_pwl_bwd_workspace_bytes(n) + mlp_bwd_dense_workspace_bytes(n); }
+
+// the CUDA-core kernels behind a device-side gate (run only if *gate != 0)
+cudaError_t launch_mlp_bwd_gated(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                                 float out_scale, float* grad_params, void* workspace, const int* gate, cudaStream_t st) {
+    const int blocks = mlp_bwd_blocks(n);
+    mlp_bwd_kernel<<<blocks, BWD_WARPS * 32, 0, st>>>(params, x, mask, grad_out, n, out_scale, (float*)workspace, gate);
+    mlp_bwd_reduce_kernel<<<(DIFFUS_MLP_NPARAMS + 127) / 128, 128, 0, st>>>((const float*)workspace, blocks, grad_params, gate);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mlp_bwd(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
@@ -248,11 +263,11 @@ cudaError_t launch_mlp_bwd(const float* params, const float* x, const uint8_t* m
         e = launch_mlp_bwd_tc(params, x, mask, grad_out, n, out_scale, (float*)workspace, blocks, st);
     } else {
         blocks = mlp_bwd_blocks(n);
-        mlp_bwd_kernel<<<blocks, BWD_WARPS * 32, 0, st>>>(params, x, mask, grad_out, n, out_scale, (float*)workspace);
+        mlp_bwd_kernel<<<blocks, BWD_WARPS * 32, 0, st>>>(params, x, mask, grad_out, n, out_scale, (float*)workspace, nullptr);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
-    mlp_bwd_reduce_kernel<<<(DIFFUS_MLP_NPARAMS + 127) / 128, 128, 0, st>>>((const float*)workspace, blocks, grad_params);
+    mlp_bwd_reduce_kernel<<<(DIFFUS_MLP_NPARAMS + 127) / 128, 128, 0, st>>>((const float*)workspace, blocks, grad_params, nullptr);
     return cudaGetLastError();
 }
 

@@ -810,8 +810,8 @@ class SplatFunction(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------
 # MLP
 # ---------------------------------------------------------------------------------------
-MLP_PATH_AUTO, MLP_PATH_CUDA_CORES, MLP_PATH_TENSOR = 0, 1, 2
-_MLP_PATH = MLP_PATH_AUTO      # tests and benchmarks pin a path through mlp_path(); AUTO = tcgen05 for volumes
+MLP_PATH_AUTO, MLP_PATH_CUDA_CORES, MLP_PATH_TENSOR, MLP_PATH_PIECEWISE = 0, 1, 2, 3
+_MLP_PATH = MLP_PATH_AUTO      # tests and benchmarks pin a path through mlp_path(); AUTO = the piecewise-linear table for volumes
 
 
 class mlp_path:

@@ -263,6 +263,92 @@ def mlp_forward(x, w1, b1, w2, b2, w3, b3):
     return h2 @ w3.t() + b3
 
 
+def mlp_piecewise_table(w1, b1, w2, b2, w3, b3):
+    """The same network (``src/impedance.py:10-17``) as the piecewise-linear function of its scalar input that it is --
+    the restatement the CUDA path ``DIFFUS_MLP_PATH_PIECEWISE`` evaluates (csrc/mlp_pwl_kernels.cu), checked here against
+    :func:`mlp_forward`.  Returns ``(breakpoints (B,), P (B+1,), Q (B+1,), midpoints (B+1,))`` in float64 with
+    ``mlp(x) = P[r] x + Q[r]`` for ``r = searchsorted(breakpoints, x, side='right')``.
+
+    Layer-1 units switch at ``-b1_i / w1_i``; between two such points the layer-1 mask is fixed, every layer-2 pre-activation
+    is affine in x and switches at most once.  Masks are taken at the midpoint of each region."""
+    import numpy as np
+    w1 = np.asarray(w1, dtype=np.float64).reshape(-1)
+    b1 = np.asarray(b1, dtype=np.float64).reshape(-1)
+    w2 = np.asarray(w2, dtype=np.float64)
+    b2 = np.asarray(b2, dtype=np.float64).reshape(-1)
+    w3 = np.asarray(w3, dtype=np.float64).reshape(-1)
+    b3 = float(np.asarray(b3, dtype=np.float64).reshape(-1)[0])
+
+    def mid(a, b):
+        if np.isinf(a) and np.isinf(b):
+            return 0.0
+        if np.isinf(a):
+            return b - 1.0 - abs(b)
+        if np.isinf(b):
+            return a + 1.0 + abs(a)
+        return 0.5 * (a + b)
+
+    def affine(xm):
+        m1 = (w1 * xm + b1) > 0
+        return m1, w2 @ (m1 * w1), w2 @ (m1 * b1) + b2
+
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(w1 != 0, -b1 / w1, np.inf)
+    first = np.sort(t[np.isfinite(t)])
+    edges = np.concatenate([[-np.inf], first, [np.inf]])
+    bps = list(first)
+    for a, b in zip(edges[:-1], edges[1:]):
+        if not a < b:
+            continue
+        _, p, q = affine(mid(a, b))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = np.where(p != 0, -q / p, np.inf)
+        bps += [v for v in r if a < v < b]
+    bps = np.sort(np.asarray(bps, dtype=np.float64))
+    edges = np.concatenate([[-np.inf], bps, [np.inf]])
+    P, Q, xm = [], [], []
+    for a, b in zip(edges[:-1], edges[1:]):
+        x0 = mid(a, b)
+        _, p, q = affine(x0)
+        m2 = (p * x0 + q) > 0
+        P.append(float(w3 @ (m2 * p)))
+        Q.append(float(w3 @ (m2 * q)) + b3)
+        xm.append(x0)
+    return bps, np.asarray(P), np.asarray(Q), np.asarray(xm)
+
+
+def mlp_piecewise_grads(x, g, w1, b1, w2, b2, w3, b3):
+    """d/d(parameters) of ``sum_v g_v mlp(x_v)`` from two moments per region, ``G0 = sum g`` and ``G1 = sum g x`` (inside a
+    region the Jacobian of the network w.r.t. its parameters is affine in x).  Returns the gradients in ``nn.Linear`` layout."""
+    import numpy as np
+    bps, _, _, xm = mlp_piecewise_table(w1, b1, w2, b2, w3, b3)
+    w1 = np.asarray(w1, dtype=np.float64).reshape(-1)
+    b1 = np.asarray(b1, dtype=np.float64).reshape(-1)
+    w2 = np.asarray(w2, dtype=np.float64)
+    b2 = np.asarray(b2, dtype=np.float64).reshape(-1)
+    w3 = np.asarray(w3, dtype=np.float64).reshape(-1)
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    g = np.asarray(g, dtype=np.float64).reshape(-1)
+    r = np.searchsorted(bps, x, side="right")
+    G0 = np.bincount(r, weights=g, minlength=len(xm))
+    G1 = np.bincount(r, weights=g * x, minlength=len(xm))
+    gw1, gb1, gw2, gb2, gw3, gb3 = np.zeros(32), np.zeros(32), np.zeros((32, 32)), np.zeros(32), np.zeros(32), 0.0
+    for k, x0 in enumerate(xm):
+        if G0[k] == 0 and G1[k] == 0:
+            continue
+        m1 = (w1 * x0 + b1) > 0
+        p, q = w2 @ (m1 * w1), w2 @ (m1 * b1) + b2
+        m2 = (p * x0 + q) > 0
+        u = m1 * (w2.T @ (m2 * w3))                            # d out / d h1 under both masks
+        gw1 += u * G1[k]
+        gb1 += u * G0[k]
+        gw2 += np.outer(m2 * w3, m1 * (w1 * G1[k] + b1 * G0[k]))
+        gb2 += m2 * w3 * G0[k]
+        gw3 += m2 * (p * G1[k] + q * G0[k])
+        gb3 += G0[k]
+    return gw1.reshape(32, 1), gb1, gw2, gb2, gw3.reshape(1, 32), np.asarray([gb3])
+
+
 # ----------------------------------------------------------------------------------------
 # MRI preprocessing  (src/utils.py:12-39, src/impedance.py:39-54)  -- SURVEY row f4
 # ----------------------------------------------------------------------------------------

@@ -269,3 +269,47 @@ def test_training_loop_port_vs_reference_fixture():
     y = torch.tensor(g["ssim_real"])
     assert abs(port.ssim_piq(y, y).item() - 1.0) < 1e-12
     assert port.ssim_piq(y, 1 - y).item() < 0.2
+
+
+def _zigzag_mlp():
+    """Weights whose network has > 1000 linear pieces: layer-1 units switch at 0, 1, ..., 31 and every layer-2 unit zigzags
+    through zero once per interval (the CUDA path falls back to the layered evaluation above 256 regions)."""
+    import torch
+    w1 = torch.ones(32, 1)
+    b1 = -torch.arange(32, dtype=torch.float32)
+    w2 = torch.zeros(32, 32)
+    for j in range(32):
+        w2[j, 0] = 1.0
+        w2[j, 1:] = 2.0 * (-1.0) ** torch.arange(1, 32)          # slopes +1, -1, +1, ... from x = 0 on
+    b2 = -(0.2 + 0.6 * torch.arange(32, dtype=torch.float32) / 32.0)   # a different crossing height per unit
+    w3 = torch.linspace(-1.0, 1.0, 32).reshape(1, 32)
+    b3 = torch.tensor([0.25])
+    return [w1, b1, w2, b2, w3, b3]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, "zigzag"])
+def test_mlp_piecewise_linear_restatement_matches_layered_oracle(seed):
+    """The piecewise-linear form of the scalar-input MLP (what DIFFUS_MLP_PATH_PIECEWISE evaluates) == the layered network
+    (src/impedance.py:10-17), values and weight gradients, in float64."""
+    import torch
+    from oracle import port
+    if seed == "zigzag":
+        prm = [p.double() for p in _zigzag_mlp()]
+    else:
+        torch.manual_seed(seed)
+        m = torch.nn.Sequential(torch.nn.Linear(1, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(), torch.nn.Linear(32, 1))
+        prm = [p.detach().double() for p in m.parameters()]
+    gen = torch.Generator().manual_seed(7)
+    x = (torch.rand(20000, generator=gen, dtype=torch.float64) * 40.0 - 4.0) if seed == "zigzag" else \
+        torch.randn(20000, generator=gen, dtype=torch.float64) * 3.0
+    g = torch.randn(20000, generator=gen, dtype=torch.float64)
+    bps, P, Q, _ = port.mlp_piecewise_table(*[p.numpy() for p in prm])
+    assert (len(bps) > 1000) if seed == "zigzag" else (32 <= len(bps) <= 1088)
+    r = np.searchsorted(bps, x.numpy(), side="right")
+    want = port.mlp_forward(x.reshape(-1, 1), *prm).reshape(-1)
+    np.testing.assert_allclose(P[r] * x.numpy() + Q[r], want.numpy(), rtol=0, atol=1e-12 * max(1.0, float(want.abs().max())))
+    leaves = [p.clone().requires_grad_(True) for p in prm]
+    (port.mlp_forward(x.reshape(-1, 1), *leaves).reshape(-1) * g).sum().backward()
+    got = port.mlp_piecewise_grads(x.numpy(), g.numpy(), *[p.numpy() for p in prm])
+    for a, b in zip(got, leaves):
+        np.testing.assert_allclose(a, b.grad.numpy(), rtol=1e-9, atol=1e-9 * float(b.grad.abs().max()))
