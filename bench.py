@@ -525,7 +525,9 @@ def run_ours(args):
                             "eager": "render_mse_loss + loss.backward() (eager autograd, explicit directions)"}[args.e2e],
                     "note": "public API call per step; pose parameters (fan: source, median direction, in-plane hint; else "
                             "source + explicit directions) from pinned host memory each step, loss and pose gradients copied "
-                            "back to pinned host memory, stream synchronised every step; volume and target frames resident"},
+                            "back to pinned host memory, stream synchronised every step; volume and target frames resident.  "
+                            "The explicit-direction forms (--e2e graph / eager, the reference's plot_beam_frame signature) move "
+                            "1.57 MB each way per step, ~0.12 ms of PCIe that the 36 KB pose-parameter form does not pay"},
             "gpu_launches": launches,
             "kernels_ms": {"fused_step(render_bwd_kernel+reduce_rays+reduce_sum)": step_ms},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -534,8 +536,11 @@ def run_ours(args):
                          "bytes_note": "SURVEY 8(d) counts 72 B/sample for forward+backward done as two passes "
                                        "(2 x (8 gathers x 4 B + 4 B)); the fused kernel gathers once and reads the "
                                        "target once, so its own algorithmic traffic is 36 B/sample.  The volume is L2-resident "
-                                       "by design (DRAM is ~6 % busy): the kernel is bound by issue slots and the L1 / texture "
-                                       "path, see gather_roof and profiles/",
+                                       "by design (DRAM is ~7 % busy, L2 18 %, L1/texture 41 %): no memory roof is near -- the "
+                                       "kernel is latency-bound on its texture gathers at 16 resident warps per SM (issue slots "
+                                       "60 % busy, 5.94 warp instructions per sample), see gather_roof and "
+                                       "profiles/r2_fused_kernel_wide.md",
+                         "binding_unit": "texture-gather latency / issue slots (ncu: long_scoreboard 31 %, issue active 60 %)",
                          "frac_vs_two_pass_bytes": samples_per_step * 72 / (step_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,
             "loss": loss_value,

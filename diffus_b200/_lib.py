@@ -85,6 +85,7 @@ SIGNATURES = {
     "diffus_splat_forward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _i64, _vp]),
     "diffus_splat_backward": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _i64, _vp]),
     "diffus_mlp_backward_ex": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _i64, _i32, _vp]),
+    "diffus_mlp_input_grad": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp]),
     "diffus_brain_mask": (_i32, [_vp, _P(_i32 * 3), _f32, _i32, _vp, _vp, _vp]),
     "diffus_masked_zscore": (_i32, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "diffus_brick_elems": (_i64, [_P(_i32 * 3)]),

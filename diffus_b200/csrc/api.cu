@@ -375,6 +375,13 @@ int32_t diffus_mlp_backward(const float* params, const float* x, const uint8_t* 
                                   DIFFUS_MLP_PATH_AUTO, stream);
 }
 
+int32_t diffus_mlp_input_grad(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                              float out_scale, float* grad_x, void* stream) {
+    if (!params || !x || !grad_out || !grad_x) return DIFFUS_E_NULL;
+    if (n < 1) return DIFFUS_E_SHAPE;
+    return cuda_rc(launch_mlp_pwl_dx(params, x, mask, grad_out, n, out_scale, grad_x, (cudaStream_t)stream));
+}
+
 int64_t diffus_splat_workspace_bytes(int32_t H, int32_t W) { return (H < 1 || W < 1) ? 0 : splat_workspace_bytes(H, W); }
 
 int32_t diffus_splat_forward(const float* c0, const float* c1, const float* c2, const float* intensities, int64_t n,

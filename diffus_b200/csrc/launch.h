@@ -153,6 +153,8 @@ int mlp_bwd_tc_blocks(int64_t n);
 int64_t mlp_pwl_bwd_workspace_bytes(int64_t n);
 cudaError_t launch_mlp_pwl_fwd(const float* params, const float* x, const uint8_t* mask, int64_t n, float out_scale, float fill,
                                float* out, cudaStream_t st);
+cudaError_t launch_mlp_pwl_dx(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                              float out_scale, float* grad_x, cudaStream_t st);
 cudaError_t launch_mlp_pwl_bwd(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
                                float out_scale, float* grad_params, void* workspace, cudaStream_t st);
 cudaError_t launch_mlp_bwd_tc(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,

@@ -261,6 +261,42 @@ __global__ void __launch_bounds__(PWL_THREADS) mlp_pwl_fwd_kernel(const float* _
         out[i] = (mask && !mask[i]) ? fill : out_scale * pwl_eval(S, nsearch, __ldg(x + i));
 }
 
+// d out / d x: the slope of the region (the input gradient nn.Sequential gives the reference's callers)
+__global__ void __launch_bounds__(PWL_THREADS) mlp_pwl_dx_kernel(const float* __restrict__ params, const float* __restrict__ x,
+                                                                const uint8_t* __restrict__ mask, const float* __restrict__ grad_out,
+                                                                int64_t n, float out_scale, float* __restrict__ grad_x) {
+    extern __shared__ __align__(16) unsigned char pwl_smem[];
+    PwlTable& S = *reinterpret_cast<PwlTable*>(pwl_smem);
+    pwl_build(S, *reinterpret_cast<PwlScratch*>(pwl_smem + PWL_TABLE_BYTES), params);
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gstride = (int64_t)gridDim.x * blockDim.x;
+    const bool table = S.nreg <= PWL_MAXR;
+    const int nsearch = S.nsearch;
+    for (int64_t i = gtid; i < n; i += gstride) {
+        const float xv = __ldg(x + i);
+        float slope;
+        if (table) {
+            slope = (float)S.P[pwl_region(S.bpf, nsearch, xv)];
+        } else {                                             // layered: sum_j w3_j [s_j > 0] sum_i W2[j][i] [h1_i > 0] w1_i
+            const float* prm = S.prm;
+            float h1[HID];
+#pragma unroll
+            for (int k = 0; k < HID; ++k) h1[k] = fmaf(prm[OFF_W1 + k], xv, prm[OFF_B1 + k]);
+            slope = 0.f;
+            for (int j = 0; j < HID; ++j) {
+                float sj = prm[OFF_B2 + j], dj = 0.f;
+#pragma unroll
+                for (int k = 0; k < HID; ++k) {
+                    const float w2 = prm[OFF_W2 + j * HID + k];
+                    sj = fmaf(w2, fmaxf(h1[k], 0.f), sj);
+                    dj = h1[k] > 0.f ? fmaf(w2, prm[OFF_W1 + k], dj) : dj;
+                }
+                if (sj > 0.f) slope = fmaf(prm[OFF_W3 + j], dj, slope);
+            }
+        }
+        grad_x[i] = (mask && !mask[i]) ? 0.f : __ldg(grad_out + i) * out_scale * slope;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // backward
 // workspace (8-byte aligned): [hdr: 4 x int32 {nreg, overflow, -, -}] [xm: PWL_MAXR doubles]
@@ -456,6 +492,17 @@ cudaError_t launch_mlp_pwl_fwd(const float* params, const float* x, const uint8_
     cudaError_t e = cudaFuncSetAttribute(mlp_pwl_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     mlp_pwl_fwd_kernel<<<pwl_blocks(n), PWL_THREADS, smem, st>>>(params, x, mask, n, out_scale, fill, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mlp_pwl_dx(const float* params, const float* x, const uint8_t* mask, const float* grad_out, int64_t n,
+                              float out_scale, float* grad_x, cudaStream_t st) {
+    const size_t smem = pwl_fwd_smem();
+    cudaError_t e = cudaFuncSetAttribute(mlp_pwl_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t want = (n + PWL_THREADS - 1) / PWL_THREADS;
+    mlp_pwl_dx_kernel<<<(unsigned)max((int64_t)1, min(want, (int64_t)148 * 4)), PWL_THREADS, smem, st>>>(params, x, mask, grad_out, n,
+                                                                                                      out_scale, grad_x);
     return cudaGetLastError();
 }
 

@@ -65,6 +65,9 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #ifndef DIFFUS_WIDE_SWEEP
 #define DIFFUS_WIDE_SWEEP 1    // one-pass pose-gradient kernels: single 512-column reverse sweep (see WideGeo)
 #endif
+#ifndef DIFFUS_WIDE_MULTIPASS
+#define DIFFUS_WIDE_MULTIPASS 0    // rays longer than one pass (config 5) as WIDE segments: 612 bytes of spills at 128 registers -- off
+#endif
 #ifndef DIFFUS_WIDE_CTAS
 #define DIFFUS_WIDE_CTAS 4      // resident 4-warp CTA equivalents per SM of the WIDE kernels (4: 128 registers, 5: 96 and spills)
 #endif
@@ -450,7 +453,28 @@ __device__ __forceinline__ void red_add_v4(float* base, uint32_t quad, const flo
                  : "memory");
 }
 
-// one parity slot: accumulate `v` under `key`; when the slot holds another quad, that quad is complete -- flush it first
+// predicated form of red_add_v4: no branch around the (rare) flush, so the eight slot updates of a sample stay straight-line code
+__device__ __forceinline__ void red_add_v4_if(float* base, uint32_t quad, const float4& v, bool go) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}\n" ::"l"(base + (size_t)quad * 4),
+        "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)go)
+        : "memory");
+}
+
+// one parity slot: accumulate a * (w0, w1) x (k-weights) under `key`; when the slot holds another quad, that quad is complete --
+// it is flushed (predicated reduction) and the slot restarts from zero.  Branch-free: 4 selects + 4 FMAs for the accumulators.
+__device__ __forceinline__ void quad_slot_fma(float* grad, uint32_t& K, float4& acc, uint32_t key, float a0, float a1, float k0, float k1,
+                                              bool nz) {
+    const bool miss = nz && key != K;
+    red_add_v4_if(grad, K, acc, miss && K != QUAD_NONE);
+    K = miss ? key : K;
+    acc.x = __fmaf_rn(a0, k0, miss ? 0.f : acc.x);          // a0 = a1 = 0 when !nz: the slot is left as it is
+    acc.y = __fmaf_rn(a0, k1, miss ? 0.f : acc.y);
+    acc.z = __fmaf_rn(a1, k0, miss ? 0.f : acc.z);
+    acc.w = __fmaf_rn(a1, k1, miss ? 0.f : acc.w);
+}
+
+// (nearest sampler) one parity slot: accumulate `v` under `key`
 __device__ __forceinline__ void quad_slot_update(float* grad, uint32_t& K, float4& acc, uint32_t key, const float4& v, bool nz) {
     const bool miss = nz && key != K;
     if (miss && K != QUAD_NONE) red_add_v4(grad, K, acc);
@@ -538,8 +562,7 @@ __device__ __forceinline__ void scatter_pass_quads(const RenderParams& p, const 
 #pragma unroll
                 for (int pk = 0; pk < 2; ++pk) {
                     const int s = (pi << 2) | (pj << 1) | pk;
-                    const float4 v = make_float4(a0 * wk[pk][0], a0 * wk[pk][1], a1 * wk[pk][0], a1 * wk[pk][1]);
-                    quad_slot_update(grad, K[s], acc[s], X[pi] + Y[pj] + Z[pk], v, nzi[pi] && nzj[pj] && nzk[pk]);
+                    quad_slot_fma(grad, K[s], acc[s], X[pi] + Y[pj] + Z[pk], a0, a1, wk[pk][0], wk[pk][1], nzi[pi] && nzj[pj] && nzk[pk]);
                 }
             }
     }
@@ -985,6 +1008,13 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
         }                                                                       \
         if (!P64_ && p.Sout <= PREFIX_STRIDE) {                                 \
             auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true>;      \
+            cudaError_t e = ensure_smem(k, smem);                               \
+            if (e != cudaSuccess) return e;                                     \
+            k<<<grid, threads, smem, st>>>(p);                                  \
+            return cudaGetLastError();                                          \
+        }                                                                       \
+        if (DIFFUS_WIDE_MULTIPASS && !P64_ && TRI && PG && !VG && p.Sout > PREFIX_STRIDE) { /* long rays (config 5) */ \
+            auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, false, (DIFFUS_WIDE_MULTIPASS && TRI && PG && !VG)>; \
             cudaError_t e = ensure_smem(k, smem);                               \
             if (e != cudaSuccess) return e;                                     \
             k<<<grid, threads, smem, st>>>(p);                                  \

@@ -901,12 +901,40 @@ def _mlp_setup(ctx, inputs, output):
     ctx.out_scale = out_scale
 
 
+def mlp_input_grad_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
+                        out_scale: float) -> torch.Tensor:
+    dev = _require_cuda(params, x, mask, grad_out)
+    p, xc, g = params.contiguous().float(), x.contiguous().float(), grad_out.contiguous().float()
+    m = None if mask is None else mask.contiguous().to(torch.uint8)
+    with torch.cuda.device(dev):
+        gx = torch.empty(x.shape, dtype=torch.float32, device=dev)
+        if xc.numel():
+            _lib.check(_lib.load().diffus_mlp_input_grad(p.data_ptr(), xc.data_ptr(), _ptr(m), g.data_ptr(), xc.numel(), out_scale,
+                                                         gx.data_ptr(), _stream(dev)), "diffus_mlp_input_grad")
+            _count(1)
+    return gx
+
+
+@torch.library.custom_op("diffus::mlp_input_grad", mutates_args=())
+def mlp_input_grad(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Tensor], grad_out: torch.Tensor,
+                   out_scale: float) -> torch.Tensor:
+    return mlp_input_grad_impl(params, x, mask, grad_out, out_scale)
+
+
+@mlp_input_grad.register_fake
+def _(params, x, mask, grad_out, out_scale):
+    return x.new_empty(x.shape, dtype=torch.float32)
+
+
 def _mlp_backward(ctx, grad):
     params, x, mask = ctx.saved_tensors
-    gp = None
+    gp = gx = None
+    m = mask if ctx.has_mask else None
     if ctx.needs_input_grad[0]:
-        gp = mlp_bwd(params, x, mask if ctx.has_mask else None, grad, ctx.out_scale).to(params.dtype)
-    return gp, None, None, None, None
+        gp = mlp_bwd(params, x, m, grad, ctx.out_scale).to(params.dtype)
+    if ctx.needs_input_grad[1]:                    # the input gradient nn.Sequential gives the reference's callers
+        gx = mlp_input_grad(params, x, m, grad, ctx.out_scale).to(x.dtype)
+    return gp, gx, None, None, None
 
 
 torch.library.register_autograd("diffus::mlp_fwd", _mlp_backward, setup_context=_mlp_setup)

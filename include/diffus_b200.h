@@ -217,6 +217,12 @@ int32_t diffus_mlp_backward_ex(const float* params, const float* x, const uint8_
                                float* grad_params, void* workspace, int64_t workspace_bytes,
                                int32_t path, void* stream);
 
+/* d / d x of sum_i grad_out[i] * out_scale * mlp(x[i]): grad_x[i] = grad_out[i] * out_scale * mlp'(x[i]) (0 where masked) --
+ * the input gradient the reference's nn.Sequential (src/impedance.py:10-17) hands to autograd.  mlp' is the slope of the linear
+ * piece x[i] lies in (piecewise-linear table; layered evaluation above 256 pieces). */
+int32_t diffus_mlp_input_grad(const float* params, const float* x, const uint8_t* mask, const float* grad_out,
+                              int64_t n, float out_scale, float* grad_x, void* stream);
+
 /* Scan conversion: differentiable_splat (src/renderer.py:694-737).  c0,c1,c2 are the three coordinate
  * arrays (float32, n each -- the reference casts x, y, z to float32, :709-710), intensities n float32.
  * The two axes of largest variance are picked on the device; pixels are rounded and clamped; duplicate

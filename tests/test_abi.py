@@ -118,6 +118,9 @@ def test_argument_validation_without_a_device(lib):
     assert lib.diffus_gather_probe(None, 1 << 20, 64, 256, 1, 0x1000, None) == -1
     assert lib.diffus_gather_probe(0x1000, 1 << 20, 60, 256, 1, 0x1000, None) == -2   # reads per thread: multiples of 8
     assert lib.diffus_mlp_backward_ex(0x1000, 0x1000, None, 0x1000, 64, 1.0, 0x1000, 0x1000, 1 << 20, 9, None) == -3
+    assert lib.diffus_mlp_backward_ex(0x1000, 0x1000, None, 0x1000, 64, 1.0, 0x1000, 0x1000, 16, 3, None) == -4   # piecewise path: workspace too small
+    assert lib.diffus_mlp_input_grad(0x1000, None, None, 0x1000, 64, 1.0, 0x1000, None) == -1
+    assert lib.diffus_mlp_input_grad(0x1000, 0x1000, None, 0x1000, 0, 1.0, 0x1000, None) == -2
 
 
 def test_library_is_sm100a_native(lib):

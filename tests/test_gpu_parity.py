@@ -143,6 +143,29 @@ def test_nearest_volume_gradient_golden(golden_tri):
     assert src.grad is None          # HEAD: round().long() cuts the graph
 
 
+def test_gradient_of_a_ray_with_a_zero_over_zero_interface_is_finite():
+    """Z1 + Z2 = 0 on one ray (the NaN rule of src/renderer.py:408): the reference's autograd returns NaN for that ray's
+    coefficients (0 * NaN inside the solve's backward); here the whole ray contributes ZERO gradient -- finite, and the
+    other rays keep theirs (deliberate deviations)."""
+    from diffus_b200 import compute_echo_traces
+    gen = torch.Generator().manual_seed(3)
+    r = (torch.rand((4, 300), generator=gen) - 0.5) * 0.2
+    r[2, 40] = float("nan")
+    r[3, 100] = float("inf")
+    w = torch.randn((4, 301), generator=gen)
+    rd = r.to(dev()).requires_grad_(True)
+    echo, _ = compute_echo_traces(rd)
+    assert torch.isfinite(echo).all() and (echo[2, 41:] == 0).all()
+    (echo * w.to(dev())).sum().backward()
+    g = rd.grad.cpu()
+    assert torch.isfinite(g).all()
+    assert (g[2] == 0).all() and (g[3] == 0).all()
+    clean = r[:2].double().requires_grad_(True)
+    from oracle import port
+    (port.echo_closed_form(clean) * w[:2].double()).sum().backward()
+    assert_grad_close(g[:2].numpy(), clean.grad.numpy(), "rays without a singular interface")
+
+
 def test_echo_traces_golden(golden_echo):
     from diffus_b200 import compute_echo_traces, propagate_full_rays_batched
     g = golden_echo
@@ -528,6 +551,40 @@ def test_mlp_piecewise_path_unaligned_and_tail():
         gb = ops.mlp_bwd_impl(params, x[1:].clone().to(dev()), mask[1:].clone().to(dev()), gup[1:].clone().to(dev()), 2.0)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=3e-7, atol=3e-7)
     assert_grad_close(ga.cpu().numpy(), gb.cpu().numpy(), "aligned vs unaligned piecewise backward")
+
+
+@pytest.mark.parametrize("weights", ["default", "zigzag"])
+def test_mlp_input_gradient_matches_autograd(weights):
+    """d / d x through ImpedanceEstimator (the slope of the linear piece) vs float64 autograd of the layered oracle."""
+    from diffus_b200 import ImpedanceEstimator, ops
+    from diffus_b200.impedance import pack_params
+    from oracle import port
+    from test_oracle_golden import _zigzag_mlp
+    torch.manual_seed(21)
+    model = ImpedanceEstimator(1)
+    prm = _zigzag_mlp() if weights == "zigzag" else [p.detach() for p in model.parameters()]
+    n = 4099
+    gen = torch.Generator().manual_seed(4)
+    x = (torch.rand(n, generator=gen) * 40.0 - 4.0) if weights == "zigzag" else torch.randn(n, generator=gen) * 2.0
+    gup, mask = torch.randn(n, generator=gen), torch.rand(n, generator=gen) > 0.25
+    x64 = x.double().requires_grad_(True)
+    out = port.mlp_forward(x64.reshape(-1, 1), *[p.double() for p in prm]).reshape(-1) * 3.0
+    (torch.where(mask, out, torch.zeros_like(out)) * gup.double()).sum().backward()
+    params = torch.cat([p.reshape(-1) for p in prm]).to(dev())
+    got = ops.mlp_input_grad_impl(params, x.to(dev()), mask.to(dev()), gup.to(dev()), 3.0)
+    # a sample within float32 rounding of a breakpoint may sit on the other piece: compare away from the kinks
+    want = x64.grad.numpy()
+    err = np.abs(got.cpu().numpy() - want)
+    tol = 1e-5 * np.abs(want).max() + 1e-5 * np.abs(want)
+    assert (err > tol).mean() < 2e-3, f"{(err > tol).sum()} of {n} input gradients off"
+    if weights == "default":                       # and through autograd: the module's forward hands d/dx back
+        m = model.to(dev())
+        xd = x.to(dev()).reshape(-1, 1).requires_grad_(True)
+        (m(xd).reshape(-1) * gup.to(dev())).sum().backward()
+        x2 = x.double().requires_grad_(True)
+        (port.mlp_forward(x2.reshape(-1, 1), *[p.double() for p in prm]).reshape(-1) * gup.double()).sum().backward()
+        e2 = np.abs(xd.grad.reshape(-1).cpu().numpy() - x2.grad.numpy())
+        assert (e2 > 1e-5 * np.abs(x2.grad.numpy()).max() + 1e-5 * np.abs(x2.grad.numpy())).mean() < 2e-3
 
 
 def test_mlp_volume_masked_and_large():
