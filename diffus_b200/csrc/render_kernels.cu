@@ -442,6 +442,9 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
 // slot is therefore flushed -- ONE red.v4 -- exactly when the ray has left its quad: 1.4 vector reductions per sample
 // instead of 4.2 scalar ones (5.6 atomics), with no shared-memory atomics, no tags in memory and no divergent control flow.
 // ---------------------------------------------------------------------------------------
+#ifndef DIFFUS_SCATTER_BRANCHY
+#define DIFFUS_SCATTER_BRANCHY 0   // slot miss handled in one branch region (flush + re-key + zero) instead of per-component selects
+#endif
 #ifndef DIFFUS_SCATTER_QUADS
 #define DIFFUS_SCATTER_QUADS 1
 #endif
@@ -465,6 +468,17 @@ __device__ __forceinline__ void red_add_v4_if(float* base, uint32_t quad, const 
 // it is flushed (predicated reduction) and the slot restarts from zero.  Branch-free: 4 selects + 4 FMAs for the accumulators.
 __device__ __forceinline__ void quad_slot_fma(float* grad, uint32_t& K, float4& acc, uint32_t key, float a0, float a1, float k0, float k1,
                                               bool nz) {
+#if DIFFUS_SCATTER_BRANCHY
+    if (nz && key != K) {                                   // one (rare) branch region: flush, re-key, restart from zero
+        red_add_v4_if(grad, K, acc, K != QUAD_NONE);
+        K = key;
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    acc.x = __fmaf_rn(a0, k0, acc.x);                       // a0 = a1 = 0 when !nz: the slot is left as it is
+    acc.y = __fmaf_rn(a0, k1, acc.y);
+    acc.z = __fmaf_rn(a1, k0, acc.z);
+    acc.w = __fmaf_rn(a1, k1, acc.w);
+#else
     const bool miss = nz && key != K;
     red_add_v4_if(grad, K, acc, miss && K != QUAD_NONE);
     K = miss ? key : K;
@@ -472,6 +486,7 @@ __device__ __forceinline__ void quad_slot_fma(float* grad, uint32_t& K, float4& 
     acc.y = __fmaf_rn(a0, k1, miss ? 0.f : acc.y);
     acc.z = __fmaf_rn(a1, k0, miss ? 0.f : acc.z);
     acc.w = __fmaf_rn(a1, k1, miss ? 0.f : acc.w);
+#endif
 }
 
 // (nearest sampler) one parity slot: accumulate `v` under `key`
