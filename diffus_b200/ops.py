@@ -44,8 +44,34 @@ def _require_cuda(*tensors: torch.Tensor) -> torch.device:
     return dev
 
 
+try:                                        # the raw handle of torch's current stream without building a Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                      # pragma: no cover
+    _raw_stream = None
+
+
 def _stream(dev: torch.device) -> C.c_void_p:
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(dev.index if dev.index is not None else torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _on_device:
+    """``with torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs ~4 us per call)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index
+        self.ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -71,7 +97,7 @@ class VolumeTexture:
         self.dims = tuple(v.shape)
         self.device = dev
         tex, arr = C.c_uint64(0), C.c_uint64(0)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.check(lib.diffus_volume_texture_create(v.data_ptr(), C.byref((C.c_int32 * 3)(*self.dims)), C.byref(tex),
                                                         C.byref(arr), _stream(dev)), "diffus_volume_texture_create")
             self.token = torch.zeros((1,), dtype=torch.int64, device=dev)
@@ -180,7 +206,7 @@ def render_fwd_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     _check_inputs(volume, bricks, dims, sources, directions)
     lib = _lib.load()
     a = DiffusRenderArgs()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
                                  product_f32)
         sout = n_samples - start
@@ -188,12 +214,15 @@ def render_fwd_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         prefix_only = prefix_only and save_prefix and nseg > 1
         frame = torch.empty((0,) if prefix_only else (P, R, max(sout, 0)), dtype=torch.float32, device=dev)
         prefix = torch.empty((P, R, nseg - 1, 4) if (save_prefix and nseg > 1) else (0,), dtype=torch.float32,
-                             device=dev)
+                             device=dev)         # (a fresh tensor even when empty: outputs of a custom op must not be shared)
         a.frame = frame.data_ptr() if frame.numel() else None
         a.seg_prefix = _ptr(prefix)
-        wbytes = lib.diffus_render_workspace_bytes(C.byref(a))
-        ws = torch.empty((max(wbytes, 1),), dtype=torch.uint8, device=dev)
-        a.workspace, a.workspace_bytes = ws.data_ptr(), wbytes
+        wbytes = lib.diffus_render_workspace_bytes(C.byref(a)) if start > 0 else 0      # only the median needs scratch
+        if wbytes:
+            ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), wbytes
+        else:
+            a.workspace, a.workspace_bytes = None, 0
         _lib.check(lib.diffus_render_forward(C.byref(a), _stream(dev)), "diffus_render_forward")
         _count(2 if start > 0 else 1)
     return frame, prefix
@@ -224,7 +253,7 @@ def render_bwd_impl(grad_frame: torch.Tensor, volume: torch.Tensor, bricks: Opti
     _check_inputs(volume, bricks, dims, sources, directions)
     lib = _lib.load()
     b = DiffusRenderBwdArgs()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         P, R = _fill_render_args(b.fwd, volume, bricks, dims, sources, directions, n_samples, start, alpha,
                                  sampler, product_f32)
         grad_frame = grad_frame.contiguous().float()
@@ -359,7 +388,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     _check_inputs(volume, bricks, dims, sources, directions)
     lib = _lib.load()
     b = DiffusRenderBwdArgs()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         P, R = _fill_render_args(b.fwd, volume, bricks, dims, sources, directions, n_samples, start, alpha,
                                  sampler, product_f32)
         sout = n_samples - start
@@ -461,7 +490,7 @@ def ray_indices(dims, sources, directions, n_samples, start, product_f32=False):
     dev = _require_cuda(sources, directions)
     lib = _lib.load()
     a = DiffusRenderArgs()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         dummy = torch.empty((1,), dtype=torch.float32, device=dev)
         P, R = _fill_render_args(a, dummy, None, dims, sources, directions, n_samples, start, 0.0, SAMPLER_NEAREST,
                                  product_f32)
@@ -478,7 +507,7 @@ def trace_values(volume, bricks, dims, sources, directions, n_samples, sampler, 
     _check_inputs(volume, bricks, dims, sources, directions)
     lib = _lib.load()
     a = DiffusRenderArgs()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, 0, 0.0, sampler, product_f32)
         out = torch.empty((P, R, n_samples), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_trace_values(C.byref(a), out.data_ptr(), _stream(dev)), "diffus_trace_values")
@@ -497,7 +526,7 @@ def sample_points(volume: torch.Tensor, points: torch.Tensor, sampler: int):
     vol.data = v.data_ptr()
     vol.dim[0], vol.dim[1], vol.dim[2] = v.shape
     vol.layout = LAYOUT_LINEAR
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         val = torch.empty((n,), dtype=torch.float32, device=dev)
         idx = torch.empty((3, n), dtype=torch.int64, device=dev)
         if n:
@@ -513,7 +542,7 @@ def trace_values_bwd(grad_values, volume, bricks, dims, sources, directions, n_s
     dev = _require_cuda(grad_values, volume, bricks, sources, directions)
     lib = _lib.load()
     a = DiffusRenderArgs()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         P, R = _fill_render_args(a, volume, bricks, dims, sources, directions, n_samples, 0, 0.0, sampler, product_f32)
         need_pose = need_pose and sampler == SAMPLER_TRILINEAR
         use_bricks = bricks is not None and bricks.numel() > 0
@@ -567,7 +596,7 @@ def echo_fwd_impl(refl: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     r = refl.contiguous().float()
     B, N = r.shape
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty((B, N + 1), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_echo_forward(r.data_ptr(), B, N, out.data_ptr(), _stream(dev)), "diffus_echo_forward")
         _count(1)
@@ -590,7 +619,7 @@ def echo_bwd_impl(refl: torch.Tensor, grad_echo: torch.Tensor) -> torch.Tensor:
     r = refl.contiguous().float()
     g = grad_echo.contiguous().float()
     B, N = r.shape
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty((B, N), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_echo_backward(r.data_ptr(), g.data_ptr(), B, N, out.data_ptr(), _stream(dev)),
                    "diffus_echo_backward")
@@ -629,7 +658,7 @@ def cone_directions(median: torch.Tensor, opening_angle: float, n_rays: int) -> 
     lib = _lib.load()
     m = median[..., :2].to(torch.float64).contiguous()
     P = m.shape[0]
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty((P, n_rays, 3), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_cone_directions(m.data_ptr(), P, n_rays, float(opening_angle), out.data_ptr(),
                                               _stream(dev)), "diffus_cone_directions")
@@ -644,7 +673,7 @@ def fan_directions_fwd(median: torch.Tensor, hint: torch.Tensor, opening_angle: 
     if m.dim() != 2 or m.shape[1] != 3 or h.shape != m.shape:
         raise _lib.DiffusError("median and hint must both be (P,3)")
     P = m.shape[0]
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty((P, n_rays, 3), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_fan_directions(m.data_ptr(), h.data_ptr(), P, n_rays, float(opening_angle), out.data_ptr(),
                                              _stream(dev)), "diffus_fan_directions")
@@ -659,7 +688,7 @@ def fan_directions_bwd(median: torch.Tensor, hint: torch.Tensor, grad_dirs: torc
     m, h = median.detach().float().contiguous(), hint.detach().float().contiguous()
     g = grad_dirs.float().contiguous()
     P = m.shape[0]
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         gm = torch.empty((P, 3), dtype=torch.float32, device=dev)
         gh = torch.empty((P, 3), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_fan_directions_backward(m.data_ptr(), h.data_ptr(), g.data_ptr(), P, n_rays, float(opening_angle),
@@ -700,7 +729,7 @@ def gather_probe(buffer_mib: int = 64, reads_per_thread: int = 64, n_threads: in
     """
     dev = device or torch.device("cuda", torch.cuda.current_device())
     lib = _lib.load()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         n = buffer_mib * (1 << 20) // 4
         buf = torch.ones((n,), dtype=torch.float32, device=dev)
         sink = torch.empty((n_threads,), dtype=torch.float32, device=dev)
@@ -730,7 +759,7 @@ def to_bricks(volume: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     v = volume.detach().contiguous().float()
     dim = (C.c_int32 * 3)(*v.shape)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty((lib.diffus_brick_elems(C.byref(dim)),), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_volume_to_bricks(v.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
                    "diffus_volume_to_bricks")
@@ -744,7 +773,7 @@ def to_quads(volume: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     v = volume.detach().contiguous().float()
     dim = (C.c_int32 * 3)(*v.shape)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty((lib.diffus_quad_elems(C.byref(dim)) // 4, 4), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_volume_to_quads(v.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
                    "diffus_volume_to_quads")
@@ -756,7 +785,7 @@ def from_bricks(bricks: torch.Tensor, dims) -> torch.Tensor:
     dev = _require_cuda(bricks)
     lib = _lib.load()
     dim = (C.c_int32 * 3)(*dims)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty(tuple(dims), dtype=torch.float32, device=dev)
         _lib.check(lib.diffus_bricks_to_volume(bricks.data_ptr(), C.byref(dim), out.data_ptr(), _stream(dev)),
                    "diffus_bricks_to_volume")
@@ -773,7 +802,7 @@ def _splat_call(fwd: bool, coords, val, H, W, sigma, grad_out=None):
     c = [t.reshape(-1).to(torch.float32).contiguous() for t in coords]
     v = val.reshape(-1).to(torch.float32).contiguous()
     n = v.numel()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         wbytes = lib.diffus_splat_workspace_bytes(H, W)
         ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
         if fwd:
@@ -838,7 +867,7 @@ def mlp_fwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Ten
     p = params.contiguous().float()
     xc = x.contiguous().float()
     m = None if mask is None else mask.contiguous().to(torch.uint8)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty(x.shape, dtype=torch.float32, device=dev)
         if xc.numel():
             _lib.check(lib.diffus_mlp_forward_ex(p.data_ptr(), xc.data_ptr(), _ptr(m), xc.numel(), out_scale, fill,
@@ -869,7 +898,7 @@ def mlp_bwd_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[torch.Ten
     xc = x.contiguous().float()
     g = grad_out.contiguous().float()
     m = None if mask is None else mask.contiguous().to(torch.uint8)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         gp = torch.zeros((MLP_NPARAMS,), dtype=torch.float32, device=dev) if grad_params_out is None else grad_params_out
         n = xc.numel()
         if n:
@@ -906,7 +935,7 @@ def mlp_input_grad_impl(params: torch.Tensor, x: torch.Tensor, mask: Optional[to
     dev = _require_cuda(params, x, mask, grad_out)
     p, xc, g = params.contiguous().float(), x.contiguous().float(), grad_out.contiguous().float()
     m = None if mask is None else mask.contiguous().to(torch.uint8)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         gx = torch.empty(x.shape, dtype=torch.float32, device=dev)
         if xc.numel():
             _lib.check(_lib.load().diffus_mlp_input_grad(p.data_ptr(), xc.data_ptr(), _ptr(m), g.data_ptr(), xc.numel(), out_scale,
@@ -953,7 +982,7 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, state: torch.Tensor, lr
     if grads.numel() < n or state.numel() != 2 * n + 1 or params.dtype != torch.float32 or grads.dtype != torch.float32 \
             or state.dtype != torch.float32 or not (params.is_contiguous() and grads.is_contiguous() and state.is_contiguous()):
         raise _lib.DiffusError("adam_step needs contiguous float32 params (n), grads (>= n) and state (2n + 1)")
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _lib.check(_lib.load().diffus_adam_step(params.data_ptr(), grads.data_ptr(), state.data_ptr(), n, lr, betas[0], betas[1], eps,
                                                 weight_decay, grad_scale, _stream(dev)), "diffus_adam_step")
         _count(1)
@@ -964,7 +993,7 @@ def volume_slice(volume: torch.Tensor, dims, layout: int, axis: int, index: int,
     """Copy one slice out of (``scatter=False``) or into (``scatter=True``) a LINEAR / BRICK volume buffer."""
     dev = _require_cuda(volume, slice_)
     rest = [d for a, d in enumerate(dims) if a != axis]
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if slice_ is None:
             slice_ = torch.empty(rest, dtype=torch.float32, device=dev)
         elif slice_.numel() != rest[0] * rest[1] or slice_.dtype != torch.float32 or not slice_.is_contiguous():
@@ -1002,7 +1031,7 @@ class SliceInsertFunction(torch.autograd.Function):
 def rotate_apex(x: torch.Tensor, z: torch.Tensor, cos_a: float, sin_a: float, shift: float, apex0: float, apex1: float):
     dev = _require_cuda(x, z)
     xf, zf = x.to(torch.float32).contiguous(), z.to(torch.float32).contiguous()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         xr, zr = torch.empty_like(xf), torch.empty_like(zf)
         if xf.numel():
             _lib.check(_lib.load().diffus_rotate_around_apex(xf.data_ptr(), zf.data_ptr(), xf.numel(), cos_a, sin_a, shift, apex0, apex1,
@@ -1016,7 +1045,7 @@ class LogCompressFunction(torch.autograd.Function):
     def forward(ctx, img):
         dev = _require_cuda(img)
         x = img.detach().contiguous().float()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             out = torch.empty_like(x)
             _lib.check(_lib.load().diffus_log_compress_forward(x.data_ptr(), x.numel(), out.data_ptr(), None, _stream(dev)),
                        "diffus_log_compress_forward")
@@ -1042,7 +1071,7 @@ def rf_to_bmode(profiles: torch.Tensor, hilbert_kernel: torch.Tensor) -> torch.T
     rf = profiles.detach().contiguous().float()
     if rf.dim() != 2 or hilbert_kernel.numel() != rf.shape[1]:
         raise _lib.DiffusError("profiles must be (n_rays, n_samples) and the Hilbert kernel n_samples long")
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         out = torch.empty_like(rf)
         ws = torch.empty((4,), dtype=torch.uint8, device=dev)
         _lib.check(_lib.load().diffus_rf_to_bmode(rf.data_ptr(), rf.shape[0], rf.shape[1], hilbert_kernel.contiguous().float().data_ptr(),
@@ -1060,7 +1089,7 @@ class MaskedMSEEdgeFunction(torch.autograd.Function):
         a, b = synth.detach().contiguous().float(), real.detach().contiguous().float()
         m = mask.contiguous().to(torch.uint8)
         H, W = a.shape
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             stats = torch.empty((3,), dtype=torch.float32, device=dev)
             _lib.check(_lib.load().diffus_masked_mse_edge_forward(a.data_ptr(), b.data_ptr(), m.data_ptr(), H, W, edge_weight,
                                                                   stats.data_ptr(), _stream(dev)), "diffus_masked_mse_edge_forward")
@@ -1096,7 +1125,7 @@ class SSIMLossFunction(torch.autograd.Function):
         wbytes = lib.diffus_ssim_workspace_bytes(H, W, ksize)
         if wbytes <= 0:
             raise _lib.DiffusError(f"SSIM window {ksize} does not fit a {H} x {W} image (or exceeds 33)")
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             ws = torch.empty((wbytes,), dtype=torch.uint8, device=dev)
             loss = torch.empty((1,), dtype=torch.float32, device=dev)
             _lib.check(lib.diffus_ssim_loss_forward(a.data_ptr(), b.data_ptr(), H, W, ksize, sigma, k1, k2, int(normalize), loss.data_ptr(),

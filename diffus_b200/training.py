@@ -106,7 +106,7 @@ class FusedTrainer:
     MLP backward and the fused render kernel write into directly (no ``cat`` / ``copy_`` round trip), the Adam moments and
     step counter, the impedance bricks and their gradient bricks.  One :meth:`step`:
 
-        Z bricks = out_scale * MLP(mri bricks)                       tcgen05 kernel
+        Z bricks = out_scale * MLP(mri bricks)                       piecewise-linear table kernel
         loss, dZ = fused render + MSE + backward                     loss and gradients pre-scaled by 1 / global elements
         dW      += MLP backward(mri bricks, dZ)                      into the flat buffer
         all-reduce(SUM) of the flat buffer over ranks                4.6 KB, one NCCL launch
