@@ -99,6 +99,8 @@ SIGNATURES = {
     "diffus_volume_texture_destroy": (_i32, [C.c_uint64, C.c_uint64]),
     "diffus_adam_step": (_i32, [_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "diffus_volume_slice": (_i32, [_vp, _P(_i32 * 3), _i32, _i32, _i32, _vp, _i32, _vp]),
+    "diffus_conv1d_rows_forward": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "diffus_conv1d_rows_backward": (_i32, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp]),
     "diffus_rotate_around_apex": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "diffus_log_compress_forward": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "diffus_log_compress_backward": (_i32, [_vp, _vp, _i64, _vp, _vp]),

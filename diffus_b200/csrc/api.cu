@@ -421,6 +421,25 @@ int32_t diffus_volume_slice(float* volume, const int32_t dim[3], int32_t layout,
     return cuda_rc(launch_volume_slice(volume, dim, layout, axis, index, slice, scatter != 0, (cudaStream_t)stream));
 }
 
+int32_t diffus_conv1d_rows_forward(const float* in, int64_t rows, int32_t n_in, const float* w, int32_t taps, int32_t pad, float* out,
+                                   void* stream) {
+    if (!in || !w || !out) return DIFFUS_E_NULL;
+    const int64_t n_out = (int64_t)n_in + 2 * (int64_t)pad - taps + 1;
+    if (rows < 1 || n_in < 1 || taps < 1 || pad < 0 || n_out < 1) return DIFFUS_E_SHAPE;
+    if (taps > 128) return DIFFUS_E_UNSUPPORTED;
+    return cuda_rc(launch_conv1d_rows(in, rows, n_in, w, taps, pad, 0, out, (int)n_out, (cudaStream_t)stream));
+}
+
+int32_t diffus_conv1d_rows_backward(const float* grad_out, int64_t rows, int32_t n_in, const float* w, int32_t taps, int32_t pad,
+                                    float* grad_in, void* stream) {
+    if (!grad_out || !w || !grad_in) return DIFFUS_E_NULL;
+    const int64_t n_out = (int64_t)n_in + 2 * (int64_t)pad - taps + 1;
+    if (rows < 1 || n_in < 1 || taps < 1 || pad < 0 || n_out < 1) return DIFFUS_E_SHAPE;
+    if (taps > 128) return DIFFUS_E_UNSUPPORTED;
+    // grad_in[i] = sum_t w[t] grad_out[i - t + pad]: the same correlation over the (rows, n_out) gradient with w flipped
+    return cuda_rc(launch_conv1d_rows(grad_out, rows, (int)n_out, w, taps, taps - 1 - pad, 1, grad_in, n_in, (cudaStream_t)stream));
+}
+
 int32_t diffus_rotate_around_apex(const float* x, const float* z, int64_t n, float cos_a, float sin_a, float shift, float apex0,
                                   float apex1, float* x_rot, float* z_rot, void* stream) {
     if (!x || !z || !x_rot || !z_rot) return DIFFUS_E_NULL;

@@ -121,6 +121,8 @@ cudaError_t launch_adam_step(float* params, const float* grads, float* state, in
                              float eps, float weight_decay, float grad_scale, cudaStream_t st);
 cudaError_t launch_volume_slice(float* vol, const int32_t dim[3], int layout, int axis, int index, float* slice, bool scatter,
                                 cudaStream_t st);
+cudaError_t launch_conv1d_rows(const float* in, int64_t rows, int n_in, const float* w, int taps, int pad, int flip, float* out,
+                               int n_out, cudaStream_t st);
 cudaError_t launch_rotate_apex(const float* x, const float* z, int64_t n, float cos_a, float sin_a, float shift, float apex0,
                                float apex1, float* xr, float* zr, cudaStream_t st);
 cudaError_t launch_log_compress_fwd(const float* x, int64_t n, float* out, float* max_out, cudaStream_t st);

@@ -216,6 +216,38 @@ __global__ void rf_normalise_kernel(float* __restrict__ out, int64_t n, const un
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) out[t] = out[t] / m;
 }
 
+// ---------------------------------------------------------------------------------------
+// compute_gaussian_pulse's F.conv1d (src/renderer.py:476): every row cross-correlated with one short kernel,
+//     out[b][o] = sum_t w[t] in[b][o + t - pad]        (zero outside the row), o = 0 .. n_out - 1.
+// The backward w.r.t. the rows is the same kernel with w flipped and pad' = L - 1 - pad.
+// ---------------------------------------------------------------------------------------
+constexpr int CONV_MAX_TAPS = 128;
+
+__global__ void __launch_bounds__(256) conv1d_rows_kernel(const float* __restrict__ in, int64_t rows, int n_in, const float* __restrict__ w,
+                                                          int taps, int pad, int flip, float* __restrict__ out, int n_out) {
+    __shared__ float ws[CONV_MAX_TAPS];
+    for (int t = threadIdx.x; t < taps; t += blockDim.x) ws[t] = __ldg(w + (flip ? taps - 1 - t : t));
+    __syncthreads();
+    const int64_t total = rows * n_out;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = e / n_out;
+        const int o = (int)(e - b * n_out);
+        const float* row = in + b * n_in;
+        float acc = 0.f;
+        const int lo = max(0, pad - o), hi = min(taps, n_in + pad - o);       // taps whose sample lies inside the row
+        for (int t = lo; t < hi; ++t) acc = fmaf(ws[t], __ldg(row + o + t - pad), acc);
+        out[e] = acc;
+    }
+}
+
+cudaError_t launch_conv1d_rows(const float* in, int64_t rows, int n_in, const float* w, int taps, int pad, int flip, float* out,
+                               int n_out, cudaStream_t st) {
+    const int64_t total = rows * n_out;
+    const unsigned grid = (unsigned)max((int64_t)1, min((total + 255) / 256, (int64_t)148 * 8));
+    conv1d_rows_kernel<<<grid, 256, 0, st>>>(in, rows, n_in, w, taps, pad, flip, out, n_out);
+    return cudaGetLastError();
+}
+
 __global__ void zero_word_kernel(unsigned* w) { *w = 0u; }
 
 cudaError_t launch_rf_to_bmode(const float* rf, int64_t n_rays, int S, const float* g, float* out, void* workspace, cudaStream_t st) {

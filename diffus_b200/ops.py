@@ -988,6 +988,40 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, state: torch.Tensor, lr
         _count(1)
 
 
+class Conv1dRows(torch.autograd.Function):
+    """``F.conv1d(x.unsqueeze(1), w[None, None], padding=pad).squeeze(1)`` on (rows, n) float32 CUDA rows (the PSF step of
+    ``compute_gaussian_pulse``, reference ``src/renderer.py:476``); differentiable w.r.t. the rows."""
+
+    @staticmethod
+    def forward(ctx, x, w, pad):
+        dev = _require_cuda(x, w)
+        xc, wc = x.detach().contiguous().float(), w.detach().contiguous().float().reshape(-1)
+        rows, n_in, taps = xc.shape[0], xc.shape[1], wc.numel()
+        n_out = n_in + 2 * pad - taps + 1
+        with _on_device(dev):
+            out = torch.empty((rows, max(n_out, 0)), dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().diffus_conv1d_rows_forward(xc.data_ptr(), rows, n_in, wc.data_ptr(), taps, pad, out.data_ptr(),
+                                                              _stream(dev)), "diffus_conv1d_rows_forward")
+            _count(1)
+        ctx.save_for_backward(wc)
+        ctx.meta = (rows, n_in, taps, pad, x.dtype)
+        return out.to(x.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        (wc,) = ctx.saved_tensors
+        rows, n_in, taps, pad, dt = ctx.meta
+        dev = gout.device
+        g = gout.contiguous().float()
+        with _on_device(dev):
+            gin = torch.empty((rows, n_in), dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().diffus_conv1d_rows_backward(g.data_ptr(), rows, n_in, wc.data_ptr(), taps, pad, gin.data_ptr(),
+                                                               _stream(dev)), "diffus_conv1d_rows_backward")
+            _count(1)
+        return gin.to(dt), None, None
+
+
 def volume_slice(volume: torch.Tensor, dims, layout: int, axis: int, index: int, slice_: Optional[torch.Tensor] = None,
                  scatter: bool = False) -> torch.Tensor:
     """Copy one slice out of (``scatter=False``) or into (``scatter=True``) a LINEAR / BRICK volume buffer."""

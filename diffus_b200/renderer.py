@@ -297,15 +297,18 @@ def compute_gaussian_pulse(refLR: torch.Tensor, spacing: float = 1.0, c: float =
                            pulse=None) -> torch.Tensor:
     """Echo traces convolved with a Gaussian pulse (reference ``src/renderer.py:459-479``).
 
-    Off the hot path (the call is commented out on HEAD, ``:250``): the echo line comes from the scan kernel, the
-    short 1-D convolution is a library ``conv1d`` on the same device.
+    Off the hot path (the call is commented out on HEAD, ``:250``): the echo line comes from the scan kernel and the short
+    1-D convolution from ``conv1d_rows_kernel`` (differentiable in ``refLR``; the pulse is a constant, as in the reference,
+    where it is a numpy array).  ``pulse``: optional (1, 1, L) tensor like the reference's.
     """
-    import torch.nn.functional as F
     echo_signals, _ = compute_echo_traces(refLR, spacing, c)
     if pulse is None:
-        pulse = gaussian_pulse(length=length, sigma=sigma)
-        pulse = torch.tensor(pulse, dtype=echo_signals.dtype, device=echo_signals.device).unsqueeze(0).unsqueeze(0)
-    return F.conv1d(echo_signals.unsqueeze(1), pulse, padding=length // 2).squeeze(1)
+        pulse = torch.tensor(gaussian_pulse(length=length, sigma=sigma), dtype=echo_signals.dtype, device=echo_signals.device)
+    else:
+        if pulse.requires_grad:
+            raise NotImplementedError("compute_gaussian_pulse is differentiable in refLR only (the reference's pulse is a numpy constant)")
+        length = pulse.shape[-1]
+    return ops.Conv1dRows.apply(echo_signals, pulse.reshape(-1), int(length) // 2)
 
 
 def propagate_full_rays_batched(refLR: torch.Tensor) -> torch.Tensor:

@@ -258,6 +258,14 @@ int32_t diffus_volume_slice(float* volume, const int32_t dim[3], int32_t layout,
 int32_t diffus_rotate_around_apex(const float* x, const float* z, int64_t n, float cos_a, float sin_a, float shift, float apex0,
                                   float apex1, float* x_rot, float* z_rot, void* stream);
 
+/* The 1-D convolution of compute_gaussian_pulse (src/renderer.py:459-479: F.conv1d of the echo lines with one pulse, a
+ * cross-correlation): out[b][o] = sum_t w[t] in[b][o + t - pad], zero outside the row, out is (rows, n_in + 2 pad - taps + 1).
+ * taps <= 128.  The backward w.r.t. the rows: grad_in (rows, n_in) from grad_out (rows, n_out). */
+int32_t diffus_conv1d_rows_forward(const float* in, int64_t rows, int32_t n_in, const float* w, int32_t taps, int32_t pad,
+                                   float* out, void* stream);
+int32_t diffus_conv1d_rows_backward(const float* grad_out, int64_t rows, int32_t n_in, const float* w, int32_t taps, int32_t pad,
+                                    float* grad_in, void* stream);
+
 /* Log compression (north_star's "log-compressed B-mode"; the reference's only form is process_rf_to_bmode,
  * notebooks/[DEMO] Renderer Alternatives.ipynb cell 14: log1p(envelope) / max).
  * diffus_log_compress_*: out = log1p(|img|) / max(log1p(|img|)) over n pixels, and its backward (the maximum's gradient is

@@ -120,6 +120,9 @@ def test_argument_validation_without_a_device(lib):
     assert lib.diffus_mlp_backward_ex(0x1000, 0x1000, None, 0x1000, 64, 1.0, 0x1000, 0x1000, 1 << 20, 9, None) == -3
     assert lib.diffus_mlp_backward_ex(0x1000, 0x1000, None, 0x1000, 64, 1.0, 0x1000, 0x1000, 16, 3, None) == -4   # piecewise path: workspace too small
     assert lib.diffus_mlp_input_grad(0x1000, None, None, 0x1000, 64, 1.0, 0x1000, None) == -1
+    assert lib.diffus_conv1d_rows_forward(0x1000, 4, 60, None, 9, 4, 0x1000, None) == -1
+    assert lib.diffus_conv1d_rows_forward(0x1000, 4, 60, 0x1000, 200, 100, 0x1000, None) == -5
+    assert lib.diffus_conv1d_rows_backward(0x1000, 4, 3, 0x1000, 9, 0, 0x1000, None) == -2
     assert lib.diffus_mlp_input_grad(0x1000, 0x1000, None, 0x1000, 0, 1.0, 0x1000, None) == -2
 
 

@@ -730,6 +730,17 @@ def test_compute_gaussian_pulse_vs_oracle():
     want = torch.nn.functional.conv1d(echo.unsqueeze(1), pulse, padding=10).squeeze(1)
     assert got.shape == want.shape
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
+    # gradient through the convolution kernel and the echo scan, odd and even pulse lengths (even: the output is one longer)
+    for length, sigma in ((20, 4), (9, 2), (1, 1)):
+        w = torch.randn((4, 60 + 1 + 2 * (length // 2) - length + 1), generator=g, dtype=torch.float64)
+        r64 = r.double().requires_grad_(True)
+        pulse = torch.tensor(gaussian_pulse(length, sigma), dtype=torch.float64)[None, None]
+        (torch.nn.functional.conv1d(port.echo_closed_form(r64).unsqueeze(1), pulse, padding=length // 2).squeeze(1) * w).sum().backward()
+        rd = r.to(dev()).requires_grad_(True)
+        out = compute_gaussian_pulse(rd, length=length, sigma=sigma)
+        assert tuple(out.shape) == tuple(w.shape)
+        (out * w.float().to(dev())).sum().backward()
+        assert_grad_close(rd.grad.cpu().numpy(), r64.grad.numpy(), f"compute_gaussian_pulse d/drefLR (length {length})")
 
 
 def test_custom_nearest_sampler_explicit_points():
