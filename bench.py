@@ -247,7 +247,7 @@ def config4_record(dev, rank, world, barrier):
     for sampler in ("trilinear", "nearest"):
         with torch.no_grad():
             tgt = render_frames(PreparedVolume(z_tgt), s, d, N_SAMPLES, ALPHA, sampler=sampler)
-        tr = FusedTrainer(model, mri, lr=1e-4, sampler=sampler, out_scale=1e6)
+        tr = FusedTrainer(model, mri, lr=1e-4, sampler=sampler, out_scale=1e6, gather=os.environ.get("DIFFUS_CONFIG4_GATHER", "auto"))
         n_total = total * N_RAYS * N_SAMPLES
         last = [None]
 
@@ -285,7 +285,7 @@ def nccl_parity_record(dev, rank, world):
     tr = FusedTrainer(copy.deepcopy(model).to(dev), mri, lr=1e-3, sampler="trilinear", out_scale=1e6)
     z = tr.forward_volume().clone()
     from diffus_b200 import ops
-    z_lin = ops.from_bricks(z, [n, n, n])
+    z_lin = z if tr.gather == "texture" else ops.from_bricks(z, [n, n, n])       # (texture gathers: the volume is in torch order)
     frames_local = render_frames(z_lin, s_h[sl].to(dev), d_h[sl].to(dev), S, 1e-3, sampler="trilinear")
     frames = D.gather_frames(frames_local)                          # ragged shards: sizes are exchanged first
     loss = tr.step(s_h[sl].to(dev).contiguous(), d_h[sl].to(dev).contiguous(), tgt_h[sl].to(dev).contiguous(), S, 1e-3,

@@ -132,11 +132,16 @@ def test_fused_trainer_matches_autograd_and_torch_adam(sampler):
     want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
     m1 = copy.deepcopy(model).to(dev())
     tr = FusedTrainer(m1, mri.to(dev()), lr=1e-2, sampler=sampler, out_scale=1e6)
+    mt = copy.deepcopy(model).to(dev())
+    tt = FusedTrainer(mt, mri.to(dev()), lr=1e-2, sampler=sampler, out_scale=1e6, gather="texture")
     m2 = copy.deepcopy(model).to(dev())
     opt = torch.optim.Adam(m2.parameters(), lr=1e-2)
     args = (sources.to(dev()), dirs.to(dev()), targets.to(dev()), S, alpha)
     l1 = tr.step(*args)
     assert_grad_close(tr.grads.cpu().numpy(), want.numpy(), f"FusedTrainer weight gradient ({sampler})")
+    lt = tt.step(*args)                                        # the same step gathering through the texture unit
+    assert_grad_close(tt.grads.cpu().numpy(), want.numpy(), f"FusedTrainer weight gradient ({sampler}, texture gathers)")
+    np.testing.assert_allclose(lt.item(), l64.item(), rtol=1e-4)
     np.testing.assert_allclose(l1.item(), l64.item(), rtol=1e-4)
     l2 = train_step(m2, opt, mri.to(dev()), *args, out_scale=1e6, sampler=sampler)
     np.testing.assert_allclose(l1.item(), l2.item(), rtol=1e-5)
