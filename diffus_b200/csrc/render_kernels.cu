@@ -68,6 +68,9 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #ifndef DIFFUS_WIDE_MULTIPASS
 #define DIFFUS_WIDE_MULTIPASS 0    // rays longer than one pass (config 5) as WIDE segments: 612 bytes of spills at 128 registers -- off
 #endif
+#ifndef DIFFUS_WIDE_VOLGRAD
+#define DIFFUS_WIDE_VOLGRAD 1     // the WIDE sweep for the fused volume-gradient kernels (config 4) too
+#endif
 #ifndef DIFFUS_WIDE_CTAS
 #define DIFFUS_WIDE_CTAS 4      // resident 4-warp CTA equivalents per SM of the WIDE kernels (4: 128 registers, 5: 96 and spills)
 #endif
@@ -1011,8 +1014,10 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
 #define DIFFUS_BWD_GO(PG, VG)                                                   \
     {                                                                           \
         /* the one-pass specialisation exists for float32 poses only (build time) */ \
-        if (DIFFUS_WIDE_SWEEP && !P64_ && TRI && PG && !VG && p.Sout <= PREFIX_STRIDE && p.Sout > BwdGeo::SEG) { \
-            auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true, (DIFFUS_WIDE_SWEEP && TRI && PG && !VG)>; \
+        if (DIFFUS_WIDE_SWEEP && !P64_ && ((TRI && PG && !VG) || (DIFFUS_WIDE_VOLGRAD && VG && !PG && LOSS == LOSS_MSE)) &&  \
+            p.Sout <= PREFIX_STRIDE && p.Sout > BwdGeo::SEG) {                  \
+            auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true,       \
+                                       (DIFFUS_WIDE_SWEEP && ((TRI && PG && !VG) || (DIFFUS_WIDE_VOLGRAD && VG && !PG && LOSS == LOSS_MSE)))>; \
             int wpb_ = threads / 32;                                            \
             if (wpb_ == 4) wpb_ = DIFFUS_WIDE_WPB;                              \
             const size_t smem_ = ((size_t)p.att_slots_padded + (size_t)wpb_ * BWD_SMEM_PER_WARP) * sizeof(float); \
