@@ -276,6 +276,8 @@ def compute_echo_traces(refLR: torch.Tensor, spacing: float = 1.0, c: float = 1.
 
     ``refLR`` (B, N) -> ``(echo (B, N+1), delays_us (N+1,))`` with ``echo = [0, d0^(1..N)]``,
     ``d0^(k)`` the surface return of the first ``k`` interfaces; differentiable in ``refLR``.
+    The scan kernels compute in float32: a float64 (or half) ``refLR`` is evaluated in float32 and the result cast back to its
+    dtype, so float64 inputs do NOT buy float64 accuracy here (the reference's float64 run differs from this by ~1e-7 of peak).
     """
     if refLR.dim() != 2:
         B, N = refLR.shape      # same ValueError as the reference's unpacking (:425)
