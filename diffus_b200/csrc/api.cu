@@ -1,6 +1,7 @@
 // extern "C" entry points of libdiffus_b200.so (see include/diffus_b200.h).
 // Argument validation and parameter packing only; kernels live in the other translation units.
 #include <mutex>
+#include <unordered_map>
 #include <unordered_set>
 
 #include "common.cuh"
@@ -9,20 +10,26 @@
 using namespace diffus;
 
 namespace diffus {
-cudaError_t prepare_kernel(const void* kernel) {
+cudaError_t prepare_kernel(const void* kernel, int carveout_pct) {
     static std::mutex mu;
-    static std::unordered_set<uint64_t> done;        // (kernel, device) pairs whose attributes are set
+    static std::unordered_map<uint64_t, int> done;   // (kernel, device) -> carveout last set
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     const uint64_t key = (uint64_t)(uintptr_t)kernel * 64u + (uint64_t)dev;
     std::lock_guard<std::mutex> lock(mu);
-    if (done.count(key)) return cudaSuccess;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    auto it = done.find(key);
+    if (it != done.end() && it->second == carveout_pct) return cudaSuccess;
+    // carveout_pct < 100: the kernel's resident CTAs need less than the whole 228 KB -- the rest stays L1 / texture cache.
+    // (Only a different launch geometry of the same kernel changes the value: the common case above is one map look-up.)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             carveout_pct >= 100 ? (int)cudaSharedmemCarveoutMaxShared : carveout_pct);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYNAMIC_SMEM);
-    if (e != cudaSuccess) return e;
-    done.insert(key);
+    if (it == done.end()) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYNAMIC_SMEM);
+        if (e != cudaSuccess) return e;
+    }
+    done[key] = carveout_pct;
     return cudaSuccess;
 }
 }  // namespace diffus

@@ -1,5 +1,6 @@
 // Host-side launcher declarations (internal to the shared library).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,11 +55,32 @@ namespace diffus {
 // and the full 227 KB of opt-in dynamic shared memory.  Two host threads launching the same kernel with different
 // sizes can then never lower each other's limit, and the ~2 x 3 us of cudaFuncSetAttribute leave the launch path.
 constexpr size_t MAX_DYNAMIC_SMEM = 227 * 1024;
-cudaError_t prepare_kernel(const void* kernel);
+cudaError_t prepare_kernel(const void* kernel, int carveout_pct = 100);
+// ctas_per_sm > 0: the kernel's launch bounds fix how many CTAs are resident, so only ctas_per_sm x (smem + 1 KB reserved) of
+// shared memory is ever needed; the preferred carveout is set to that (first launch decides) and the remainder of the 256 KB
+// stays L1 / texture cache for the gathers.
 template <typename K>
-static inline cudaError_t ensure_smem(K kernel, size_t smem) {
+static inline cudaError_t ensure_smem(K kernel, size_t smem, int ctas_per_sm = 0) {
     if (smem > MAX_DYNAMIC_SMEM) return cudaErrorInvalidValue;
-    return prepare_kernel((const void*)kernel);
+    int pct = 100;
+    if (ctas_per_sm > 0) {
+        const size_t need = (size_t)ctas_per_sm * (smem + 1024);
+        // ask for the smallest shared-memory configuration of sm_100 that holds `need`.  Measured on B200 (carveout sweep,
+        // profiles/r2_carveout.md): the driver rounds percent x 228 KB UP to the next configuration -- 72..82 % give the
+        // 196 KB one (ncu: launch__shared_mem_config_size 200.7 KB), 86 % already the full 228 KB -- so the request is the
+        // configuration's own size rounded DOWN to a whole percent.
+        const size_t sizes_kb[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+        size_t pick = 228;
+        for (size_t kb : sizes_kb)
+            if (kb * 1024 >= need) { pick = kb; break; }
+        pct = (int)(pick * 100 / 228);
+        if (pct > 100) pct = 100;
+    }
+    if (ctas_per_sm > 0) {                                   // kernel-development override: DIFFUS_CARVEOUT_PCT=<percent>
+        static const int forced = [] { const char* e = getenv("DIFFUS_CARVEOUT_PCT"); return e ? atoi(e) : 0; }();
+        if (forced > 0) pct = forced;
+    }
+    return prepare_kernel((const void*)kernel, pct);
 }
 
 // render_kernels.cu

@@ -71,6 +71,12 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #ifndef DIFFUS_WIDE_VOLGRAD
 #define DIFFUS_WIDE_VOLGRAD 1     // the WIDE sweep for the fused volume-gradient kernels (config 4) too
 #endif
+#ifndef DIFFUS_CARVEOUT
+#define DIFFUS_CARVEOUT 1         // the same for the forward and the other backward kernels (resident warps from their launch bounds)
+#endif
+#ifndef DIFFUS_WIDE_CARVEOUT
+#define DIFFUS_WIDE_CARVEOUT 1    // WIDE kernels: shared-memory carveout sized to their 4 resident CTAs (more L1 / texture cache)
+#endif
 #ifndef DIFFUS_WIDE_CTAS
 #define DIFFUS_WIDE_CTAS 4      // resident 4-warp CTA equivalents per SM of the WIDE kernels (4: 128 registers, 5: 96 and spills)
 #endif
@@ -1002,7 +1008,7 @@ cudaError_t DIFFUS_FWD_NAME(const RenderParams& p, int sampler, int layout, int 
     int wpb = warps_per_block(p.total_rays);
     size_t smem = ((size_t)p.att_slots + (size_t)wpb * FWD_SMEM_PER_WARP) * sizeof(float);
     unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
-    DIFFUS_DISPATCH(auto k = render_fwd_kernel<S_, L_, P64_>; cudaError_t e = ensure_smem(k, smem);
+    DIFFUS_DISPATCH(auto k = render_fwd_kernel<S_, L_, P64_>; cudaError_t e = ensure_smem(k, smem, DIFFUS_CARVEOUT ? 28 / wpb : 0);
                     if (e != cudaSuccess) return e; k<<<grid, wpb * 32, smem, st>>>(p); return cudaGetLastError())
     return cudaErrorInvalidValue;
 }
@@ -1021,14 +1027,14 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
             int wpb_ = threads / 32;                                            \
             if (wpb_ == 4) wpb_ = DIFFUS_WIDE_WPB;                              \
             const size_t smem_ = ((size_t)p.att_slots_padded + (size_t)wpb_ * BWD_SMEM_PER_WARP) * sizeof(float); \
-            cudaError_t e = ensure_smem(k, smem_);                              \
+            cudaError_t e = ensure_smem(k, smem_, DIFFUS_WIDE_CARVEOUT ? DIFFUS_WIDE_CTAS * 4 / wpb_ : 0); \
             if (e != cudaSuccess) return e;                                     \
             k<<<(unsigned)((p.total_rays + wpb_ - 1) / wpb_), wpb_ * 32, smem_, st>>>(p); \
             return cudaGetLastError();                                          \
         }                                                                       \
         if (!P64_ && p.Sout <= PREFIX_STRIDE) {                                 \
             auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true>;      \
-            cudaError_t e = ensure_smem(k, smem);                               \
+            cudaError_t e = ensure_smem(k, smem, DIFFUS_CARVEOUT ? ((VG) ? 16 : 20) / (threads / 32) : 0); \
             if (e != cudaSuccess) return e;                                     \
             k<<<grid, threads, smem, st>>>(p);                                  \
             return cudaGetLastError();                                          \
@@ -1041,7 +1047,7 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
             return cudaGetLastError();                                          \
         }                                                                       \
         auto k = render_bwd_kernel<S_, L_, P64_, PG, VG, LOSS, false>;          \
-        cudaError_t e = ensure_smem(k, smem);                                   \
+        cudaError_t e = ensure_smem(k, smem, DIFFUS_CARVEOUT ? 16 / (threads / 32) : 0); \
         if (e != cudaSuccess) return e;                                         \
         k<<<grid, threads, smem, st>>>(p);                                      \
         return cudaGetLastError();                                              \
