@@ -60,7 +60,7 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #define DIFFUS_H_ROLLED 0    // 1: the sub-segment loop of the reverse sweep is not unrolled (half the sweep code, one more branch)
 #endif
 #ifndef DIFFUS_GATHER_PIPE
-#define DIFFUS_GATHER_PIPE 1   // fused backward, TEXTURE layout: two batches of gathers in flight (software pipeline)
+#define DIFFUS_GATHER_PIPE 0   // 1: fused backward, TEXTURE layout: two batches of gathers in flight (software pipeline)
 #endif
 #ifndef DIFFUS_WIDE_SWEEP
 #define DIFFUS_WIDE_SWEEP 1    // one-pass pose-gradient kernels: single 512-column reverse sweep (see WideGeo)
@@ -83,8 +83,14 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #ifndef DIFFUS_WIDE_WPB
 #define DIFFUS_WIDE_WPB 4       // rays (warps) per CTA of the WIDE kernels on large batches
 #endif
+#ifndef DIFFUS_FWD_GB
+#define DIFFUS_FWD_GB 1      // tiles per gather batch of the forward kernel (trilinear)
+#endif
 #ifndef DIFFUS_TEX_GB
-#define DIFFUS_TEX_GB 1      // tiles of tld4 gathers in flight per warp in the fused backward (TEXTURE layout)
+#define DIFFUS_TEX_GB 2      // tiles of tld4 gathers in flight per warp in the fused backward (TEXTURE layout)
+#endif
+#ifndef DIFFUS_TEX_GB_WIDE
+#define DIFFUS_TEX_GB_WIDE 4 // the same in the WIDE kernels (128 registers; the multi-pass kernel spills 620 bytes with 4: config 5 14.4 -> 15.8 ms)
 #endif
 constexpr int BWD_DZ_STRIDE = FwdGeo::OBUF;   // floats between the per-axis rows of the spatial-gradient buffer
 
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p
         // batches of tiles: every load of a batch is issued before the first one is combined.  One tile per batch for
         // the trilinear sampler: measured, 28 resident warps (7 CTAs at 72 registers) hide the gather latency better than
         // deeper batches at fewer warps (0.460 vs 0.470 ms per 1024 poses)
-        constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : 1;
+        constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : DIFFUS_FWD_GB;
         const int nt_full = (ncol >> 5) / GB * GB;       // batches of complete tiles run without the per-lane bounds tests
         for (int t0 = 0; t0 < nt_full; t0 += GB) {
             Fetch<SAMPLER, LAYOUT> fe[GB];
@@ -665,7 +671,10 @@ render_bwd_kernel(const RenderParams p) {
             // Measured on the one-pass pose kernel (96 registers, 5 CTAs = 20 warps per SM), batches of 1 / 2 / 4 tiles:
             // 0.701 / 0.687 / 0.705 ms per 1024 poses (before the bounds tests left the loop below, two tiles still
             // spilled and one tile per batch was the fastest: 0.753 / 0.779 / 0.785).
-            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : (LAYOUT == DIFFUS_LAYOUT_TEXTURE ? DIFFUS_TEX_GB : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2));
+            // TEXTURE (round 2): with the shared-memory carveout sized to the resident CTAs (60 KB of L1 / texture cache instead of 28)
+            // deeper batches pay again on the WIDE kernel (128 registers): 1 pipelined / 2 / 2 pipelined / 4 / 4 pipelined / 8 tiles:
+            // 0.564 / 0.573 / 0.555 / 0.542 / 0.562 / 0.586 ms (profiles/r2_carveout.md).
+            constexpr int GB = SAMPLER == DIFFUS_SAMPLER_NEAREST ? 8 : (LAYOUT == DIFFUS_LAYOUT_TEXTURE ? (WIDE ? DIFFUS_TEX_GB_WIDE : DIFFUS_TEX_GB) : ((LAYOUT == DIFFUS_LAYOUT_QUAD && ONE_PASS) ? 4 : 2));
             // batches whose tiles are all complete run without the per-lane bounds tests; the tail keeps them
             const int nt_full = (ncol >> 5) / GB * GB;
             auto issue_batch = [&](Fetch<SAMPLER, LAYOUT>(&fe)[GB], int t0) {
