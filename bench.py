@@ -536,11 +536,11 @@ def run_ours(args):
                          "bytes_note": "SURVEY 8(d) counts 72 B/sample for forward+backward done as two passes "
                                        "(2 x (8 gathers x 4 B + 4 B)); the fused kernel gathers once and reads the "
                                        "target once, so its own algorithmic traffic is 36 B/sample.  The volume is L2-resident "
-                                       "by design (DRAM is ~7 % busy, L2 18 %, L1/texture 41 %): no memory roof is near -- the "
-                                       "kernel is latency-bound on its texture gathers at 16 resident warps per SM (issue slots "
-                                       "60 % busy, 5.94 warp instructions per sample), see gather_roof and "
-                                       "profiles/r2_fused_kernel_wide.md",
-                         "binding_unit": "texture-gather latency / issue slots (ncu: long_scoreboard 31 %, issue active 60 %)",
+                                       "by design (DRAM is ~9 % busy, L2 19 %, L1/texture 46 %): no memory roof is near -- the "
+                                       "kernel is bound by its issue slots (68 % busy at 16 resident warps per SM, 5.99 warp "
+                                       "instructions per sample) and the latency of its texture gathers, see gather_roof and "
+                                       "profiles/r2_fused_kernel_final.md",
+                         "binding_unit": "issue slots / texture-gather latency (ncu: issue active 68 %, long_scoreboard 21 %)",
                          "frac_vs_two_pass_bytes": samples_per_step * 72 / (step_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,
             "loss": loss_value,
