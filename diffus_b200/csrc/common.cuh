@@ -271,14 +271,16 @@ __device__ __forceinline__ void tri_axis(float p, int n, int& i0, int& i1, float
     if (COLLAPSE) i1 = (p > 0.f) ? i1 : i0;
 }
 
-// the same for an axis addressed through the texture unit: the tld4 coordinate whose footprint is (fl, fl + 1) is fl + 1,
-// clamp addressing does the top face, and coordinate 0 selects the collapsed cell (0, 0) at the bottom face
+// The same for an axis addressed through the texture unit.  The tld4 coordinate whose footprint is (fl, fl + 1) is fl + 1, and
+// CLAMP ADDRESSING does the rest: no explicit clamp of the coordinate is needed.  Beyond the top face both texels clamp to
+// n - 1, below the bottom face both clamp to 0 -- the two corners are then the same texel, so whatever fraction p - floor(p)
+// says, the value is that texel and the derivative 0.  Only p <= 0 with floor(p) = 0 (p = 0 exactly, where grid_sample's
+// derivative is 0 but the cell (0, 1) has one) needs the collapse: coordinate 0 selects the footprint (-1, 0) = (0, 0).
 template <bool COLLAPSE>
 __device__ __forceinline__ void tri_axis_tex(float p, int n, float& coord, float& f) {
-    float hi = (float)(n - 1);
-    float pc = fminf(fmaxf(p, 0.f), hi);
-    float fl = floorf(pc);
-    f = pc - fl;
+    (void)n;
+    const float fl = floorf(p);
+    f = p - fl;
     coord = fl + 1.0f;
     if (COLLAPSE) coord = (p > 0.f) ? coord : 0.f;
 }
