@@ -50,17 +50,6 @@ __device__ __forceinline__ M2 forward_chunk(const float r[G::CHUNK], M2 carry, f
     return m2_shfl(P, 31);
 }
 
-// 32 bytes of a row that is read twice within one ray and never again (the target frame): one 256-bit load (sm_100),
-// evict-first in L2 so that the stream does not push the volume out
-__device__ __forceinline__ void ldg_stream8(const float* p, float v[8]) {
-    uint32_t r[8];
-    asm volatile("ld.global.nc.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // What the upstream gradient of a column is made of.
 //   LOSS_GRAD : gbuf holds d loss / d frame                               -> ebar = g * att
 //   LOSS_MSE  : gbuf holds the target frame; the kernel forms frame = echo * att,
@@ -85,10 +74,9 @@ constexpr int LOSS_GRAD = 0, LOSS_MSE = 1;
 #ifndef DIFFUS_CARVEOUT
 #define DIFFUS_CARVEOUT 1         // the same for the forward and the other backward kernels (resident warps from their launch bounds)
 #endif
-#ifndef DIFFUS_TARGET_DIRECT
-#define DIFFUS_TARGET_DIRECT 0    // 1: WIDE fused pose kernel reads the target row from global memory in both sweeps instead of staging it in
-                                 // shared memory (4 CTAs then fit the 164 KB carveout, 92 KB of L1).  Measured: bit-identical results, but 452 bytes
-                                 // of spills and the loads inside the sweeps cost far more than the cache buys: 0.763 vs 0.541 ms.
+#ifndef DIFFUS_LANE_MAJOR_TARGET
+#define DIFFUS_LANE_MAJOR_TARGET 0   // 1: WIDE fused pose kernel stages the target / e-bar row lane-major (four 16-byte cp.async per lane,
+                                     // float4 accesses in the sweeps: 132 fewer instructions per ray).  Measured: bit-identical, 0.560 vs 0.536 ms.
 #endif
 #ifndef DIFFUS_WIDE_CARVEOUT
 #define DIFFUS_WIDE_CARVEOUT 1    // WIDE kernels: shared-memory carveout sized to their 4 resident CTAs (more L1 / texture cache)
@@ -137,37 +125,19 @@ struct ZTail {
 //   vin         adjoint flowing into the segment's last column from later segments
 //   ncol_lane   number of existing columns in this lane's chunk (may be <= 0 or > CHUNK)
 // returns the adjoint flowing out of the segment's first column (into the previous segment)
-//   TGT         (LOSS_MSE, no STORE_ZBAR) the target row is NOT staged in shared memory: `tgt_lane` points at this lane's first
-//               column in global memory (32-byte aligned, CHUNK % 8 == 0); the forward loop reads it into registers, the
-//               reverse loop re-reads it (L1 hits) and recomputes e-bar instead of parking it -- gbuf is then not touched at
-//               all, and the ray buffer is one row (2.1 KB per warp) smaller
-template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false, bool FULL = false, bool TGT = false>
+//   LM          (LOSS_MSE, no STORE_ZBAR) `gbuf` is this lane's OWN row of CHUNK floats, 16-byte aligned (lane-major staging of
+//               the target, see render_bwd_kernel): target and e-bar move as float4 -- 12 instead of 48 shared-memory
+//               instructions per lane and ray
+template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false, bool FULL = false, bool LM = false>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
                                              float& loss_acc, int lane, ZTail* zt = nullptr,
-                                             const M2* known_total = nullptr, const M2* known_prefix = nullptr,
-                                             const float* tgt_lane = nullptr) {
+                                             const M2* known_total = nullptr, const M2* known_prefix = nullptr) {
     constexpr int CHUNK = G_::CHUNK;
-    static_assert(!TGT || (LOSS == LOSS_MSE && !STORE_ZBAR && CHUNK % 8 == 0), "TGT: fused MSE without a volume gradient");
-    const int base = G_::pad(lane * CHUNK);        // columns lane*CHUNK .. +CHUNK-1 share a 32-column block
-    // TGT: the lane's target columns arrive in two 256-bit loads -- the first is issued here, before the chunk product and the
-    // scan that hide its latency, the second when the forward loop starts on the first half (all 16 values at once cost
-    // 428 bytes of spills)
-    float tgv[TGT ? 8 : 1], tgw[TGT ? 8 : 1];
-    auto load_half = [&](int q, float (&dst)[TGT ? 8 : 1]) {
-        if (TGT) {
-            float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (FULL || 8 * q + 7 < ncol_lane) ldg_stream8(tgt_lane + 8 * q, t8);
-            else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (8 * q + j < ncol_lane) t8[j] = __ldg(tgt_lane + 8 * q + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[TGT ? j : 0] = t8[j];
-        }
-    };
-    load_half(0, tgv);
+    static_assert(!LM || (LOSS == LOSS_MSE && !STORE_ZBAR && CHUNK % 4 == 0), "LM: fused MSE without a volume gradient");
+    const int base = LM ? 0 : G_::pad(lane * CHUNK);        // columns lane*CHUNK .. +CHUNK-1 share a 32-column block
+    float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = t4;   // LM: four columns of the target / of e-bar at a time
+    auto comp = [](const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; };
     // chunk product and exclusive prefix: reuse them when the caller already ran this sweep (prefix pass)
     M2 T, P;
     if (known_total) {
@@ -195,8 +165,8 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         const float att = att_lane ? att_lane[i] : 1.f;
         if (LOSS == LOSS_MSE) {
             float fr = __fmul_rn(nan_to_num(e), att);
-            if (TGT && CHUNK > 8 && i == 0) load_half(1, tgw);
-            float diff = fr - (TGT ? (i < 8 ? tgv[TGT ? i & 7 : 0] : tgw[TGT ? i & 7 : 0]) : gbuf[base + i]);
+            if (LM && (i & 3) == 0) t4 = *reinterpret_cast<const float4*>(gbuf + i);
+            float diff = fr - (LM ? comp(t4, i & 3) : gbuf[base + i]);
             if (FULL || i < ncol_lane) {
                 loss_acc += diff * diff;
                 if (frame_lane) frame_lane[i] = fr;      // 8 consecutive floats per lane: whole 32-byte sectors
@@ -206,7 +176,12 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
             ge = gbuf[base + i] * att;
         }
         if (!finite || (!FULL && i >= ncol_lane)) ge = 0.f;   // columns that do not exist: the table beyond Sout is not filled
-        if (!TGT) gbuf[base + i] = ge;
+        if (LM) {
+            if ((i & 3) == 0) g4.x = ge; else if ((i & 3) == 1) g4.y = ge; else if ((i & 3) == 2) g4.z = ge; else g4.w = ge;
+            if ((i & 3) == 3) *reinterpret_cast<float4*>(gbuf + i - 3) = g4;
+        } else {
+            gbuf[base + i] = ge;
+        }
         const float2 dcol = make_float2(ge * inv, -ge * e * inv);   // D = [[0, da], [0, db]];  B += D G^T
         B.c0 = __ffma2_rn(dcol, bcast(G.b()), B.c0);
         B.c1 = __ffma2_rn(dcol, bcast(G.d()), B.c1);
@@ -255,17 +230,8 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         const float2 pc1 = __ffma2_rn(Q.c0, bcast(r[i]), Q.c1);      // (b, d) of the prefix through column i
         float inv = fast_rcp(pc1.y);
         float e = echo_of(pc1.x, inv);
-        float ge;
-        if (TGT) {                                     // the forward loop's e-bar again, from the same operations
-            if (CHUNK > 8 && i == CHUNK - 1) load_half(1, tgw);        // (L1 / L2 hits: the forward loop just read them)
-            if (i == 7) load_half(0, tgv);
-            const float att = att_lane ? att_lane[i] : 1.f;
-            const float diff = __fmul_rn(nan_to_num(e), att) - (i < 8 ? tgv[TGT ? i & 7 : 0] : tgw[TGT ? i & 7 : 0]);
-            ge = grad_scale * diff * att;
-            if (!(fabsf(e) <= FLT_MAX) || (!FULL && i >= ncol_lane)) ge = 0.f;
-        } else {
-            ge = gbuf[base + i];
-        }
+        if (LM && (i & 3) == 3) g4 = *reinterpret_cast<const float4*>(gbuf + i - 3);
+        float ge = LM ? comp(g4, i & 3) : gbuf[base + i];
         M2 Pbar = V;
         Pbar.c1 = __fadd2_rn(Pbar.c1, make_float2(ge * inv, -ge * e * inv));
         const float2 t0 = __fmul2_rn(Q.c0, Pbar.c0), t1 = __fmul2_rn(Q.c0, Pbar.c1), t2 = __fmul2_rn(Q.c1, Pbar.c0);
@@ -316,6 +282,12 @@ __device__ __forceinline__ void cp_async_stream4(float* smem_dst, const float* g
 __device__ __forceinline__ int64_t pose_of_ray(int64_t ray, const RenderParams& p) {
     if (p.total_rays <= 0xffffffffLL) return (int64_t)((uint32_t)ray / (uint32_t)p.n_rays);
     return ray / p.n_rays;
+}
+
+__device__ __forceinline__ void cp_async_stream16(float* smem_dst, const float* gmem_src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "l"(policy)
+                 : "memory");
 }
 
 // coefficient of the interface owned by column c from the two impedances around it
@@ -376,7 +348,7 @@ __device__ __forceinline__ void store_prefix(const RenderParams& p, int64_t ray,
 template <int SAMPLER, int LAYOUT, bool POSE64>
 __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p) {
     using G = FwdGeo;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* att = smem;
     fill_attenuation(att, p.Sout, p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -666,23 +638,29 @@ __device__ __forceinline__ void scatter_pass_quads(const RenderParams& p, const 
 // prefix scan and one suffix scan per ray instead of two of each, no prefix pre-pass over the first sub-segment, for 1.5
 // instead of 0.5 recomputed transfer products per column.
 using WideGeo = Geo<16, 4>;
-constexpr int BWD_SMEM_PER_WARP_TGT = BWD_ZBUF + 3 * BWD_DZ;      // TGT: no target / e-bar row
-template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false, bool TGT = false>
+constexpr int BWD_LM_STRIDE = WideGeo::CHUNK + 4;                 // lane-major target / e-bar row: 20 floats per lane (80 B: float4 accesses
+                                                                  // of the eight lanes of a quarter warp fall on distinct banks)
+constexpr int BWD_LM_ROW = 32 * BWD_LM_STRIDE;
+constexpr int BWD_SMEM_PER_WARP_LM = (BWD_LM_ROW + BWD_ZBUF + 3 * BWD_DZ + 3) / 4 * 4;   // the lane-major row comes first: 16-byte aligned
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false, bool LM = false>
 __global__ void __launch_bounds__(WIDE ? 32 * DIFFUS_WIDE_WPB : 128, WIDE ? DIFFUS_WIDE_CTAS * 4 / DIFFUS_WIDE_WPB : ((ONE_PASS && !VOL_GRAD) ? 5 : 4))
 render_bwd_kernel(const RenderParams p) {
     using G = typename std::conditional<WIDE, WideGeo, BwdGeo>::type;
     constexpr int BWD_SUB = PREFIX_STRIDE / G::SEG;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* att = smem;                       // padded like the column buffers: conflict free in the chunk phase
     fill_attenuation_padded<G>(att, p.Sout, p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
-    static_assert(!TGT || (WIDE && ONE_PASS && LOSS == LOSS_MSE && !VOL_GRAD), "TGT: the one-pass fused pose kernels");
-    float* zbuf = smem + p.att_slots_padded + warp * (TGT ? BWD_SMEM_PER_WARP_TGT : BWD_SMEM_PER_WARP);
-    float* gbuf = zbuf + BWD_ZBUF;           // target / upstream gradient in, d loss / d r out (TGT: not there)
-    float* dz = TGT ? gbuf : gbuf + BWD_OBUF;    // [3][BWD_DZ] spatial gradient of Z at each sample (padded rows)
+    static_assert(!LM || (WIDE && ONE_PASS && LOSS == LOSS_MSE && !VOL_GRAD), "LM: the one-pass fused pose kernels");
+    // LM: the target / e-bar row is laid out LANE-major (lane l owns floats [20 l, 20 l + 16)): the chunk phase is its only
+    // reader, so it is staged with four 16-byte cp.async per lane and moved as float4 (132 fewer instructions per ray)
+    float* wbase = smem + p.att_slots_padded + warp * (LM ? BWD_SMEM_PER_WARP_LM : BWD_SMEM_PER_WARP);   // att_slots_padded % 4 == 0
+    float* zbuf = LM ? wbase + BWD_LM_ROW : wbase;
+    float* gbuf = LM ? wbase : zbuf + BWD_ZBUF;    // target / upstream gradient in, d loss / d r out
+    float* dz = LM ? zbuf + BWD_ZBUF : gbuf + BWD_OBUF;    // [3][BWD_DZ] spatial gradient of Z at each sample (padded rows)
     const int64_t pose = pose_of_ray(ray, p);
     RaySetup<POSE64> rs;
     rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
@@ -712,9 +690,21 @@ render_bwd_kernel(const RenderParams p) {
         // memory with cp.async at the top of the pass so its latency hides behind the gathers.
         {
             const int nt = nsub * (G::SEG / 32);
-            if (TGT) {                                   // no staging: pull this lane's 64 bytes of the row towards L2 now
+            if (LM) {
                 const int lc = lane * G::CHUNK;
-                if (lc < ncol) asm volatile("prefetch.global.L2 [%0];" ::"l"(gin + c0 + lc));
+                float* dst = gbuf + lane * BWD_LM_STRIDE;
+                const float* src = gin + c0 + lc;
+                if (lc + G::CHUNK <= ncol && (((uintptr_t)src) & 15u) == 0) {        // the usual case: four 16-byte copies
+#pragma unroll
+                    for (int q = 0; q < G::CHUNK / 4; ++q) cp_async_stream16(dst + 4 * q, src + 4 * q, stream_policy);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < G::CHUNK; ++i) {
+                        if (lc + i < ncol) cp_async_stream4(dst + i, src + i, stream_policy);
+                        else dst[i] = 0.f;                   // columns that do not exist carry no gradient
+                    }
+                }
+                __pipeline_commit();
             } else {
                 for (int t = 0; t < (ncol >> 5); ++t) {      // complete tiles: no bounds test
                     int idx = t * 32 + lane;
@@ -812,7 +802,7 @@ render_bwd_kernel(const RenderParams p) {
                     }
                 }
             }
-            if (!TGT) __pipeline_wait_prior(0);
+            __pipeline_wait_prior(0);
         }
         if (lane == 0) {
             if (s > 0) {                     // left neighbour of the pass's first column
@@ -869,15 +859,15 @@ render_bwd_kernel(const RenderParams p) {
                 M2 ch = carry[0];                        // (a select, not an indexed read: the loop may be rolled)
                 if (BWD_SUB == 2 && h == 1) ch = carry[BWD_SUB - 1];
                 float* fl = fout ? fout + c0 + lane_col : nullptr;
-                const float* tl = TGT ? gin + c0 + lane_col : nullptr;
+                float* gl = LM ? gbuf + lane * BWD_LM_STRIDE : gbuf + G::pad(off);
                 if (full)
-                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true, TGT>(
-                        r, ch, vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
-                        loss_acc, lane, &zt, kt, &E0, tl);
+                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true, LM>(
+                        r, ch, vin, gl, att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
+                        loss_acc, lane, &zt, kt, &E0);
                 else
-                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false, TGT>(
-                        r, ch, vin, gbuf + G::pad(off), att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
-                        loss_acc, lane, &zt, kt, &E0, tl);
+                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false, LM>(
+                        r, ch, vin, gl, att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
+                        loss_acc, lane, &zt, kt, &E0);
                 zt.w_after = zt.w_first;
             }
         }
@@ -925,7 +915,7 @@ render_bwd_kernel(const RenderParams p) {
 __global__ void __launch_bounds__(128) echo_fwd_kernel(const float* __restrict__ refl, int64_t n_rays, int N,
                                                        float* __restrict__ echo) {
     using G = FwdGeo;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= n_rays) return;
@@ -956,7 +946,7 @@ __global__ void __launch_bounds__(128) echo_fwd_kernel(const float* __restrict__
 __global__ void __launch_bounds__(128) echo_bwd_kernel(const float* __restrict__ refl, const float* __restrict__ grad_echo,
                                                        int64_t n_rays, int N, float* __restrict__ grad_refl) {
     using G = BwdGeo;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= n_rays) return;
@@ -1094,14 +1084,13 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
 #define DIFFUS_BWD_GO(PG, VG)                                                   \
     {                                                                           \
         /* the one-pass specialisation exists for float32 poses only (build time) */ \
-        if (DIFFUS_TARGET_DIRECT && DIFFUS_WIDE_SWEEP && !P64_ && TRI && PG && !VG && LOSS == LOSS_MSE &&               \
-            p.Sout <= PREFIX_STRIDE && p.Sout > BwdGeo::SEG && p.Sout % 8 == 0 && ((uintptr_t)p.target & 31u) == 0) {    \
-            /* target row read from global memory in both sweeps: 8.5 instead of 10.6 KB of shared memory per ray */     \
+        if (DIFFUS_LANE_MAJOR_TARGET && DIFFUS_WIDE_SWEEP && !P64_ && TRI && PG && !VG && LOSS == LOSS_MSE &&            \
+            p.Sout <= PREFIX_STRIDE && p.Sout > BwdGeo::SEG) {                  \
             auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, true, true,                                          \
-                                       (DIFFUS_TARGET_DIRECT && DIFFUS_WIDE_SWEEP && TRI && PG && !VG && LOSS == LOSS_MSE)>; \
+                                       (DIFFUS_LANE_MAJOR_TARGET && DIFFUS_WIDE_SWEEP && TRI && PG && !VG && LOSS == LOSS_MSE)>; \
             int wpb_ = threads / 32;                                            \
             if (wpb_ == 4) wpb_ = DIFFUS_WIDE_WPB;                              \
-            const size_t smem_ = ((size_t)p.att_slots_padded + (size_t)wpb_ * BWD_SMEM_PER_WARP_TGT) * sizeof(float); \
+            const size_t smem_ = ((size_t)p.att_slots_padded + (size_t)wpb_ * BWD_SMEM_PER_WARP_LM) * sizeof(float); \
             cudaError_t e = ensure_smem(k, smem_, DIFFUS_WIDE_CTAS * 4 / wpb_); \
             if (e != cudaSuccess) return e;                                     \
             k<<<(unsigned)((p.total_rays + wpb_ - 1) / wpb_), wpb_ * 32, smem_, st>>>(p); \
