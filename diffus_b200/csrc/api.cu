@@ -104,7 +104,10 @@ RenderParams pack(const DiffusRenderArgs* a) {
     p.Sout = a->n_samples - a->start;
     p.nprefix = (p.Sout + PREFIX_STRIDE - 1) / PREFIX_STRIDE - 1;
     p.att_slots = (p.Sout + 3) / 4 * 4;
-    p.att_slots_padded = (p.Sout + p.Sout / 32 + 8) / 4 * 4;
+    {   // the backward's padded table: rays longer than one pass keep one pass's worth (render_bwd_kernel)
+        const int n = p.Sout <= PREFIX_STRIDE ? p.Sout : PREFIX_STRIDE;
+        p.att_slots_padded = (n + n / 32 + 8) / 4 * 4;
+    }
     p.alpha = a->attenuation;
     p.frame = a->frame;
     p.seg_prefix = a->seg_prefix;

@@ -132,7 +132,8 @@ template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool S
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
                                              float& loss_acc, int lane, ZTail* zt = nullptr,
-                                             const M2* known_total = nullptr, const M2* known_prefix = nullptr) {
+                                             const M2* known_total = nullptr, const M2* known_prefix = nullptr,
+                                             const float* att_scale = nullptr) {
     constexpr int CHUNK = G_::CHUNK;
     static_assert(!LM || (LOSS == LOSS_MSE && !STORE_ZBAR && CHUNK % 4 == 0), "LM: fused MSE without a volume gradient");
     const int base = LM ? 0 : G_::pad(lane * CHUNK);        // columns lane*CHUNK .. +CHUNK-1 share a 32-column block
@@ -162,7 +163,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         float e = echo_of(P.b(), inv);
         bool finite = fabsf(e) <= FLT_MAX;             // nan_to_num passes no gradient at NaN/inf
         float ge;
-        const float att = att_lane ? att_lane[i] : 1.f;
+        const float att = att_lane ? (att_scale ? __fmul_rn(att_lane[i], *att_scale) : att_lane[i]) : 1.f;     // (scale: see render_bwd_kernel)
         if (LOSS == LOSS_MSE) {
             float fr = __fmul_rn(nan_to_num(e), att);
             if (LM && (i & 3) == 0) t4 = *reinterpret_cast<const float4*>(gbuf + i);
@@ -650,7 +651,10 @@ render_bwd_kernel(const RenderParams p) {
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
     extern __shared__ __align__(16) float smem[];
     float* att = smem;                       // padded like the column buffers: conflict free in the chunk phase
-    fill_attenuation_padded<G>(att, p.Sout, p.alpha);
+    // Rays longer than one pass keep only the first 512 entries, exp(-alpha i), and multiply by exp(-alpha c0) per pass
+    // (one more rounding, one more multiply per column): the table then costs 2 KB instead of 8 KB at 2048 samples, and four
+    // CTAs fit the 196 KB carveout -- 60 instead of 28 KB of L1 / texture cache for the gathers of config 5.
+    fill_attenuation_padded<G>(att, ONE_PASS ? p.Sout : min(p.Sout, SS), p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
@@ -860,14 +864,16 @@ render_bwd_kernel(const RenderParams p) {
                 if (BWD_SUB == 2 && h == 1) ch = carry[BWD_SUB - 1];
                 float* fl = fout ? fout + c0 + lane_col : nullptr;
                 float* gl = LM ? gbuf + lane * BWD_LM_STRIDE : gbuf + G::pad(off);
+                const float pass_scale = ONE_PASS ? 1.f : expf(-p.alpha * (float)c0);
+                const float* asc = ONE_PASS ? nullptr : &pass_scale;
                 if (full)
                     vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true, LM>(
-                        r, ch, vin, gl, att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
-                        loss_acc, lane, &zt, kt, &E0);
+                        r, ch, vin, gl, att + G::pad(ONE_PASS ? c0 + lane_col : lane_col), fl, p.grad_scale, ncol - lane_col,
+                        loss_acc, lane, &zt, kt, &E0, asc);
                 else
                     vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false, LM>(
-                        r, ch, vin, gl, att + G::pad(c0 + lane_col), fl, p.grad_scale, ncol - lane_col,
-                        loss_acc, lane, &zt, kt, &E0);
+                        r, ch, vin, gl, att + G::pad(ONE_PASS ? c0 + lane_col : lane_col), fl, p.grad_scale, ncol - lane_col,
+                        loss_acc, lane, &zt, kt, &E0, asc);
                 zt.w_after = zt.w_first;
             }
         }
