@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(128, 7) render_fwd_kernel(const RenderParams p
     using G = FwdGeo;
     extern __shared__ __align__(16) float smem[];
     float* att = smem;
-    fill_attenuation(att, p.Sout, p.alpha);
+    if (p.frame) fill_attenuation(att, p.Sout, p.alpha);     // (a prefix-only run forms no frame: no table, att_slots = 0)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (ray >= p.total_rays) return;
@@ -1074,7 +1074,9 @@ static int warps_per_block(int64_t total_rays) {
 #define DIFFUS_FWD_NAME DIFFUS_CAT(launch_render_fwd_layout, DIFFUS_LAYOUT_SLICE)
 #define DIFFUS_BWD_NAME DIFFUS_CAT(launch_render_bwd_layout, DIFFUS_LAYOUT_SLICE)
 
-cudaError_t DIFFUS_FWD_NAME(const RenderParams& p, int sampler, int layout, int pose64, cudaStream_t st) {
+cudaError_t DIFFUS_FWD_NAME(const RenderParams& p_in, int sampler, int layout, int pose64, cudaStream_t st) {
+    RenderParams p = p_in;
+    if (!p.frame) p.att_slots = 0;               // prefix-only run (the fused backward of long rays): no attenuation table
     int wpb = warps_per_block(p.total_rays);
     size_t smem = ((size_t)p.att_slots + (size_t)wpb * FWD_SMEM_PER_WARP) * sizeof(float);
     unsigned grid = (unsigned)((p.total_rays + wpb - 1) / wpb);
