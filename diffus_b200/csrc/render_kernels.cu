@@ -710,9 +710,18 @@ render_bwd_kernel(const RenderParams p) {
                 }
                 __pipeline_commit();
             } else {
-                for (int t = 0; t < (ncol >> 5); ++t) {      // complete tiles: no bounds test
-                    int idx = t * 32 + lane;
-                    cp_async_stream4(gbuf + G::pad(idx), gin + c0 + idx, stream_policy);
+                // complete tiles: no bounds test.  pad(32 t + lane) = 33 t + lane: both addresses advance by a constant per
+                // tile, so the copies are one instruction each with immediate offsets
+                {
+                    float* dst = gbuf + lane;
+                    const float* src = gin + c0 + lane;
+                    const int nfull = ncol >> 5;
+                    if (ONE_PASS && nfull == SS / 32) {
+#pragma unroll
+                        for (int t = 0; t < SS / 32; ++t) cp_async_stream4(dst + 33 * t, src + 32 * t, stream_policy);
+                    } else {
+                        for (int t = 0; t < nfull; ++t) cp_async_stream4(dst + 33 * t, src + 32 * t, stream_policy);
+                    }
                 }
                 for (int t = ncol >> 5; t < nt; ++t) {
                     int idx = t * 32 + lane;
@@ -742,16 +751,19 @@ render_bwd_kernel(const RenderParams p) {
                     fe[u].template issue<POSE_GRAD>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k));
                 }
             };
+            // pad(32 t + lane) = 33 t + lane and pad(32 t + lane + 1) = 33 t + lane + 1 (+ 1 more for lane 31): one base per
+            // batch, immediate offsets per tile
+            const int lane_z = lane + 1 + (lane == 31 ? 1 : 0);
             auto finish_batch = [&](const Fetch<SAMPLER, LAYOUT>(&fe)[GB], int t0) {
+                float* zt0 = zbuf + 33 * t0 + lane_z;
+                float* dt0 = dz + 33 * t0 + lane;
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
-                    int idx = (t0 + u) * 32 + lane;
                     float g[3];
                     float z = fe[u].template finish<POSE_GRAD>(g);
-                    zbuf[G::pad(idx + 1)] = z;
+                    zt0[33 * u] = z;
                     if (POSE_GRAD) {
-                        const int di = G::pad(idx);
-                        dz[di] = g[0]; dz[BWD_DZ + di] = g[1]; dz[2 * BWD_DZ + di] = g[2];
+                        dt0[33 * u] = g[0]; dt0[BWD_DZ + 33 * u] = g[1]; dt0[2 * BWD_DZ + 33 * u] = g[2];
                     }
                 }
             };
