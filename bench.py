@@ -334,13 +334,12 @@ def config5_record(dev, poses, layout):
     peak, _ = load_peaks()
     gs = samples / (ms * 1e-3) / 1e9
     rec = {"what": f"config 5: {n}^3 volume ({layout}), {R} rays x {S} samples, {poses} poses over the sphere, fused fwd+MSE+bwd with pose "
-                   "gradients: prefix-only forward pre-pass + four 512-column backward passes per ray",
+                   "gradients: ONE launch, one CTA per ray walking its four 512-column passes together (one warp each; no forward pre-pass)",
            "poses": poses, "ms_per_step": ms, "gsamples_per_s": gs, "frames_per_s": poses / (ms * 1e-3),
            "ms_for_4096_poses": ms * 4096 / poses, "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,
            "hbm_frac_at_36B": gs * BYTES_PER_SAMPLE_FUSED / peak}
     try:
         hbm = ops.gather_probe(2048, device=dev)
-        # 8 gathers per sample in the backward passes + 8 in the prefix pre-pass over 3 of 4 segments
         rec["hbm_random_sector_roof"] = {"sectors_per_s": hbm["sectors_per_s"], "buffer_mib": 2048}
     except Exception as exc:
         rec["hbm_random_sector_roof"] = {"error": str(exc)}

@@ -69,6 +69,7 @@ SIGNATURES = {
     "diffus_render_workspace_bytes": (_i64, [_P(DiffusRenderArgs)]),
     "diffus_render_forward": (_i32, [_P(DiffusRenderArgs), _vp]),
     "diffus_render_bwd_workspace_bytes": (_i64, [_P(DiffusRenderBwdArgs)]),
+    "diffus_render_bwd_needs_prefix": (_i32, [_P(DiffusRenderBwdArgs)]),
     "diffus_render_backward": (_i32, [_P(DiffusRenderBwdArgs), _vp]),
     "diffus_ray_indices": (_i32, [_P(DiffusRenderArgs), _vp, _vp, _vp, _vp]),
     "diffus_trace_values": (_i32, [_P(DiffusRenderArgs), _vp, _vp]),
@@ -147,3 +148,10 @@ def check(code: int, what: str):
     if code != 0:
         msg = load().diffus_error_string(code).decode()
         raise DiffusError(f"{what} failed with code {code}: {msg}")
+
+
+def check_count(code: int, what: str) -> int:
+    """For entry points that answer with a non-negative number (negative = error code)."""
+    if code < 0:
+        check(code, what)
+    return code

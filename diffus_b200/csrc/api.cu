@@ -219,6 +219,19 @@ int64_t diffus_render_bwd_workspace_bytes(const DiffusRenderBwdArgs* b) {
     return bwd_workspace(b, nullptr).bytes;
 }
 
+int32_t diffus_render_bwd_needs_prefix(const DiffusRenderBwdArgs* b) {
+    if (!b) return DIFFUS_E_NULL;
+    const DiffusRenderArgs* a = &b->fwd;
+    if (a->pose_dtype != DIFFUS_POSE_F32 && a->pose_dtype != DIFFUS_POSE_F64) return DIFFUS_E_ENUM;
+    if (a->sampler != DIFFUS_SAMPLER_NEAREST && a->sampler != DIFFUS_SAMPLER_TRILINEAR) return DIFFUS_E_ENUM;
+    if (a->n_poses < 1 || a->n_rays < 1 || a->n_samples < 2 || a->start < 0 || a->start > a->n_samples - 2) return DIFFUS_E_SHAPE;
+    const int sout = (int)(a->n_samples - a->start);
+    if (sout <= PREFIX_STRIDE) return 0;
+    const bool pose_grad = a->sampler == DIFFUS_SAMPLER_TRILINEAR && (b->grad_sources || b->grad_directions);
+    return render_bwd_is_coop(sout, a->n_poses * a->n_rays, a->sampler, a->pose_dtype == DIFFUS_POSE_F64, pose_grad,
+                              b->grad_volume != nullptr) ? 0 : 1;
+}
+
 int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     if (!b) return DIFFUS_E_NULL;
     const DiffusRenderArgs* a = &b->fwd;
@@ -232,10 +245,11 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
     if (!pose_grad && !vol_grad && !(mse && (b->loss || a->frame))) return DIFFUS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     RenderParams p = pack(a);
-    if (p.nprefix > 0 && !a->seg_prefix) return DIFFUS_E_NULL;
+    const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;
+    const bool coop = render_bwd_is_coop(p.Sout, p.total_rays, a->sampler, pose64, pose_grad, vol_grad);
+    if (p.nprefix > 0 && !coop && !a->seg_prefix) return DIFFUS_E_NULL;
     BwdWorkspace w = bwd_workspace(b, b->workspace);
     if (w.bytes > 0 && (!b->workspace || b->workspace_bytes < w.bytes)) return DIFFUS_E_WORKSPACE;
-    const int pose64 = a->pose_dtype == DIFFUS_POSE_F64;
     cudaError_t ce;
     if (a->start > 0) {
         ce = launch_first_refl_median(p, a->sampler, a->volume.layout, pose64, w.fwd.median, w.fwd.tie_count, st);

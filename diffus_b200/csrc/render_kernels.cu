@@ -111,7 +111,21 @@ struct ZTail {
     float w_after;         // weight w of the column after the segment's last one (later segment / pass), 0 if none
     float w_first;         // out: w of the segment's first column (all lanes)
     float2 acc[3];         // per axis: (d loss / d source, d loss / d direction) partial sums of this lane
+    float* xch;            // COOP: the CTA's exchange area (CoopXch), else unused
 };
+
+// COOP (rays of four passes, one pass per warp of a 4-warp CTA -- see render_bwd_kernel): what the warps of a ray tell each
+// other through shared memory, in floats from the start of the exchange area
+struct CoopXch {
+    static constexpr int TOTAL = 0;      // [4][4] transfer product of each pass
+    static constexpr int MAP_A = 16;     // [4][4] \ the pass's reverse sweep as the affine map
+    static constexpr int MAP_B = 32;     // [4][4] /  V -> V A + B of the adjoint entering it
+    static constexpr int W_FIRST = 48;   // [4]    weight w of each pass's first column
+    static constexpr int OUT = 52;       // [4][8] per-pass partial sums of the pose gradient and the loss
+    static constexpr int FLOATS = 96;
+};
+__device__ __forceinline__ void xch_store(float* x, const M2& m) { x[0] = m.a(); x[1] = m.b(); x[2] = m.c(); x[3] = m.d(); }
+__device__ __forceinline__ M2 xch_load(const float* x) { return m2_make(x[0], x[1], x[2], x[3]); }
 
 // Backward chunk phase for one segment.
 //   r[i]        coefficient of column c0 + lane*CH + i (0 where the column does not exist)
@@ -128,13 +142,19 @@ struct ZTail {
 //   LM          (LOSS_MSE, no STORE_ZBAR) `gbuf` is this lane's OWN row of CHUNK floats, 16-byte aligned (lane-major staging of
 //               the target, see render_bwd_kernel): target and e-bar move as float4 -- 12 instead of 48 shared-memory
 //               instructions per lane and ray
-template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false, bool FULL = false, bool LM = false>
+//   COOP        the segment is one of the four passes of a ray, each walked by one warp of the CTA (ZMODE only): `vin` is
+//               ignored -- the passes exchange their affine maps (and, for the last column's d loss / d Z, the weight of the
+//               next pass's first column) through zt->xch.  Every warp of the CTA must run the SAME instantiation:
+//               the function holds two __syncthreads().
+template <class G_, int LOSS, bool ZMODE = false, bool POSE_GRAD = false, bool STORE_ZBAR = false, bool FULL = false, bool LM = false,
+          bool COOP = false>
 __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2& carry, const M2& vin, float* gbuf,
                                              const float* att_lane, float* frame_lane, float grad_scale, int ncol_lane,
                                              float& loss_acc, int lane, ZTail* zt = nullptr,
                                              const M2* known_total = nullptr, const M2* known_prefix = nullptr,
                                              const float* att_scale = nullptr) {
     constexpr int CHUNK = G_::CHUNK;
+    static_assert(!COOP || ZMODE, "COOP: render kernels only");
     static_assert(!LM || (LOSS == LOSS_MSE && !STORE_ZBAR && CHUNK % 4 == 0), "LM: fused MSE without a volume gradient");
     const int base = LM ? 0 : G_::pad(lane * CHUNK);        // columns lane*CHUNK .. +CHUNK-1 share a 32-column block
     float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = t4;   // LM: four columns of the target / of e-bar at a time
@@ -199,8 +219,20 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     }
     // adjoint entering this lane's last column: maps of lanes lane+1..31 applied to vin
     M2 An = m2_shfl_down(As, 1), Bn = m2_shfl_down(Bs, 1);
-    M2 V = (lane == 31) ? vin : m2_add(m2_mul(vin, An), Bn);
-    M2 vout = m2_add(m2_mul(vin, As), Bs);             // valid on lane 0
+    M2 vin_ = vin;
+    if (COOP) {                                        // lane 0 holds the whole pass's map: publish it, then fold the later passes' maps
+        const int w = threadIdx.x >> 5;
+        if (lane == 0) {
+            xch_store(zt->xch + CoopXch::MAP_A + 4 * w, As);
+            xch_store(zt->xch + CoopXch::MAP_B + 4 * w, Bs);
+        }
+        __syncthreads();
+        vin_ = m2_zero();
+        for (int u = 3; u > w; --u)
+            vin_ = m2_add(m2_mul(vin_, xch_load(zt->xch + CoopXch::MAP_A + 4 * u)), xch_load(zt->xch + CoopXch::MAP_B + 4 * u));
+    }
+    M2 V = (lane == 31) ? vin_ : m2_add(m2_mul(vin_, An), Bn);
+    M2 vout = m2_add(m2_mul(vin_, As), Bs);            // valid on lane 0
     // ZMODE state: impedances of the samples at columns c+1, c (slot s = sample of column s-1) and the last weight
     const float* zl = nullptr;
     const float* dzl = nullptr;
@@ -259,9 +291,16 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
     }
     if (ZMODE) {
         float w_next = __shfl_down_sync(FULL, w_prev, 1);
-        if (lane == 31) w_next = zt->w_after;
-        emit(CHUNK - 1, part_last - w_next * z_after);
         zt->w_first = __shfl_sync(FULL, w_prev, 0);
+        if (COOP) {                                    // the column after this pass's last one belongs to the next warp
+            const int w = threadIdx.x >> 5;
+            if (lane == 0) zt->xch[CoopXch::W_FIRST + w] = zt->w_first;
+            __syncthreads();
+            if (lane == 31) w_next = w < 3 ? zt->xch[CoopXch::W_FIRST + w + 1] : 0.f;
+        } else if (lane == 31) {
+            w_next = zt->w_after;
+        }
+        emit(CHUNK - 1, part_last - w_next * z_after);
     }
     return m2_shfl(vout, 0);
 }
@@ -643,9 +682,19 @@ constexpr int BWD_LM_STRIDE = WideGeo::CHUNK + 4;                 // lane-major 
                                                                   // of the eight lanes of a quarter warp fall on distinct banks)
 constexpr int BWD_LM_ROW = 32 * BWD_LM_STRIDE;
 constexpr int BWD_SMEM_PER_WARP_LM = (BWD_LM_ROW + BWD_ZBUF + 3 * BWD_DZ + 3) / 4 * 4;   // the lane-major row comes first: 16-byte aligned
-template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false, bool LM = false>
-__global__ void __launch_bounds__(WIDE ? 32 * DIFFUS_WIDE_WPB : 128, WIDE ? DIFFUS_WIDE_CTAS * 4 / DIFFUS_WIDE_WPB : ((ONE_PASS && !VOL_GRAD) ? 5 : 4))
+// COOP (rays of 1537..2048 columns = four passes; config 5): ONE ray per 4-warp CTA, warp w walks pass w.  The passes of a ray
+// depend on each other only through (i) the forward prefix entering the pass = the product of the earlier passes' transfer
+// products, (ii) the adjoint entering its last column = the later passes' reverse sweeps, each an affine map V -> V A + B that
+// the pass knows once its own prefix is known, and (iii) the weight of the next pass's first column.  All three go through
+// shared memory (CoopXch, three __syncthreads per ray), so the ray is gathered ONCE: no forward pre-pass for the 512-column
+// prefixes (it re-gathered 3 of 4 passes, ~30 % of the config-5 step), no state carried from pass to pass through the gather
+// loop (the single 512-column WIDE sweep fits 128 registers like the one-pass kernel's).
+template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false, bool LM = false,
+          bool COOP = false>
+__global__ void __launch_bounds__((WIDE && !COOP) ? 32 * DIFFUS_WIDE_WPB : 128,
+                                  COOP ? 4 : WIDE ? DIFFUS_WIDE_CTAS * 4 / DIFFUS_WIDE_WPB : ((ONE_PASS && !VOL_GRAD) ? 5 : 4))
 render_bwd_kernel(const RenderParams p) {
+    static_assert(!COOP || (WIDE && !ONE_PASS && !VOL_GRAD && !LM && !POSE64), "COOP: long rays, WIDE sweep, no volume gradient");
     using G = typename std::conditional<WIDE, WideGeo, BwdGeo>::type;
     constexpr int BWD_SUB = PREFIX_STRIDE / G::SEG;
     constexpr int SS = PREFIX_STRIDE;        // columns gathered per pass (BWD_SUB sub-segments of G::SEG)
@@ -656,8 +705,8 @@ render_bwd_kernel(const RenderParams p) {
     // CTAs fit the 196 KB carveout -- 60 instead of 28 KB of L1 / texture cache for the gathers of config 5.
     fill_attenuation_padded<G>(att, ONE_PASS ? p.Sout : min(p.Sout, SS), p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (ray >= p.total_rays) return;
+    const int64_t ray = COOP ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ray >= p.total_rays) return;         // (COOP: the grid is exactly the rays -- no warp leaves before the barriers)
     static_assert(!LM || (WIDE && ONE_PASS && LOSS == LOSS_MSE && !VOL_GRAD), "LM: the one-pass fused pose kernels");
     // LM: the target / e-bar row is laid out LANE-major (lane l owns floats [20 l, 20 l + 16)): the chunk phase is its only
     // reader, so it is staged with four 16-byte cp.async per lane and moved as float4 (132 fewer instructions per ray)
@@ -681,11 +730,12 @@ render_bwd_kernel(const RenderParams p) {
     zt.zbuf = zbuf;
     zt.dz = dz;
     zt.rbar1 = nullptr;
+    zt.xch = smem + p.att_slots_padded + (blockDim.x >> 5) * BWD_SMEM_PER_WARP;     // (COOP only; the launcher adds the room)
 #pragma unroll
     for (int a = 0; a < 3; ++a) zt.acc[a] = make_float2(0.f, 0.f);
     float loss_acc = 0.f;
 
-    for (int s = nss - 1; s >= 0; --s) {
+    for (int s = COOP ? warp : nss - 1; s >= (COOP ? warp : 0); --s) {
         const int c0 = s * SS;
         const int ncol = min(SS, p.Sout - c0);
         const int ntile = (ncol + 31) >> 5;
@@ -826,22 +876,39 @@ render_bwd_kernel(const RenderParams p) {
                 float g[3];
                 zbuf[G::pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);
             }
-            zbuf[G::pad(ncol + 1)] = carry_z;    // the sample after the pass's last column lives in the later pass
+            if (!COOP) zbuf[G::pad(ncol + 1)] = carry_z;    // the sample after the pass's last column lives in the later pass
         }
         __syncwarp();
 
         // forward prefixes entering each sub-segment (the first one comes from the forward kernel)
         M2 carry[BWD_SUB];
         carry[0] = m2_identity();
-        if (s > 0) {
+        if (!COOP && s > 0) {
             float4 c4 = __ldg((const float4*)(p.seg_prefix + (ray * p.nprefix + (s - 1)) * 4));
             carry[0] = m2_make(c4.x, c4.y, c4.z, c4.w);
         }
         float r[G::CHUNK];
         M2 T0 = m2_identity(), E0 = m2_identity();       // sub-segment 0's chunk products and prefixes, kept for its reverse scan
         static_assert(BWD_SUB <= 2, "the prefix pass keeps one sub-segment's products in registers");
+        static_assert(!COOP || BWD_SUB == 1, "COOP: one sub-segment per pass");
         const bool have0 = BWD_SUB == 2 && nsub > 1;
-        if (BWD_SUB == 1) {
+        // COOP: every pass but the last is complete; the instantiation of the reverse sweep must be the same for the four warps
+        const bool coop_full = COOP && p.Sout == 4 * SS;
+        if (COOP) {
+            if (ncol == SS) chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, 0);
+            else chunk_reflections<G, false>(zbuf, c0, ncol, p.median, med, lane, r, 0);
+#pragma unroll
+            for (int i = 0; i < G::CHUNK; ++i) T0 = m2_mul_interface(T0, r[i]);
+            const M2 el = warp_exclusive_prefix(T0, m2_identity(), lane);          // within the pass
+            const M2 tot = m2_shfl(m2_mul(el, T0), 31);
+            if (lane == 0) xch_store(zt.xch + CoopXch::TOTAL + 4 * warp, tot);
+            __syncthreads();
+            for (int u = 0; u < warp; ++u) carry[0] = m2_mul(carry[0], xch_load(zt.xch + CoopXch::TOTAL + 4 * u));
+            E0 = m2_mul(carry[0], el);
+            // the sample after the pass's last column is the next warp's first one (its gathers are done: same barrier)
+            if (lane == 0) zbuf[G::pad(ncol + 1)] = warp < 3 ? zbuf[BWD_SMEM_PER_WARP + G::pad(1)] : 0.f;
+            __syncwarp();
+        } else if (BWD_SUB == 1) {
         } else if (have0) {                      // sub-segment 0 is complete whenever there is a second one
             chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, 0);
 #pragma unroll
@@ -861,8 +928,9 @@ render_bwd_kernel(const RenderParams p) {
         for (int h = BWD_SUB - 1; h >= 0; --h) {
             if (h < nsub) {
                 const int off = h * G::SEG;
-                const bool full = ncol - off >= G::SEG;          // warp-uniform: every column of this sub-segment exists
-                if (full) chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, off);
+                const bool full = COOP ? coop_full : ncol - off >= G::SEG;   // warp-uniform (COOP: CTA-uniform): every column of this sub-segment exists
+                if (COOP) {                              // r is already there
+                } else if (full) chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, off);
                 else chunk_reflections<G, false>(zbuf, c0, ncol, p.median, med, lane, r, off);
                 const int lane_col = off + lane * G::CHUNK;
                 // columns without a direct impedance dependence: column 0 and the median-replaced column 1
@@ -871,7 +939,7 @@ render_bwd_kernel(const RenderParams p) {
                 zt.lane_col = lane_col;
                 zt.kbase = (float)(p.start + c0 + lane_col);
                 zt.rbar1 = (p.first_rbar && s == 0 && h == 0) ? p.first_rbar + ray : nullptr;
-                const M2* kt = (h == 0 && have0) ? &T0 : nullptr;
+                const M2* kt = (COOP || (h == 0 && have0)) ? &T0 : nullptr;
                 M2 ch = carry[0];                        // (a select, not an indexed read: the loop may be rolled)
                 if (BWD_SUB == 2 && h == 1) ch = carry[BWD_SUB - 1];
                 float* fl = fout ? fout + c0 + lane_col : nullptr;
@@ -879,11 +947,11 @@ render_bwd_kernel(const RenderParams p) {
                 const float pass_scale = ONE_PASS ? 1.f : expf(-p.alpha * (float)c0);
                 const float* asc = ONE_PASS ? nullptr : &pass_scale;
                 if (full)
-                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true, LM>(
+                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, true, LM, COOP>(
                         r, ch, vin, gl, att + G::pad(ONE_PASS ? c0 + lane_col : lane_col), fl, p.grad_scale, ncol - lane_col,
                         loss_acc, lane, &zt, kt, &E0, asc);
                 else
-                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false, LM>(
+                    vin = backward_chunk<G, LOSS, true, POSE_GRAD, VOL_GRAD, false, LM, COOP>(
                         r, ch, vin, gl, att + G::pad(ONE_PASS ? c0 + lane_col : lane_col), fl, p.grad_scale, ncol - lane_col,
                         loss_acc, lane, &zt, kt, &E0, asc);
                 zt.w_after = zt.w_first;
@@ -908,6 +976,27 @@ render_bwd_kernel(const RenderParams p) {
             }
             __syncwarp();
         }
+    }
+    if (COOP) {                                  // the ray's four passes add up in a fixed order: warp 0 writes the ray's partials
+        float* out = zt.xch + CoopXch::OUT + 8 * warp;
+        if (POSE_GRAD) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float ss = warp_sum(zt.acc[a].x), dd = warp_sum(zt.acc[a].y);
+                if (lane == 0) { out[a] = ss; out[3 + a] = dd; }
+            }
+        }
+        const float l = warp_sum(loss_acc);
+        if (lane == 0) out[6] = l;
+        __syncthreads();
+        if (warp == 0 && lane < 7) {
+            const float* o = zt.xch + CoopXch::OUT + lane;
+            const float v = ((o[0] + o[8]) + o[16]) + o[24];
+            if (POSE_GRAD && lane < 3) p.grad_src_partial[ray * 3 + lane] = v;
+            if (POSE_GRAD && lane >= 3 && lane < 6) p.grad_dir[ray * 3 + lane - 3] = v;
+            if (LOSS == LOSS_MSE && lane == 6 && p.loss_partial) p.loss_partial[ray] = v;
+        }
+        return;
     }
     if (POSE_GRAD) {
 #pragma unroll
@@ -1133,6 +1222,14 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
             cudaError_t e = ensure_smem(k, smem, DIFFUS_CARVEOUT ? ((VG) ? 16 : 20) / (threads / 32) : 0); \
             if (e != cudaSuccess) return e;                                     \
             k<<<grid, threads, smem, st>>>(p);                                  \
+            return cudaGetLastError();                                          \
+        }                                                                       \
+        if (render_bwd_is_coop(p.Sout, p.total_rays, S_, P64_, PG, VG)) { /* rays of four passes (config 5): one ray per CTA, no pre-pass */ \
+            auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, false, (TRI && PG && !VG && !P64_), false, (TRI && PG && !VG && !P64_)>; \
+            const size_t smem_ = ((size_t)p.att_slots_padded + 4 * (size_t)BWD_SMEM_PER_WARP + CoopXch::FLOATS) * sizeof(float); \
+            cudaError_t e = ensure_smem(k, smem_, 4);                           \
+            if (e != cudaSuccess) return e;                                     \
+            k<<<(unsigned)p.total_rays, 128, smem_, st>>>(p);                   \
             return cudaGetLastError();                                          \
         }                                                                       \
         if (DIFFUS_WIDE_MULTIPASS && !P64_ && TRI && PG && !VG && p.Sout > PREFIX_STRIDE) { /* long rays (config 5) */ \

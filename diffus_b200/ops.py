@@ -375,8 +375,9 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     """loss = mean((frame - target)^2) with d loss/d volume, d loss/d sources, d loss/d directions.
 
     Returns ``(loss (1,), frame or empty, grad_volume or empty, grad_sources or empty,
-    grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns this is ONE kernel
-    launch (+ two tiny reductions); longer rays first run the forward kernel for the
+    grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns, and for rays of 1537..2048 columns
+    with a pose gradient only (one CTA per ray, one 512-column pass per warp), this is ONE kernel
+    launch (+ two tiny reductions); other long rays first run the forward kernel for the
     512-column segment prefixes.
 
     ``n_total``: number of frame elements of the GLOBAL batch when this call renders one rank's shard of it -- loss and
@@ -395,11 +396,6 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         if tuple(target.shape) != (P, R, sout) or target.dtype != torch.float32 or not target.is_contiguous():
             raise _lib.DiffusError(f"target must be contiguous float32 {(P, R, sout)}")
         need_pose = need_pose and sampler == SAMPLER_TRILINEAR
-        launches = 0
-        prefix = None
-        if _nseg(sout) > 1:
-            _, prefix = render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
-                                        product_f32, True, prefix_only=True)
         n = P * R * sout if n_total is None else int(n_total)
         def empty():                      # outputs of a custom op must not alias each other
             return torch.empty((0,), dtype=torch.float32, device=dev)
@@ -415,10 +411,17 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
             gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else empty()
         gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else empty()
-        b.fwd.frame = _ptr(frame)
-        b.fwd.seg_prefix = _ptr(prefix)
         b.grad_frame = None
         b.grad_volume, b.grad_sources, b.grad_directions = _ptr(gvol), _ptr(gsrc), _ptr(gdir)
+        # rays longer than 512 columns: the 512-column prefixes come from a prefix-only run of the forward kernel -- unless
+        # the library walks the four passes of a ray in one CTA (1537..2048 columns, pose gradient only) and forms them itself
+        prefix = None
+        need_prefix = _lib.check_count(lib.diffus_render_bwd_needs_prefix(C.byref(b)), "diffus_render_bwd_needs_prefix")
+        if need_prefix:
+            _, prefix = render_fwd_impl(volume, bricks, dims, sources, directions, n_samples, start, alpha, sampler,
+                                        product_f32, True, prefix_only=True)
+        b.fwd.frame = _ptr(frame)
+        b.fwd.seg_prefix = _ptr(prefix)
         b.target, b.grad_scale, b.loss_scale, b.loss = target.data_ptr(), 2.0 / n, 1.0 / n, loss.data_ptr()
         wbytes = lib.diffus_render_bwd_workspace_bytes(C.byref(b))
         ws = torch.empty((max(wbytes, 1),), dtype=torch.uint8, device=dev)

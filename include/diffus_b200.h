@@ -105,7 +105,7 @@ typedef struct DiffusRenderBwdArgs {
     DiffusRenderArgs fwd;       /* same inputs as the forward; fwd.frame is only written in the
                                    fused-loss mode below and may be NULL;
                                    fwd.seg_prefix = the buffer the forward filled (required
-                                   when S-start > 512)                                        */
+                                   when diffus_render_bwd_needs_prefix() says so)             */
     const float* grad_frame;    /* (P,R,S-start)                                             */
     float* grad_volume;         /* QUAD and TEXTURE volumes: a BRICK buffer.  Otherwise the
                                    same layout as fwd.volume (LINEAR (D,H,W), or diffus_brick_elems()
@@ -132,6 +132,11 @@ const char* diffus_error_string(int32_t code);
 int64_t diffus_render_workspace_bytes(const DiffusRenderArgs* args);
 int32_t diffus_render_forward(const DiffusRenderArgs* args, void* stream);
 int64_t diffus_render_bwd_workspace_bytes(const DiffusRenderBwdArgs* args);
+/* 1 when diffus_render_backward needs fwd.seg_prefix for these arguments, 0 when it does not (S-start <= 512, or rays of
+ * 1537..2048 columns with a pose gradient and no volume gradient: one CTA walks the four 512-column passes of such a ray
+ * together and forms the prefixes itself -- no forward pre-pass), negative error code for invalid arguments.  Reads only
+ * the shapes, enums and which output pointers are set. */
+int32_t diffus_render_bwd_needs_prefix(const DiffusRenderBwdArgs* args);
 int32_t diffus_render_backward(const DiffusRenderBwdArgs* args, void* stream);
 
 /* Clamped nearest-voxel indices of every ray point: the x, y, z int64 outputs of

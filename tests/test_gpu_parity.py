@@ -306,6 +306,67 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
         assert gsf is None and gdf is None
 
 
+@pytest.mark.parametrize("S,start,prepared,shared", [(2048, 0, None, False), (1537, 0, "texture", False), (1800, 37, "brick", True),
+                                                     (2047, 0, "quad", False), (2053, 5, "texture", True), (1700, 0, None, False)])
+def test_four_pass_rays_one_cta_per_ray_vs_oracle(S, start, prepared, shared):
+    """Rays of 1537..2048 columns with pose gradients only (config 5's shape): one CTA walks the four 512-column passes of a
+    ray together (no forward pre-pass for the prefixes).  Fused MSE step and the autograd backward against the fp64 oracle
+    (frame, loss, d/dsources, d/ddirections), and against the multi-pass kernel that the same call takes when the volume
+    gradient is wanted too."""
+    from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
+    from diffus_b200.phantoms import layered_phantom
+    n, P, R = 36, 3, 5
+    vol = layered_phantom(n, seed=7)
+    g = torch.Generator().manual_seed(S + start)
+    sources = torch.tensor([[3.0, 2.0, 4.0], [n * 0.5, n * 0.3, 1.5], [n - 3.5, n * 0.6, n - 4.0]])
+    aim = torch.tensor([n * 0.5, n * 0.5, n * 0.5]) - sources
+    d = aim[:, None, :] / aim.norm(dim=-1)[:, None, None] + 0.25 * torch.randn((P, R, 3), generator=g)
+    dirs = d / d.norm(dim=-1, keepdim=True) * 0.017           # sub-voxel steps: 2048 samples cross the whole 36^3 volume
+    if shared:
+        dirs = dirs[0]
+    alpha = 7e-4
+    with torch.no_grad():
+        target = render_frames(vol.to(dev()), sources.to(dev()) + 0.6, dirs.to(dev()), S, alpha, start, sampler="trilinear")
+    tgt64 = target.cpu().double()
+
+    def oracle(v_, s_, d_):
+        f_ = _oracle_frames(v_, s_, d_, S, alpha, start, "trilinear")
+        l_ = (f_ - tgt64.to(f_.dtype)).square().mean()
+        return l_, (l_, f_)
+    want, noise, (l64, f64) = oracle_grads(oracle, vol, sources, dirs)
+
+    def run(fused, with_volume):
+        v = vol.to(dev()).requires_grad_(with_volume)
+        s = sources.to(dev()).requires_grad_(True)
+        dd = dirs.to(dev()).requires_grad_(True)
+        vv = PreparedVolume(v, prepared) if prepared else v
+        if fused:
+            loss, frame = render_mse_loss(vv, s, dd, target, S, alpha, start, sampler="trilinear", return_frame=True)
+        else:
+            frame = render_frames(vv, s, dd, S, alpha, start, sampler="trilinear")
+            loss = torch.nn.functional.mse_loss(frame, target)
+        loss.backward()
+        return loss.detach(), frame.detach(), s.grad, dd.grad
+
+    what = f"S={S} start={start} {prepared} shared={shared}"
+    ref = run(True, True)                                   # pose + volume gradient: the multi-pass kernel
+    for fused in (True, False):
+        lf, ff, gs, gd = run(fused, False)                  # pose gradient only: one CTA per ray
+        tag = f"{what} {'fused' if fused else 'autograd'}"
+        assert_frame_close(ff.cpu().numpy(), f64.detach().numpy(), tag + " frame")
+        np.testing.assert_allclose(lf.item(), l64.item(), rtol=1e-4)
+        assert_grad_close(gs.cpu().numpy(), want[1].numpy(), tag + " d/dsources", noise=noise[1])
+        assert_grad_close(gd.cpu().numpy(), want[2].numpy(), tag + " d/ddirections", noise=noise[2])
+        # the two kernels differ only in the association order of the pass prefixes / adjoints
+        torch.testing.assert_close(ff, ref[1], rtol=1e-5, atol=2e-6 * float(ff.abs().max()))
+        np.testing.assert_allclose(lf.item(), ref[0].item(), rtol=1e-5)
+        scale = float(ref[2].abs().max())
+        torch.testing.assert_close(gs, ref[2], rtol=1e-3, atol=1e-4 * scale)
+    # run to run identical (fixed-order sums across the four passes of a ray)
+    a, b = run(True, False), run(True, False)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 @pytest.mark.parametrize("dims,R,S,start", [((1, 1, 1), 2, 2, 0), ((2, 3, 1), 3, 5, 3), ((5, 4, 7), 2, 33, 0),
                                              ((9, 9, 9), 37, 31, 29), ((6, 5, 4), 4, 513, 1), ((7, 3, 5), 3, 1025, 512)])
 @pytest.mark.parametrize("sampler", ["nearest", "trilinear"])
