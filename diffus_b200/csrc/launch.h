@@ -83,12 +83,12 @@ static inline cudaError_t ensure_smem(K kernel, size_t smem, int ctas_per_sm = 0
     return prepare_kernel((const void*)kernel, pct);
 }
 
-// Rays of four 512-column passes (1537..2048 columns) with a pose gradient and no volume gradient go through the COOP form of
-// render_bwd_kernel (one ray per CTA, one pass per warp): it needs no forward pre-pass for the 512-column prefixes, so
+// Rays of two to four 512-column passes (513..2048 columns) with a pose gradient and no volume gradient go through the COOP form
+// of render_bwd_kernel (one ray per CTA, one pass per warp): it needs no forward pre-pass for the 512-column prefixes, so
 // DiffusRenderArgs.seg_prefix may be NULL for them.  DIFFUS_COOP=0 (kernel development) switches back to the multi-pass kernel.
 inline bool render_bwd_is_coop(int Sout, int64_t total_rays, int sampler, bool pose64, bool pose_grad, bool vol_grad) {
     static const bool enabled = [] { const char* e = getenv("DIFFUS_COOP"); return !e || atoi(e) != 0; }();
-    return enabled && sampler == DIFFUS_SAMPLER_TRILINEAR && !pose64 && pose_grad && !vol_grad && Sout > 3 * PREFIX_STRIDE &&
+    return enabled && sampler == DIFFUS_SAMPLER_TRILINEAR && !pose64 && pose_grad && !vol_grad && Sout > PREFIX_STRIDE &&
            Sout <= 4 * PREFIX_STRIDE && total_rays <= 0x7fffffffLL;      // (one CTA per ray)
 }
 

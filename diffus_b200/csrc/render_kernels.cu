@@ -114,7 +114,7 @@ struct ZTail {
     float* xch;            // COOP: the CTA's exchange area (CoopXch), else unused
 };
 
-// COOP (rays of four passes, one pass per warp of a 4-warp CTA -- see render_bwd_kernel): what the warps of a ray tell each
+// COOP (rays of two to four passes, one pass per warp of the CTA -- see render_bwd_kernel): what the warps of a ray tell each
 // other through shared memory, in floats from the start of the exchange area
 struct CoopXch {
     static constexpr int TOTAL = 0;      // [4][4] transfer product of each pass
@@ -142,7 +142,7 @@ __device__ __forceinline__ M2 xch_load(const float* x) { return m2_make(x[0], x[
 //   LM          (LOSS_MSE, no STORE_ZBAR) `gbuf` is this lane's OWN row of CHUNK floats, 16-byte aligned (lane-major staging of
 //               the target, see render_bwd_kernel): target and e-bar move as float4 -- 12 instead of 48 shared-memory
 //               instructions per lane and ray
-//   COOP        the segment is one of the four passes of a ray, each walked by one warp of the CTA (ZMODE only): `vin` is
+//   COOP        the segment is one of the passes of a ray, each walked by one warp of the CTA (ZMODE only): `vin` is
 //               ignored -- the passes exchange their affine maps (and, for the last column's d loss / d Z, the weight of the
 //               next pass's first column) through zt->xch.  Every warp of the CTA must run the SAME instantiation:
 //               the function holds two __syncthreads().
@@ -228,7 +228,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
         }
         __syncthreads();
         vin_ = m2_zero();
-        for (int u = 3; u > w; --u)
+        for (int u = (int)(blockDim.x >> 5) - 1; u > w; --u)
             vin_ = m2_add(m2_mul(vin_, xch_load(zt->xch + CoopXch::MAP_A + 4 * u)), xch_load(zt->xch + CoopXch::MAP_B + 4 * u));
     }
     M2 V = (lane == 31) ? vin_ : m2_add(m2_mul(vin_, An), Bn);
@@ -296,7 +296,7 @@ __device__ __forceinline__ M2 backward_chunk(const float r[G_::CHUNK], const M2&
             const int w = threadIdx.x >> 5;
             if (lane == 0) zt->xch[CoopXch::W_FIRST + w] = zt->w_first;
             __syncthreads();
-            if (lane == 31) w_next = w < 3 ? zt->xch[CoopXch::W_FIRST + w + 1] : 0.f;
+            if (lane == 31) w_next = w + 1 < (int)(blockDim.x >> 5) ? zt->xch[CoopXch::W_FIRST + w + 1] : 0.f;
         } else if (lane == 31) {
             w_next = zt->w_after;
         }
@@ -682,7 +682,8 @@ constexpr int BWD_LM_STRIDE = WideGeo::CHUNK + 4;                 // lane-major 
                                                                   // of the eight lanes of a quarter warp fall on distinct banks)
 constexpr int BWD_LM_ROW = 32 * BWD_LM_STRIDE;
 constexpr int BWD_SMEM_PER_WARP_LM = (BWD_LM_ROW + BWD_ZBUF + 3 * BWD_DZ + 3) / 4 * 4;   // the lane-major row comes first: 16-byte aligned
-// COOP (rays of 1537..2048 columns = four passes; config 5): ONE ray per 4-warp CTA, warp w walks pass w.  The passes of a ray
+// COOP (rays of 513..2048 columns = two to four passes; config 5 has four): ONE ray per CTA of as many warps as the ray has
+// passes, warp w walks pass w.  The passes of a ray
 // depend on each other only through (i) the forward prefix entering the pass = the product of the earlier passes' transfer
 // products, (ii) the adjoint entering its last column = the later passes' reverse sweeps, each an affine map V -> V A + B that
 // the pass knows once its own prefix is known, and (iii) the weight of the next pass's first column.  All three go through
@@ -892,8 +893,8 @@ render_bwd_kernel(const RenderParams p) {
         static_assert(BWD_SUB <= 2, "the prefix pass keeps one sub-segment's products in registers");
         static_assert(!COOP || BWD_SUB == 1, "COOP: one sub-segment per pass");
         const bool have0 = BWD_SUB == 2 && nsub > 1;
-        // COOP: every pass but the last is complete; the instantiation of the reverse sweep must be the same for the four warps
-        const bool coop_full = COOP && p.Sout == 4 * SS;
+        // COOP: every pass but the last is complete; the instantiation of the reverse sweep must be the same for all the warps
+        const bool coop_full = COOP && p.Sout == (int)(blockDim.x >> 5) * SS;
         if (COOP) {
             if (ncol == SS) chunk_reflections<G, true>(zbuf, c0, ncol, p.median, med, lane, r, 0);
             else chunk_reflections<G, false>(zbuf, c0, ncol, p.median, med, lane, r, 0);
@@ -906,7 +907,7 @@ render_bwd_kernel(const RenderParams p) {
             for (int u = 0; u < warp; ++u) carry[0] = m2_mul(carry[0], xch_load(zt.xch + CoopXch::TOTAL + 4 * u));
             E0 = m2_mul(carry[0], el);
             // the sample after the pass's last column is the next warp's first one (its gathers are done: same barrier)
-            if (lane == 0) zbuf[G::pad(ncol + 1)] = warp < 3 ? zbuf[BWD_SMEM_PER_WARP + G::pad(1)] : 0.f;
+            if (lane == 0) zbuf[G::pad(ncol + 1)] = warp + 1 < (int)(blockDim.x >> 5) ? zbuf[BWD_SMEM_PER_WARP + G::pad(1)] : 0.f;
             __syncwarp();
         } else if (BWD_SUB == 1) {
         } else if (have0) {                      // sub-segment 0 is complete whenever there is a second one
@@ -977,7 +978,7 @@ render_bwd_kernel(const RenderParams p) {
             __syncwarp();
         }
     }
-    if (COOP) {                                  // the ray's four passes add up in a fixed order: warp 0 writes the ray's partials
+    if (COOP) {                                  // the ray's passes add up in a fixed order: warp 0 writes the ray's partials
         float* out = zt.xch + CoopXch::OUT + 8 * warp;
         if (POSE_GRAD) {
 #pragma unroll
@@ -991,7 +992,8 @@ render_bwd_kernel(const RenderParams p) {
         __syncthreads();
         if (warp == 0 && lane < 7) {
             const float* o = zt.xch + CoopXch::OUT + lane;
-            const float v = ((o[0] + o[8]) + o[16]) + o[24];
+            float v = o[0];
+            for (int u = 1; u < (int)(blockDim.x >> 5); ++u) v += o[8 * u];
             if (POSE_GRAD && lane < 3) p.grad_src_partial[ray * 3 + lane] = v;
             if (POSE_GRAD && lane >= 3 && lane < 6) p.grad_dir[ray * 3 + lane - 3] = v;
             if (LOSS == LOSS_MSE && lane == 6 && p.loss_partial) p.loss_partial[ray] = v;
@@ -1224,12 +1226,13 @@ static cudaError_t launch_bwd_g(const RenderParams& p, bool pg, bool vg, unsigne
             k<<<grid, threads, smem, st>>>(p);                                  \
             return cudaGetLastError();                                          \
         }                                                                       \
-        if (render_bwd_is_coop(p.Sout, p.total_rays, S_, P64_, PG, VG)) { /* rays of four passes (config 5): one ray per CTA, no pre-pass */ \
+        if (render_bwd_is_coop(p.Sout, p.total_rays, S_, P64_, PG, VG)) { /* rays of 2..4 passes (config 5: 4): one ray per CTA, no pre-pass */ \
             auto k = render_bwd_kernel<S_, L_, false, PG, VG, LOSS, false, (TRI && PG && !VG && !P64_), false, (TRI && PG && !VG && !P64_)>; \
-            const size_t smem_ = ((size_t)p.att_slots_padded + 4 * (size_t)BWD_SMEM_PER_WARP + CoopXch::FLOATS) * sizeof(float); \
-            cudaError_t e = ensure_smem(k, smem_, 4);                           \
+            const int nw_ = (p.Sout + PREFIX_STRIDE - 1) / PREFIX_STRIDE;       /* 2, 3 or 4 warps: 8, 5 or 4 CTAs per SM */ \
+            const size_t smem_ = ((size_t)p.att_slots_padded + (size_t)nw_ * BWD_SMEM_PER_WARP + CoopXch::FLOATS) * sizeof(float); \
+            cudaError_t e = ensure_smem(k, smem_, 16 / nw_);                    \
             if (e != cudaSuccess) return e;                                     \
-            k<<<(unsigned)p.total_rays, 128, smem_, st>>>(p);                   \
+            k<<<(unsigned)p.total_rays, nw_ * 32, smem_, st>>>(p);              \
             return cudaGetLastError();                                          \
         }                                                                       \
         if (DIFFUS_WIDE_MULTIPASS && !P64_ && TRI && PG && !VG && p.Sout > PREFIX_STRIDE) { /* long rays (config 5) */ \

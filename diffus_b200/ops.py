@@ -375,7 +375,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     """loss = mean((frame - target)^2) with d loss/d volume, d loss/d sources, d loss/d directions.
 
     Returns ``(loss (1,), frame or empty, grad_volume or empty, grad_sources or empty,
-    grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns, and for rays of 1537..2048 columns
+    grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns, and for rays of 513..2048 columns
     with a pose gradient only (one CTA per ray, one 512-column pass per warp), this is ONE kernel
     launch (+ two tiny reductions); other long rays first run the forward kernel for the
     512-column segment prefixes.
@@ -414,7 +414,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
         b.grad_frame = None
         b.grad_volume, b.grad_sources, b.grad_directions = _ptr(gvol), _ptr(gsrc), _ptr(gdir)
         # rays longer than 512 columns: the 512-column prefixes come from a prefix-only run of the forward kernel -- unless
-        # the library walks the four passes of a ray in one CTA (1537..2048 columns, pose gradient only) and forms them itself
+        # the library walks the passes of a ray in one CTA (513..2048 columns, pose gradient only) and forms them itself
         prefix = None
         need_prefix = _lib.check_count(lib.diffus_render_bwd_needs_prefix(C.byref(b)), "diffus_render_bwd_needs_prefix")
         if need_prefix:

@@ -133,8 +133,8 @@ int64_t diffus_render_workspace_bytes(const DiffusRenderArgs* args);
 int32_t diffus_render_forward(const DiffusRenderArgs* args, void* stream);
 int64_t diffus_render_bwd_workspace_bytes(const DiffusRenderBwdArgs* args);
 /* 1 when diffus_render_backward needs fwd.seg_prefix for these arguments, 0 when it does not (S-start <= 512, or rays of
- * 1537..2048 columns with a pose gradient and no volume gradient: one CTA walks the four 512-column passes of such a ray
- * together and forms the prefixes itself -- no forward pre-pass), negative error code for invalid arguments.  Reads only
+ * 513..2048 columns with a pose gradient and no volume gradient: one CTA walks the two to four 512-column passes of such a
+ * ray together, one warp each, and forms the prefixes itself -- no forward pre-pass), negative error code for invalid arguments.  Reads only
  * the shapes, enums and which output pointers are set. */
 int32_t diffus_render_bwd_needs_prefix(const DiffusRenderBwdArgs* args);
 int32_t diffus_render_backward(const DiffusRenderBwdArgs* args, void* stream);

@@ -80,6 +80,28 @@ def test_argument_validation_without_a_device(lib):
     assert lib.diffus_render_forward(C.byref(a), None) == -5           # > 2^31 voxels: 32-bit offsets
     b = DiffusRenderBwdArgs()
     assert lib.diffus_render_backward(C.byref(b), None) == -1
+    # which backward calls want the forward's 512-column prefixes (a pure function of shapes / enums / requested outputs)
+    assert lib.diffus_render_bwd_needs_prefix(None) == -1
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == -2                     # no shape yet
+    b.fwd.n_poses, b.fwd.n_rays, b.fwd.n_samples, b.fwd.sampler = 2, 8, 512, 1
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 0                      # one pass
+    b.fwd.n_samples = 2048
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 1                      # no gradient output named yet: multi-pass form
+    b.grad_sources = 0x1000
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 0                      # pose gradient only: one CTA per ray
+    b.fwd.n_samples, b.fwd.start = 600, 37
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 0                      # 563 columns: two passes, two warps
+    b.fwd.n_samples, b.fwd.start = 2049, 0
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 1                      # five passes
+    b.fwd.n_samples = 2048
+    b.grad_volume = 0x1000
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 1                      # with the volume gradient
+    b.grad_volume, b.fwd.pose_dtype = None, 1
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 1                      # float64 poses
+    b.fwd.pose_dtype, b.fwd.sampler = 0, 0
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == 1                      # nearest sampler: no pose gradient
+    b.fwd.sampler = 9
+    assert lib.diffus_render_bwd_needs_prefix(C.byref(b)) == -3
     assert lib.diffus_echo_forward(None, 1, 1, None, None) == -1
     assert lib.diffus_echo_forward(0x1000, 0, 4, 0x1000, None) == -2
     assert lib.diffus_mlp_forward(None, None, None, 4, 1.0, 0.0, None, None) == -1

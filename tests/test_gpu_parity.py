@@ -307,10 +307,12 @@ def test_fused_mse_step_matches_oracle_and_unfused(sampler, S, start, prepared):
 
 
 @pytest.mark.parametrize("S,start,prepared,shared", [(2048, 0, None, False), (1537, 0, "texture", False), (1800, 37, "brick", True),
-                                                     (2047, 0, "quad", False), (2053, 5, "texture", True), (1700, 0, None, False)])
-def test_four_pass_rays_one_cta_per_ray_vs_oracle(S, start, prepared, shared):
-    """Rays of 1537..2048 columns with pose gradients only (config 5's shape): one CTA walks the four 512-column passes of a
-    ray together (no forward pre-pass for the prefixes).  Fused MSE step and the autograd backward against the fp64 oracle
+                                                     (2047, 0, "quad", False), (2053, 5, "texture", True), (1700, 0, None, False),
+                                                     (513, 0, "texture", False), (1024, 0, None, True), (1100, 37, "brick", False),
+                                                     (1536, 0, "quad", False), (1025, 1, "texture", False)])
+def test_multi_pass_rays_one_cta_per_ray_vs_oracle(S, start, prepared, shared):
+    """Rays of 513..2048 columns with pose gradients only (config 5's shape: 2048): one CTA walks the two to four 512-column
+    passes of a ray together, one warp each (no forward pre-pass for the prefixes).  Fused MSE step and the autograd backward against the fp64 oracle
     (frame, loss, d/dsources, d/ddirections), and against the multi-pass kernel that the same call takes when the volume
     gradient is wanted too."""
     from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
