@@ -767,7 +767,7 @@ render_bwd_kernel(const RenderParams p) {
                     float* dst = gbuf + lane;
                     const float* src = gin + c0 + lane;
                     const int nfull = ncol >> 5;
-                    if (ONE_PASS && nfull == SS / 32) {
+                    if ((ONE_PASS || COOP) && nfull == SS / 32) {
 #pragma unroll
                         for (int t = 0; t < SS / 32; ++t) cp_async_stream4(dst + 33 * t, src + 32 * t, stream_policy);
                     } else {

@@ -83,13 +83,16 @@ class GraphedFanPoseStep:
         self.out = torch.zeros((9 * P + 1,), dtype=torch.float32, device=dev)
         start_i = _resolve_start(start, num_samples)
 
+        # every result is written straight into its slice of the static output block: the graph is five kernels (fans, fused
+        # step, two reductions, fan backward) with no copy kernels behind them
+        o_gs, o_gm, o_gh, o_loss = self.out[:3 * P], self.out[3 * P:6 * P], self.out[6 * P:9 * P], self.out[9 * P:]
+
         def step():
             dirs = ops.fan_directions_fwd(self.median, self.hint, opening_angle, n_rays)
-            loss, _, _, gs, gd = ops.render_mse_impl(vol, bricks, list(vol.shape), self.sources, dirs, tgt, int(num_samples),
-                                                     start_i, float(attenuation_coeff), SAMPLER_TRILINEAR, False, False, True,
-                                                     False)
-            gm, gh = ops.fan_directions_bwd(self.median, self.hint, gd, opening_angle, n_rays)
-            return loss, gs, gm, gh
+            _, _, _, _, gd = ops.render_mse_impl(vol, bricks, list(vol.shape), self.sources, dirs, tgt, int(num_samples),
+                                                 start_i, float(attenuation_coeff), SAMPLER_TRILINEAR, False, False, True,
+                                                 False, loss_out=o_loss, grad_sources_out=o_gs)
+            ops.fan_directions_bwd(self.median, self.hint, gd, opening_angle, n_rays, grad_median_out=o_gm, grad_hint_out=o_gh)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -99,11 +102,7 @@ class GraphedFanPoseStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            loss, gs, gm, gh = step()
-            self.out[:3 * P].copy_(gs.reshape(-1))
-            self.out[3 * P:6 * P].copy_(gm.reshape(-1))
-            self.out[6 * P:9 * P].copy_(gh.reshape(-1))
-            self.out[9 * P:].copy_(loss)
+            step()
         self.P = P
         self.loss = self.out[9 * P]
         self.grad_sources = self.out[:3 * P].view(P, 3)

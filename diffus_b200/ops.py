@@ -370,7 +370,8 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
                directions: torch.Tensor, target: torch.Tensor, n_samples: int, start: int, alpha: float,
                sampler: int, product_f32: bool, need_volume: bool, need_pose: bool,
                want_frame: bool, keep_brick_grad: bool = False, n_total: Optional[int] = None,
-               grad_volume_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None
+               grad_volume_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
+               grad_sources_out: Optional[torch.Tensor] = None
                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     """loss = mean((frame - target)^2) with d loss/d volume, d loss/d sources, d loss/d directions.
 
@@ -383,7 +384,8 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     ``n_total``: number of frame elements of the GLOBAL batch when this call renders one rank's shard of it -- loss and
     gradients are then this shard's share of the global mean, so that a SUM all-reduce over ranks gives exactly the
     single-process result even for ragged shards.  ``grad_volume_out`` (a zero-filled buffer in the gradient layout) and
-    ``loss_out`` (1 float) let a training loop hand in persistent buffers instead of fresh allocations.
+    ``loss_out`` (1 float) let a training loop hand in persistent buffers instead of fresh allocations; ``grad_sources_out``
+    (3P floats) likewise for d loss / d sources (a slice of a CUDA graph's static output block).
     """
     dev = _require_cuda(volume, bricks, sources, directions, target)
     _check_inputs(volume, bricks, dims, sources, directions)
@@ -409,7 +411,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
             gvol = grad_volume_out
         else:
             gvol = torch.zeros(gshape, dtype=torch.float32, device=dev) if need_volume else empty()
-        gsrc = torch.empty((P, 3), dtype=torch.float32, device=dev) if need_pose else empty()
+        gsrc = _out_buffer(grad_sources_out, (P, 3), dev, "grad_sources_out") if need_pose else empty()
         gdir = torch.empty((P, R, 3), dtype=torch.float32, device=dev) if need_pose else empty()
         b.grad_frame = None
         b.grad_volume, b.grad_sources, b.grad_directions = _ptr(gvol), _ptr(gsrc), _ptr(gdir)
@@ -684,16 +686,30 @@ def fan_directions_fwd(median: torch.Tensor, hint: torch.Tensor, opening_angle: 
     return out
 
 
+def _out_buffer(out: Optional[torch.Tensor], shape, dev, what: str) -> torch.Tensor:
+    """A caller-provided contiguous float32 output of the right size (e.g. a slice of a static block inside a CUDA graph), or a
+    fresh tensor."""
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=dev)
+    n = 1
+    for d in shape:
+        n *= d
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n or out.device != dev:
+        raise _lib.DiffusError(f"{what} must be a contiguous float32 CUDA tensor of {n} elements on {dev}")
+    return out
+
+
 def fan_directions_bwd(median: torch.Tensor, hint: torch.Tensor, grad_dirs: torch.Tensor, opening_angle: float,
-                       n_rays: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                       n_rays: int, grad_median_out: Optional[torch.Tensor] = None,
+                       grad_hint_out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     dev = _require_cuda(median, hint, grad_dirs)
     lib = _lib.load()
     m, h = median.detach().float().contiguous(), hint.detach().float().contiguous()
     g = grad_dirs.float().contiguous()
     P = m.shape[0]
     with _on_device(dev):
-        gm = torch.empty((P, 3), dtype=torch.float32, device=dev)
-        gh = torch.empty((P, 3), dtype=torch.float32, device=dev)
+        gm = _out_buffer(grad_median_out, (P, 3), dev, "grad_median_out")
+        gh = _out_buffer(grad_hint_out, (P, 3), dev, "grad_hint_out")
         _lib.check(lib.diffus_fan_directions_backward(m.data_ptr(), h.data_ptr(), g.data_ptr(), P, n_rays, float(opening_angle),
                                                       gm.data_ptr(), gh.data_ptr(), _stream(dev)),
                    "diffus_fan_directions_backward")
