@@ -525,6 +525,10 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
 // a straight ray the samples that touch a given quad are consecutive, and a quad can only ever live in its own slot.  A
 // slot is therefore flushed -- ONE red.v4 -- exactly when the ray has left its quad: 1.4 vector reductions per sample
 // instead of 4.2 scalar ones (5.6 atomics), with no shared-memory atomics, no tags in memory and no divergent control flow.
+// Measured and rejected (benchmarks/gpu/r2_call45.sh): six per-axis key components instead of eight slot keys, every slot
+// re-keyed at every sample and flushed inside a branch when one of its components changed -- fewer instructions on paper
+// (no slot-key sums, no "touched" flags), but a slot misses in some lane of the warp at almost every sample, so the branch
+// bodies run nearly always: config 4 step 5.78 vs 5.10 ms (5.65 with two samples per trip).
 // ---------------------------------------------------------------------------------------
 #ifndef DIFFUS_SCATTER_BRANCHY
 #define DIFFUS_SCATTER_BRANCHY 0   // slot miss handled in one branch region (flush + re-key + zero) instead of per-component selects
