@@ -528,7 +528,7 @@ def run_ours(args):
                             "The explicit-direction forms (--e2e graph / eager, the reference's plot_beam_frame signature) move "
                             "1.57 MB each way per step, ~0.12 ms of PCIe that the 36 KB pose-parameter form does not pay"},
             "gpu_launches": launches,
-            "kernels_ms": {"fused_step(render_bwd_kernel+reduce_rays+reduce_sum)": step_ms},
+            "kernels_ms": {"fused_step(render_bwd_kernel+reduce_rays_and_sum)": step_ms},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(P, args.layout), "peak_source": peak_src,
                          "bytes_per_sample": BYTES_PER_SAMPLE_FUSED,

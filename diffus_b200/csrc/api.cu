@@ -271,6 +271,11 @@ int32_t diffus_render_backward(const DiffusRenderBwdArgs* b, void* stream) {
         ce = launch_median_backward(p, a->sampler, a->volume.layout, pose64, w.fwd.tie_count, pose_grad, vol_grad, st);
         if (ce != cudaSuccess) return (int32_t)ce;
     }
+    if (pose_grad && b->grad_sources && w.loss_partial && reduce_rays_and_sum_fits(a->n_poses * a->n_rays)) {
+        // the fused pose step: both reductions in one launch
+        return cuda_rc(launch_reduce_rays_and_sum(w.src_partial, a->n_poses, a->n_rays, b->grad_sources, w.loss_partial,
+                                                  a->n_poses * a->n_rays, b->loss_scale, b->loss, st));
+    }
     if (pose_grad && b->grad_sources) {
         ce = launch_reduce_rays(w.src_partial, a->n_poses, a->n_rays, b->grad_sources, st);
         if (ce != cudaSuccess) return (int32_t)ce;

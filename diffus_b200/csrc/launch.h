@@ -107,6 +107,9 @@ DIFFUS_DECLARE_SLICE(2)
 DIFFUS_DECLARE_SLICE(3)
 int64_t reduce_sum_workspace_bytes();
 cudaError_t launch_reduce_sum(const float* partial, int64_t n, float scale, float* out, void* workspace, cudaStream_t st);
+bool reduce_rays_and_sum_fits(int64_t n);
+cudaError_t launch_reduce_rays_and_sum(const float* src_partial, int64_t n_poses, int64_t n_rays, float* grad_src,
+                                       const float* loss_partial, int64_t n, float scale, float* loss_out, cudaStream_t st);
 cudaError_t launch_echo_fwd(const float* refl, int64_t n_rays, int N, float* echo, cudaStream_t st);
 cudaError_t launch_echo_bwd(const float* refl, const float* grad_echo, int64_t n_rays, int N, float* grad_refl,
                             cudaStream_t st);

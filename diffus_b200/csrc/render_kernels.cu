@@ -1149,6 +1149,51 @@ __global__ void reduce_final_kernel(const double* __restrict__ block_sums, int n
     }
 }
 
+// The two reductions behind the fused pose step in ONE launch (one launch gap less per step: what a 128-pose shard of a strong-
+// scaled sweep, or a single pose-recovery step, notices): the last CTA sums the per-ray loss partials (the job of
+// reduce_sum_kernel<<<1, 1024>>>), every other CTA sums the per-ray d loss / d source partials of 32 poses exactly like
+// reduce_rays_kernel (one warp per pose: same operations in the same order, bit-identical).  The loss is summed in double in a
+// fixed order of its own (vector loads, four chains per thread): run-to-run identical, equal to reduce_sum_kernel's to the last
+// bit or two of the float32 result.
+__global__ void __launch_bounds__(1024) reduce_rays_and_sum_kernel(const float* __restrict__ src_partial, int64_t n_poses, int64_t n_rays,
+                                                                   float* __restrict__ grad_src, const float* __restrict__ loss_partial,
+                                                                   int64_t n, float scale, float* __restrict__ loss_out) {
+    __shared__ double warp_part[32];
+    if (blockIdx.x == gridDim.x - 1) {
+        // four independent chains of 16-byte loads per thread: the sum of 2^17 partials is latency, not bandwidth
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int64_t n4 = ((((uintptr_t)loss_partial) & 15u) == 0) ? n >> 2 : 0;
+        const float4* lp4 = (const float4*)loss_partial;
+#pragma unroll 4
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = __ldg(lp4 + i);
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+        }
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) a0 += (double)__ldg(loss_partial + i);
+        const double acc = (a0 + a1) + (a2 + a3);
+        const double t = block_sum_fixed_order(acc, warp_part);
+        if (threadIdx.x == 0) loss_out[0] = (float)(t * (double)scale);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pose = (int64_t)blockIdx.x * 32 + warp;
+    if (pose >= n_poses) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const float* src = src_partial + pose * n_rays * 3;
+    for (int64_t r = lane; r < n_rays; r += 32) { a0 += src[r * 3]; a1 += src[r * 3 + 1]; a2 += src[r * 3 + 2]; }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { grad_src[pose * 3] = a0; grad_src[pose * 3 + 1] = a1; grad_src[pose * 3 + 2] = a2; }
+}
+
+bool reduce_rays_and_sum_fits(int64_t n) { return n <= ((int64_t)1 << 18); }      // (the single-CTA form of the loss sum)
+
+cudaError_t launch_reduce_rays_and_sum(const float* src_partial, int64_t n_poses, int64_t n_rays, float* grad_src,
+                                       const float* loss_partial, int64_t n, float scale, float* loss_out, cudaStream_t st) {
+    const unsigned grid = (unsigned)((n_poses + 31) / 32) + 1u;
+    reduce_rays_and_sum_kernel<<<grid, 1024, 0, st>>>(src_partial, n_poses, n_rays, grad_src, loss_partial, n, scale, loss_out);
+    return cudaGetLastError();
+}
+
 constexpr int REDUCE_BLOCKS = 64;
 int64_t reduce_sum_workspace_bytes() { return REDUCE_BLOCKS * sizeof(double); }
 
