@@ -241,7 +241,34 @@ __global__ void __launch_bounds__(PWL_THREADS) mlp_pwl_fwd_kernel(const float* _
     const int nsearch = S.nsearch;
     const bool vec = ((((uintptr_t)x) | ((uintptr_t)out)) & 15u) == 0 && (!mask || (((uintptr_t)mask) & 3u) == 0);
     const int64_t n4 = vec ? n >> 2 : 0;
-    for (int64_t i = gtid; i < n4; i += gstride) {
+    // four 16-byte loads in flight per thread (one per trip left the stream at 1.1 TB/s: a DRAM round trip per 16 bytes per thread)
+    constexpr int PF = 4;
+    int64_t i0 = gtid;
+    for (; i0 + (PF - 1) * gstride < n4; i0 += PF * gstride) {
+        float4 xv[PF];
+        uchar4 mv[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            xv[u] = __ldg((const float4*)x + i0 + u * gstride);
+            if (mask) mv[u] = __ldg((const uchar4*)mask + i0 + u * gstride);
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            float4 o;
+            o.x = out_scale * pwl_eval(S, nsearch, xv[u].x);
+            o.y = out_scale * pwl_eval(S, nsearch, xv[u].y);
+            o.z = out_scale * pwl_eval(S, nsearch, xv[u].z);
+            o.w = out_scale * pwl_eval(S, nsearch, xv[u].w);
+            if (mask) {
+                if (!mv[u].x) o.x = fill;
+                if (!mv[u].y) o.y = fill;
+                if (!mv[u].z) o.z = fill;
+                if (!mv[u].w) o.w = fill;
+            }
+            ((float4*)out)[i0 + u * gstride] = o;
+        }
+    }
+    for (int64_t i = i0; i < n4; i += gstride) {
         const float4 xv = __ldg((const float4*)x + i);
         float4 o;
         o.x = out_scale * pwl_eval(S, nsearch, xv.x);
@@ -363,9 +390,11 @@ __global__ void __launch_bounds__(PWL_THREADS) mlp_pwl_bwd_kernel(const float* _
     const bool vec = ((((uintptr_t)x) | ((uintptr_t)grad_out)) & 15u) == 0 && (!mask || (((uintptr_t)mask) & 3u) == 0);
     const int64_t n4 = vec ? n >> 2 : 0;
     const int64_t wstride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n4; base += wstride) {      // warp-uniform trip count
-        const int64_t i = base + lane;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+    // the loads of the next trip are issued before this trip's voxels are binned (the binning is a chain of warp votes and
+    // reductions: with one trip in flight the stream ran at 0.75 TB/s)
+    auto fetch = [&](int64_t i, float4& xv, float4& gv) {
+        xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        gv = xv;
         if (i < n4) {
             xv = __ldg((const float4*)x + i);
             gv = __ldg((const float4*)grad_out + i);
@@ -377,6 +406,12 @@ __global__ void __launch_bounds__(PWL_THREADS) mlp_pwl_bwd_kernel(const float* _
                 if (!m.w) gv.w = 0.f;
             }
         }
+    };
+    float4 xn, gn;
+    fetch((int64_t)blockIdx.x * blockDim.x + warp * 32 + lane, xn, gn);
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n4; base += wstride) {      // warp-uniform trip count
+        const float4 xv = xn, gv = gn;
+        fetch(base + wstride + lane, xn, gn);
         if (!__any_sync(FULL, gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f)) continue;      // voxels no ray touched
         const int r[4] = {pwl_region(S.bpf, nsearch, xv.x), pwl_region(S.bpf, nsearch, xv.y), pwl_region(S.bpf, nsearch, xv.z),
                           pwl_region(S.bpf, nsearch, xv.w)};

@@ -1127,13 +1127,27 @@ __device__ __forceinline__ double block_sum_fixed_order(double acc, double* warp
     return t;                                 // valid on thread 0
 }
 
+// this thread's share of the sum of n floats, in double: four independent chains of 16-byte loads when the array is 16-byte
+// aligned (a single chain of scalar loads made the sum of 2^17 loss partials a 10 us latency chain in one CTA)
+__device__ __forceinline__ double sum_partials(const float* __restrict__ x, int64_t n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int64_t n4 = ((((uintptr_t)x) & 15u) == 0) ? n >> 2 : 0;
+    const float4* x4 = (const float4*)x;
+#pragma unroll 4
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const float4 v = __ldg(x4 + i);
+        a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+    }
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) a0 += (double)__ldg(x + i);
+    return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ partial, int64_t n, float scale,
                                                           float* __restrict__ out, double* __restrict__ block_sums) {
     __shared__ double warp_part[32];
-    double acc = 0.0;
-    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)__ldg(partial + i);
+    const int64_t per = ((n + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;      // a multiple of 4: every block starts 16-byte aligned
+    const int64_t lo = min(n, (int64_t)blockIdx.x * per), hi = min(n, lo + per);
+    const double acc = sum_partials(partial + lo, hi - lo);
     const double t = block_sum_fixed_order(acc, warp_part);
     if (threadIdx.x == 0) {
         if (block_sums) block_sums[blockIdx.x] = t;
@@ -1152,26 +1166,14 @@ __global__ void reduce_final_kernel(const double* __restrict__ block_sums, int n
 // The two reductions behind the fused pose step in ONE launch (one launch gap less per step: what a 128-pose shard of a strong-
 // scaled sweep, or a single pose-recovery step, notices): the last CTA sums the per-ray loss partials (the job of
 // reduce_sum_kernel<<<1, 1024>>>), every other CTA sums the per-ray d loss / d source partials of 32 poses exactly like
-// reduce_rays_kernel (one warp per pose: same operations in the same order, bit-identical).  The loss is summed in double in a
-// fixed order of its own (vector loads, four chains per thread): run-to-run identical, equal to reduce_sum_kernel's to the last
-// bit or two of the float32 result.
+// reduce_rays_kernel (one warp per pose: same operations in the same order, bit-identical).  The loss is summed in double in the
+// fixed order of sum_partials, like reduce_sum_kernel<<<1, 1024>>>: run-to-run identical.
 __global__ void __launch_bounds__(1024) reduce_rays_and_sum_kernel(const float* __restrict__ src_partial, int64_t n_poses, int64_t n_rays,
                                                                    float* __restrict__ grad_src, const float* __restrict__ loss_partial,
                                                                    int64_t n, float scale, float* __restrict__ loss_out) {
     __shared__ double warp_part[32];
     if (blockIdx.x == gridDim.x - 1) {
-        // four independent chains of 16-byte loads per thread: the sum of 2^17 partials is latency, not bandwidth
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const int64_t n4 = ((((uintptr_t)loss_partial) & 15u) == 0) ? n >> 2 : 0;
-        const float4* lp4 = (const float4*)loss_partial;
-#pragma unroll 4
-        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-            const float4 v = __ldg(lp4 + i);
-            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
-        }
-        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) a0 += (double)__ldg(loss_partial + i);
-        const double acc = (a0 + a1) + (a2 + a3);
-        const double t = block_sum_fixed_order(acc, warp_part);
+        const double t = block_sum_fixed_order(sum_partials(loss_partial, n), warp_part);
         if (threadIdx.x == 0) loss_out[0] = (float)(t * (double)scale);
         return;
     }
