@@ -315,6 +315,19 @@ def test_multi_pass_rays_one_cta_per_ray_vs_oracle(S, start, prepared, shared):
     passes of a ray together, one warp each (no forward pre-pass for the prefixes).  Fused MSE step and the autograd backward against the fp64 oracle
     (frame, loss, d/dsources, d/ddirections), and against the multi-pass kernel that the same call takes when the volume
     gradient is wanted too."""
+    _pose_only_step_vs_oracle_and_volume_grad_kernel(S, start, prepared, shared, step=0.017)
+
+
+@pytest.mark.parametrize("S,start,prepared,shared", [(512, 0, "texture", False), (512, 0, None, True), (129, 0, "brick", False),
+                                                     (256, 0, "quad", False), (257, 1, "texture", False), (300, 37, None, False),
+                                                     (385, 0, "texture", True), (540, 40, "brick", False), (128, 0, "texture", False)])
+def test_one_pass_rays_pose_gradients_only_vs_oracle(S, start, prepared, shared):
+    """Rays of at most 512 columns with pose gradients only (config 2 / 3's kernels: the one-pass forms, the single 512-column
+    sweep above 256 columns), every layout, own and shared fans, start crops: the same checks as for the multi-pass rays."""
+    _pose_only_step_vs_oracle_and_volume_grad_kernel(S, start, prepared, shared, step=0.07)
+
+
+def _pose_only_step_vs_oracle_and_volume_grad_kernel(S, start, prepared, shared, step):
     from diffus_b200 import PreparedVolume, render_frames, render_mse_loss
     from diffus_b200.phantoms import layered_phantom
     n, P, R = 36, 3, 5
@@ -323,7 +336,7 @@ def test_multi_pass_rays_one_cta_per_ray_vs_oracle(S, start, prepared, shared):
     sources = torch.tensor([[3.0, 2.0, 4.0], [n * 0.5, n * 0.3, 1.5], [n - 3.5, n * 0.6, n - 4.0]])
     aim = torch.tensor([n * 0.5, n * 0.5, n * 0.5]) - sources
     d = aim[:, None, :] / aim.norm(dim=-1)[:, None, None] + 0.25 * torch.randn((P, R, 3), generator=g)
-    dirs = d / d.norm(dim=-1, keepdim=True) * 0.017           # sub-voxel steps: 2048 samples cross the whole 36^3 volume
+    dirs = d / d.norm(dim=-1, keepdim=True) * step            # sub-voxel steps: the samples cross the whole 36^3 volume
     if shared:
         dirs = dirs[0]
     alpha = 7e-4
