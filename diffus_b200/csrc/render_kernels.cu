@@ -533,6 +533,15 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
 #ifndef DIFFUS_SCATTER_BRANCHY
 #define DIFFUS_SCATTER_BRANCHY 0   // slot miss handled in one branch region (flush + re-key + zero) instead of per-component selects
 #endif
+#ifndef DIFFUS_COOP_NEIGHBOUR_SMEM
+#define DIFFUS_COOP_NEIGHBOUR_SMEM 1   // COOP: the sample before a pass comes from the previous warp's buffer (one more barrier) instead of
+                                       // one more dependent single-lane gather per pass: config 5 9.64 -> 9.42 ms (benchmarks/gpu/r2_call57.sh)
+#endif
+#ifndef DIFFUS_SCATTER_UNROLL
+#define DIFFUS_SCATTER_UNROLL 1    // samples per trip of the trilinear quad-slot loop (2: config 4 step 5.26 vs 5.04 ms, benchmarks/gpu/r2_call56.sh)
+#endif
+#define DIFFUS_PRAGMA_(x) _Pragma(#x)
+#define DIFFUS_PRAGMA_UNROLL(n) DIFFUS_PRAGMA_(unroll n)
 #ifndef DIFFUS_SCATTER_QUADS
 #define DIFFUS_SCATTER_QUADS 1
 #endif
@@ -628,7 +637,7 @@ __device__ __forceinline__ void scatter_pass_quads(const RenderParams& p, const 
     float4 acc[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) { K[s] = QUAD_NONE; acc[s] = make_float4(0.f, 0.f, 0.f, 0.f); }
-#pragma unroll 1
+    DIFFUS_PRAGMA_UNROLL(DIFFUS_SCATTER_UNROLL)
     for (int i = 0; i < SCATTER_RUN; ++i) {
         const int c = col0 + i;
         const float zbar = c < ncol ? gbuf[G::pad(c)] : 0.f;
@@ -691,7 +700,7 @@ constexpr int BWD_SMEM_PER_WARP_LM = (BWD_LM_ROW + BWD_ZBUF + 3 * BWD_DZ + 3) / 
 // depend on each other only through (i) the forward prefix entering the pass = the product of the earlier passes' transfer
 // products, (ii) the adjoint entering its last column = the later passes' reverse sweeps, each an affine map V -> V A + B that
 // the pass knows once its own prefix is known, and (iii) the weight of the next pass's first column.  All three go through
-// shared memory (CoopXch, three __syncthreads per ray), so the ray is gathered ONCE: no forward pre-pass for the 512-column
+// shared memory (CoopXch; five __syncthreads per ray in all), so the ray is gathered ONCE: no forward pre-pass for the 512-column
 // prefixes (it re-gathered 3 of 4 passes, ~30 % of the config-5 step), no state carried from pass to pass through the gather
 // loop (the single 512-column WIDE sweep fits 128 registers like the one-pass kernel's).
 template <int SAMPLER, int LAYOUT, bool POSE64, bool POSE_GRAD, bool VOL_GRAD, int LOSS, bool ONE_PASS, bool WIDE = false, bool LM = false,
@@ -875,8 +884,14 @@ render_bwd_kernel(const RenderParams p) {
             }
             __pipeline_wait_prior(0);
         }
+        if (COOP && DIFFUS_COOP_NEIGHBOUR_SMEM) {
+            // the sample before the pass's first column is the previous warp's last one: one more barrier instead of one more
+            // (dependent, single-lane) gather per pass
+            __syncthreads();
+            if (lane == 0 && warp > 0) zbuf[G::pad(0)] = zbuf[G::pad(SS) - BWD_SMEM_PER_WARP];
+        }
         if (lane == 0) {
-            if (s > 0) {                     // left neighbour of the pass's first column
+            if (s > 0 && !(COOP && DIFFUS_COOP_NEIGHBOUR_SMEM)) {                     // left neighbour of the pass's first column
                 int k = p.start + c0 - 1;
                 float g[3];
                 zbuf[G::pad(0)] = sample_volume<SAMPLER, LAYOUT, false>(p.vol, rs.coord(0, k), rs.coord(1, k), rs.coord(2, k), g);

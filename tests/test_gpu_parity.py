@@ -166,6 +166,44 @@ def test_gradient_of_a_ray_with_a_zero_over_zero_interface_is_finite():
     assert_grad_close(g[:2].numpy(), clean.grad.numpy(), "rays without a singular interface")
 
 
+@pytest.mark.parametrize("S,step", [(400, 0.09), (1100, 0.033), (2048, 0.017)])
+def test_render_gradient_of_rays_through_a_zero_impedance_block_is_finite(S, step):
+    """The same rule inside the fused render kernels (one-pass, and one CTA per ray for the multi-pass rays, whose warps hand
+    each other prefixes and adjoint maps that are NaN from the singular interface on): a ray that crosses a block of exactly
+    zero impedance (0 / 0 interfaces) renders zeros from there on and contributes a ZERO pose gradient; every other ray is
+    bit-identical to the same render without the block."""
+    from diffus_b200 import render_frames, render_mse_loss
+    from diffus_b200.phantoms import layered_phantom
+    n, P, R = 36, 2, 12
+    clean = layered_phantom(n, seed=11)
+    holed = clean.clone()
+    holed[15:21, 15:21, 15:21] = 0.0
+    g = torch.Generator().manual_seed(S)
+    sources = torch.tensor([[2.0, 3.0, 2.5], [n - 3.0, 4.0, n * 0.5]])
+    aim = torch.tensor([n * 0.5, n * 0.5, n * 0.5]) - sources
+    d = aim[:, None, :] / aim.norm(dim=-1)[:, None, None] + 0.45 * torch.randn((P, R, 3), generator=g)
+    dirs = d / d.norm(dim=-1, keepdim=True) * step
+    out = {}
+    for name, vol in (("clean", clean), ("holed", holed)):
+        v = vol.to(dev())
+        with torch.no_grad():
+            target = render_frames(clean.to(dev()), sources.to(dev()) + 0.4, dirs.to(dev()), S, 8e-4, sampler="trilinear")
+        s_ = sources.to(dev()).requires_grad_(True)
+        d_ = dirs.to(dev()).requires_grad_(True)
+        loss, frame = render_mse_loss(v, s_, d_, target, S, 8e-4, 0, sampler="trilinear", return_frame=True)
+        loss.backward()
+        out[name] = (frame.detach().cpu(), d_.grad.cpu(), s_.grad.cpu(), float(loss.detach()))
+    fc, gc, _, _ = out["clean"]
+    fh, gh, sh, lh = out["holed"]
+    assert torch.isfinite(fh).all() and torch.isfinite(gh).all() and torch.isfinite(sh).all() and np.isfinite(lh)
+    untouched = (fc == fh).all(dim=-1)                    # rays whose trilinear cells never reach the block
+    singular = (fh[..., -1] == 0) & ~untouched            # rays that went through exact zeros: NaN rule, zeros to the end
+    assert untouched.any() and singular.any(), (untouched.sum().item(), singular.sum().item())
+    assert torch.equal(gh[untouched], gc[untouched])
+    assert (gh[singular] == 0).all()
+    assert (fh[singular][:, -8:] == 0).all()
+
+
 def test_echo_traces_golden(golden_echo):
     from diffus_b200 import compute_echo_traces, propagate_full_rays_batched
     g = golden_echo
