@@ -533,6 +533,12 @@ __device__ __forceinline__ void scatter_volume_grad(const RenderParams& p, const
 #ifndef DIFFUS_SCATTER_BRANCHY
 #define DIFFUS_SCATTER_BRANCHY 0   // slot miss handled in one branch region (flush + re-key + zero) instead of per-component selects
 #endif
+#ifndef DIFFUS_EARLY_POSE_LOAD
+#define DIFFUS_EARLY_POSE_LOAD 1   // backward kernels: the ray's pose is loaded before the attenuation table is filled (A/B switch)
+#endif
+#ifndef DIFFUS_WARP_SUM8
+#define DIFFUS_WARP_SUM8 1     // pose-gradient kernels: the ray's seven final sums in one transposing warp reduction (A/B switch)
+#endif
 #ifndef DIFFUS_COOP_NEIGHBOUR_SMEM
 #define DIFFUS_COOP_NEIGHBOUR_SMEM 1   // COOP: the sample before a pass comes from the previous warp's buffer (one more barrier) instead of
                                        // one more dependent single-lane gather per pass: config 5 9.64 -> 9.42 ms (benchmarks/gpu/r2_call57.sh)
@@ -717,10 +723,24 @@ render_bwd_kernel(const RenderParams p) {
     // Rays longer than one pass keep only the first 512 entries, exp(-alpha i), and multiply by exp(-alpha c0) per pass
     // (one more rounding, one more multiply per column): the table then costs 2 KB instead of 8 KB at 2048 samples, and four
     // CTAs fit the 196 KB carveout -- 60 instead of 28 KB of L1 / texture cache for the gathers of config 5.
-    fill_attenuation_padded<G>(att, ONE_PASS ? p.Sout : min(p.Sout, SS), p.alpha);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ray = COOP ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    if (ray >= p.total_rays) return;         // (COOP: the grid is exactly the rays -- no warp leaves before the barriers)
+    const bool live = ray < p.total_rays;
+    // the ray's pose is loaded BEFORE the attenuation table is filled: the loads fly while the table is computed (a CTA's
+    // serial start -- table, barrier, pose loads, first gathers -- is time during which its slot on the SM does no work)
+    const int64_t pose = live ? pose_of_ray(ray, p) : 0;
+    RaySetup<POSE64> rs;
+    float med = 0.f;
+    if (DIFFUS_EARLY_POSE_LOAD && live) {
+        rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
+        if (p.median) med = __ldg(p.median + pose);
+    }
+    fill_attenuation_padded<G>(att, ONE_PASS ? p.Sout : min(p.Sout, SS), p.alpha);
+    if (!live) return;                       // (COOP: the grid is exactly the rays -- no warp leaves before the barriers)
+    if (!DIFFUS_EARLY_POSE_LOAD) {
+        rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
+        if (p.median) med = __ldg(p.median + pose);
+    }
     static_assert(!LM || (WIDE && ONE_PASS && LOSS == LOSS_MSE && !VOL_GRAD), "LM: the one-pass fused pose kernels");
     // LM: the target / e-bar row is laid out LANE-major (lane l owns floats [20 l, 20 l + 16)): the chunk phase is its only
     // reader, so it is staged with four 16-byte cp.async per lane and moved as float4 (132 fewer instructions per ray)
@@ -728,10 +748,6 @@ render_bwd_kernel(const RenderParams p) {
     float* zbuf = LM ? wbase + BWD_LM_ROW : wbase;
     float* gbuf = LM ? wbase : zbuf + BWD_ZBUF;    // target / upstream gradient in, d loss / d r out
     float* dz = LM ? zbuf + BWD_ZBUF : gbuf + BWD_OBUF;    // [3][BWD_DZ] spatial gradient of Z at each sample (padded rows)
-    const int64_t pose = pose_of_ray(ray, p);
-    RaySetup<POSE64> rs;
-    rs.load(p.sources, p.directions, pose, ray - pose * p.n_rays, p.n_rays, p.dir_pose_stride, p.product_f32);
-    const float med = p.median ? __ldg(p.median + pose) : 0.f;
     const float* gin = (LOSS == LOSS_MSE ? p.target : p.grad_frame) + ray * (int64_t)p.Sout;
     float* fout = (LOSS == LOSS_MSE && p.frame) ? p.frame + ray * (int64_t)p.Sout : nullptr;
     if (lane == 0) zbuf[0] = 0.f;
@@ -999,15 +1015,11 @@ render_bwd_kernel(const RenderParams p) {
     }
     if (COOP) {                                  // the ray's passes add up in a fixed order: warp 0 writes the ray's partials
         float* out = zt.xch + CoopXch::OUT + 8 * warp;
-        if (POSE_GRAD) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                float ss = warp_sum(zt.acc[a].x), dd = warp_sum(zt.acc[a].y);
-                if (lane == 0) { out[a] = ss; out[3 + a] = dd; }
-            }
+        {                                        // (COOP kernels are pose-gradient kernels) the pass's seven sums, transposed
+            float v[8] = {zt.acc[0].x, zt.acc[1].x, zt.acc[2].x, zt.acc[0].y, zt.acc[1].y, zt.acc[2].y, loss_acc, 0.f};
+            const float t = warp_sum8(v, lane);
+            if (lane < 8) out[warp_sum8_index(lane)] = t;
         }
-        const float l = warp_sum(loss_acc);
-        if (lane == 0) out[6] = l;
         __syncthreads();
         if (warp == 0 && lane < 7) {
             const float* o = zt.xch + CoopXch::OUT + lane;
@@ -1019,6 +1031,19 @@ render_bwd_kernel(const RenderParams p) {
         }
         return;
     }
+#if DIFFUS_WARP_SUM8
+    if (POSE_GRAD) {              // the ray's seven sums (3 + 3 + loss) in one transposing reduction: 9 shuffles instead of 35
+        float v[8] = {zt.acc[0].x, zt.acc[1].x, zt.acc[2].x, zt.acc[0].y, zt.acc[1].y, zt.acc[2].y, loss_acc, 0.f};
+        const float t = warp_sum8(v, lane);
+        const int j = warp_sum8_index(lane);
+        if (lane < 8) {
+            if (j < 3) p.grad_src_partial[ray * 3 + j] = t;
+            else if (j < 6) p.grad_dir[ray * 3 + j - 3] = t;
+            else if (j == 6 && LOSS == LOSS_MSE && p.loss_partial) p.loss_partial[ray] = t;
+        }
+        return;
+    }
+#endif
     if (POSE_GRAD) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
