@@ -378,7 +378,7 @@ def render_mse_impl(volume: torch.Tensor, bricks: Optional[torch.Tensor], dims: 
     Returns ``(loss (1,), frame or empty, grad_volume or empty, grad_sources or empty,
     grad_directions (P,R,3) or empty)``.  For rays of at most 512 columns, and for rays of 513..2048 columns
     with a pose gradient only (one CTA per ray, one 512-column pass per warp), this is ONE kernel
-    launch (+ two tiny reductions); other long rays first run the forward kernel for the
+    launch (+ one launch for the two small reductions); other long rays first run the forward kernel for the
     512-column segment prefixes.
 
     ``n_total``: number of frame elements of the GLOBAL batch when this call renders one rank's shard of it -- loss and
