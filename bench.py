@@ -536,10 +536,10 @@ def run_ours(args):
                                        "(2 x (8 gathers x 4 B + 4 B)); the fused kernel gathers once and reads the "
                                        "target once, so its own algorithmic traffic is 36 B/sample.  The volume is L2-resident "
                                        "by design (DRAM is ~9 % busy, L2 19 %, L1/texture 46 %): no memory roof is near -- the "
-                                       "kernel is bound by its issue slots (64 % busy at 16 resident warps per SM, 5.50 warp "
+                                       "kernel is bound by its issue slots (65 % busy at 16 resident warps per SM, 5.44 warp "
                                        "instructions per sample) and the latency of its texture gathers, see gather_roof and "
                                        "profiles/r2_fused_kernel_final.md",
-                         "binding_unit": "issue slots / texture-gather latency (ncu: issue active 64 %, long_scoreboard 26 %)",
+                         "binding_unit": "issue slots / texture-gather latency (ncu: issue active 65 %, long_scoreboard 25 %)",
                          "frac_vs_two_pass_bytes": samples_per_step * 72 / (step_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,
             "loss": loss_value,
